@@ -1,0 +1,253 @@
+/*
+ * libswiftgpu - B200-native SPH neighbour-interaction path for SWIFT.
+ *
+ * Public C ABI. Plain C types only (no CUDA, no torch types): this is the file
+ * a SWIFT maintainer includes from runner_main.c / engine.c, or binds through
+ * ctypes/cffi. Every entry point names the reference interface it stands in
+ * for (paths relative to the SWIFT 2026.04 source tree).
+ *
+ * The reference has no run-time plugin interface; hydro schemes are chosen by
+ * #define (src/hydro.h:31-93) and the loops are called from the task switch in
+ * runner_main (src/runner_main.c:214-375). The seam is therefore "one call per
+ * task TYPE over the whole active set" instead of one call per task:
+ *
+ *   task_type_sort                      -> swiftgpu_run_sort
+ *   task_type_{self,pair}/density       -> swiftgpu_run_density
+ *   task_type_ghost                     -> swiftgpu_run_ghost
+ *   task_type_{self,pair}/gradient      -> swiftgpu_run_gradient      (SPHENIX)
+ *   task_type_extra_ghost               -> swiftgpu_run_extra_ghost   (SPHENIX)
+ *   task_type_{self,pair}/force         -> swiftgpu_run_force
+ *   task_type_end_hydro_force           -> swiftgpu_run_end_force
+ *
+ * All functions return 0 on success and non-zero on failure; the library never
+ * calls abort()/exit() (the reference's error() macro, src/error.h:60-80, is the
+ * caller's job). swiftgpu_last_error() returns the message of the last failure.
+ * One handle drives one GPU; calls on one handle must be serialised.
+ */
+#ifndef SWIFTGPU_H
+#define SWIFTGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWIFTGPU_ABI_VERSION 1
+
+/* --with-hydro=minimal|gadget2|sphenix (configure.ac:2233-2300). */
+enum swiftgpu_scheme {
+  SWIFTGPU_SCHEME_MINIMAL = 0,
+  SWIFTGPU_SCHEME_GADGET2 = 1,
+  SWIFTGPU_SCHEME_SPHENIX = 2
+};
+
+/* Task-type bits for swiftgpu_run_step() / the oracle driver. */
+enum swiftgpu_phase {
+  SWIFTGPU_PHASE_SORT = 1 << 0,        /* runner_do_hydro_sort, runner_sort.c:203 */
+  SWIFTGPU_PHASE_DENSITY = 1 << 1,     /* runner_dosub_{self,pair}1_density */
+  SWIFTGPU_PHASE_GHOST = 1 << 2,       /* runner_do_ghost, runner_ghost.c:1113 */
+  SWIFTGPU_PHASE_GRADIENT = 1 << 3,    /* runner_dosub_{self,pair}1_gradient */
+  SWIFTGPU_PHASE_EXTRA_GHOST = 1 << 4, /* runner_do_extra_ghost, runner_ghost.c:1016 */
+  SWIFTGPU_PHASE_FORCE = 1 << 5,       /* runner_dosub_{self,pair}2_force */
+  SWIFTGPU_PHASE_END_FORCE = 1 << 6,   /* runner_do_end_hydro_force, runner_others.c:815 */
+  SWIFTGPU_PHASE_ALL = 0x7f
+};
+
+/*
+ * Byte offsets of the fields of the host's `struct part` (AoS) that the path
+ * reads or writes. The three schemes lay the record out differently
+ * (hydro/Minimal/hydro_part.h:103-232, Gadget2/hydro_part.h:91-236,
+ * SPHENIX/hydro_part.h:105-324) and debugging options change it again, so the
+ * caller passes offsetof() values; -1 marks a field the scheme does not have.
+ * swiftgpu_default_layout() returns the layout of the default build.
+ */
+typedef struct swiftgpu_part_layout {
+  int32_t size; /* sizeof(struct part) */
+  int32_t id, x, v, a_hydro, mass, h;
+  int32_t u, u_dt;             /* Minimal, SPHENIX */
+  int32_t entropy, entropy_dt; /* Gadget2 */
+  int32_t rho;
+  /* union { density; force } */
+  int32_t wcount, wcount_dh, rho_dh, rot_v;
+  int32_t div_v; /* density.div_v (Minimal, Gadget2) or viscosity.div_v (SPHENIX) */
+  int32_t f, pressure /* Minimal, SPHENIX */, P_over_rho2 /* Gadget2 */, soundspeed;
+  int32_t v_sig; /* force.v_sig (Minimal, Gadget2) or viscosity.v_sig (SPHENIX) */
+  int32_t h_dt, balsara;
+  /* SPHENIX only */
+  int32_t div_v_dt, div_v_previous_step, visc_alpha, laplace_u, diff_alpha,
+      alpha_visc_max_ngb;
+  int32_t time_bin, depth_h;
+  int32_t min_ngb_time_bin; /* limiter_data.min_ngb_time_bin */
+} swiftgpu_part_layout;
+
+/*
+ * The scalars the loops read from struct engine / struct space /
+ * struct hydro_props / struct cosmology (SURVEY section 5 "Config" row).
+ */
+typedef struct swiftgpu_config {
+  int32_t abi_version; /* SWIFTGPU_ABI_VERSION */
+  int32_t scheme;      /* enum swiftgpu_scheme */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t periodic;    /* space->periodic */
+  double dim[3];       /* space->dim */
+
+  /* struct hydro_props (hydro_properties.c:60-215) */
+  float eta_neighbours;
+  float h_tolerance;
+  float h_max;
+  float h_min;
+  int32_t max_smoothing_iterations;
+  int32_t use_mass_weighted_num_ngb;
+  float CFL_condition;
+  /* SPHENIX viscosity / diffusion (hydro/SPHENIX/hydro_parameters.h:53-176) */
+  float viscosity_alpha, viscosity_alpha_max, viscosity_alpha_min,
+      viscosity_length;
+  float diffusion_alpha, diffusion_beta, diffusion_alpha_max,
+      diffusion_alpha_min;
+
+  /* domain decomposition: this rank and the number of ranks (engine->nodeID);
+   * cells with nodeID != rank are foreign: read, never updated. */
+  int32_t rank, nranks;
+
+  swiftgpu_part_layout layout;
+} swiftgpu_config;
+
+/* Per-step scalars (struct engine / struct cosmology). */
+typedef struct swiftgpu_step {
+  int64_t ti_current;     /* engine->ti_current */
+  int32_t max_active_bin; /* engine->max_active_bin (active.h:349) */
+  int32_t with_cosmology; /* must be 0 in this version */
+  double time_base;       /* engine->time_base (dt = 2^(bin+1) * time_base... timeline.h:91) */
+  float a, H;             /* cosmology->a, cosmology->H (1, 0 without cosmology) */
+} swiftgpu_step;
+
+/*
+ * One node of the flattened cell tree: the fields of struct cell
+ * (cell.h:372-529) and struct cell_hydro (cell_hydro.h:34-177) the path reads.
+ * Cells are referred to by index into the array passed to
+ * swiftgpu_upload_cells(); -1 = NULL. Particles of a cell are the contiguous
+ * range [first_part, first_part+count) of the particle array and a split
+ * cell's progeny partition that range in progeny order, exactly like
+ * c->hydro.parts in the reference.
+ */
+typedef struct swiftgpu_cell {
+  double loc[3];
+  double width[3];
+  float dmin;
+  float h_min_allowed;
+  float h_max_allowed;
+  float h_max;        /* hydro.h_max */
+  float h_max_active; /* hydro.h_max_active */
+  float h_max_old;    /* hydro.h_max_old */
+  float dx_max_part;
+  float dx_max_part_old;
+  float dx_max_sort;
+  float dx_max_sort_old;
+  int32_t depth;
+  int32_t split;
+  int32_t parent;
+  int32_t progeny[8];
+  int32_t nodeID;
+  int32_t top; /* index of the top-level ancestor (itself for depth 0) */
+  int64_t first_part;
+  int32_t count;
+  int32_t pad_;
+  int64_t ti_end_min; /* hydro.ti_end_min: cell active iff == ti_current */
+} swiftgpu_cell;
+
+typedef struct swiftgpu_handle swiftgpu_t;
+
+/* Timing / counters of the last swiftgpu_run_* calls (device time, CUDA events). */
+typedef struct swiftgpu_stats {
+  double ms_sort, ms_density, ms_ghost, ms_gradient, ms_extra_ghost, ms_force,
+      ms_end_force;
+  int64_t n_density;  /* directed density interactions (runner_iact_nonsym_density calls) */
+  int64_t n_gradient; /* directed gradient interactions */
+  int64_t n_force;    /* directed force interactions */
+  int64_t n_launches; /* kernel launches by the library */
+  int32_t ghost_iterations;
+  int32_t ghost_unconverged;
+} swiftgpu_stats;
+
+/* Fills `out` with the struct part layout of the reference's default build of
+ * `scheme` (no debugging options, *_NONE sub-grid models). */
+int swiftgpu_default_layout(int scheme, swiftgpu_part_layout *out);
+
+/* Fills cfg with the defaults of hydro_props_init (hydro_properties.c:41-48,
+ * hydro/SPHENIX/hydro_parameters.h:53-101) and the default layout. */
+int swiftgpu_default_config(int scheme, swiftgpu_config *cfg);
+
+/* Creates a handle bound to cfg->device. Stands in for the scheme selection
+ * done at configure time + hydro_props_init + the engine fields of
+ * tests/test125cells.c:570-610. */
+int swiftgpu_init(swiftgpu_t **h, const swiftgpu_config *cfg);
+void swiftgpu_destroy(swiftgpu_t *h);
+const char *swiftgpu_last_error(const swiftgpu_t *h);
+
+/* Upload the flattened tree (space->cells_top + progeny, cell.h:372). `top`
+ * lists the indices of the top-level cells in space->cells_top order. */
+int swiftgpu_upload_cells(swiftgpu_t *h, const swiftgpu_cell *cells,
+                          int32_t ncells, const int32_t *top, int32_t ntop);
+
+/* Upload space->parts: raw AoS `struct part[nparts]` in the layout given at
+ * init. A device kernel transposes it to the SoA columns the loops read. */
+int swiftgpu_upload_parts(swiftgpu_t *h, const void *parts_aos, int64_t nparts);
+
+/* Same with the AoS array already resident in device memory (bench "value"). */
+int swiftgpu_upload_parts_device(swiftgpu_t *h, const void *d_parts_aos,
+                                 int64_t nparts);
+
+int swiftgpu_set_step(swiftgpu_t *h, const swiftgpu_step *step);
+
+/* runner_do_hydro_sort (runner.h:107) for every cell and every sid the
+ * density/force work lists need. */
+int swiftgpu_run_sort(swiftgpu_t *h);
+/* hydro_init_part (as cell_drift_part does for active parts, cell_drift.c:361)
+ * + runner_dosub_self1_density / runner_dosub_pair1_density
+ * (runner_doiact_hydro.h:187,192) over all top-level selfs and pairs. */
+int swiftgpu_run_density(swiftgpu_t *h);
+/* runner_do_ghost (runner.h:96) for every top-level cell, including the
+ * subset re-runs of the density loop for unconverged particles. Returns
+ * non-zero if particles remain unconverged after max_smoothing_iterations
+ * (runner_ghost.c:1583-1593). */
+int swiftgpu_run_ghost(swiftgpu_t *h);
+/* runner_dosub_{self,pair}1_gradient; no-op for Minimal and Gadget2. */
+int swiftgpu_run_gradient(swiftgpu_t *h);
+/* runner_do_extra_ghost (runner.h:98); no-op for Minimal and Gadget2. */
+int swiftgpu_run_extra_ghost(swiftgpu_t *h);
+/* runner_dosub_self2_force / runner_dosub_pair2_force (runner_doiact_hydro.h:189,194). */
+int swiftgpu_run_force(swiftgpu_t *h);
+/* runner_do_end_hydro_force (runner_others.c:815). */
+int swiftgpu_run_end_force(swiftgpu_t *h);
+/* Convenience: the phases of `mask` in dependency order
+ * (engine_maketasks.c:2541-2583). */
+int swiftgpu_run_step(swiftgpu_t *h, uint32_t phase_mask);
+
+/* Scatter the device columns back into the host AoS array (the fields valid
+ * after the last phase run: struct part's density/force union). */
+int swiftgpu_download_parts(swiftgpu_t *h, void *parts_aos, int64_t nparts);
+int swiftgpu_download_parts_device(swiftgpu_t *h, void *d_parts_aos,
+                                   int64_t nparts);
+/* Per-cell h_max / h_max_active after the ghost (runner_ghost.c:1621-1632). */
+int swiftgpu_download_cells(swiftgpu_t *h, swiftgpu_cell *cells, int32_t ncells);
+/* Per-particle directed interaction counts of the last density / gradient /
+ * force loops (the reference's N_density/N_gradient/N_force debugging counters,
+ * hydro/SPHENIX/hydro_iact.h:121-126, minus the self term). Any pointer may be
+ * NULL. */
+int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density,
+                             int32_t *n_gradient, int32_t *n_force,
+                             int64_t nparts);
+int swiftgpu_get_stats(swiftgpu_t *h, swiftgpu_stats *out);
+
+/* Multi-GPU halo exchange (replaces send/recv xv, rho, gradient tasks,
+ * scheduler.c:977-988,1088-1112). `nccl_comm` is an ncclComm_t created by the
+ * caller (one rank per GPU); phase: 0 = xv, 1 = rho, 2 = gradient. */
+int swiftgpu_halo_setup(swiftgpu_t *h, void *nccl_comm);
+int swiftgpu_halo_exchange(swiftgpu_t *h, int phase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIFTGPU_H */
