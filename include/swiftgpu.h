@@ -150,10 +150,9 @@ typedef struct swiftgpu_cell {
   int32_t parent;
   int32_t progeny[8];
   int32_t nodeID;
-  int32_t top; /* index of the top-level ancestor (itself for depth 0) */
-  int64_t first_part;
-  int32_t count;
-  int32_t pad_;
+  int32_t top;   /* index of the top-level ancestor (itself for depth 0) */
+  int32_t count; /* hydro.count */
+  int64_t first_part; /* hydro.parts - space->parts */
   int64_t ti_end_min; /* hydro.ti_end_min: cell active iff == ti_current */
 } swiftgpu_cell;
 

@@ -1,0 +1,230 @@
+"""Host-side harness around the C ABI: synthetic initial conditions, the cell
+tree (libswiftgpu_host.so, mirrors space_regrid/space_split) and AoS packing.
+
+In a real deployment SWIFT owns all of this (struct space); the harness exists
+for the tests and the benchmark only.
+"""
+import ctypes as C
+import math
+import numpy as np
+
+from . import abi
+
+KERNEL_GAMMA = np.float32(1.825742)          # kernel_hydro.h:52
+HYDRO_GAMMA = 5.0 / 3.0                       # adiabatic_index.h:43
+
+
+_FIELD_TYPES = {"id": ("<i8", ()), "x": ("<f8", (3,)), "v": ("<f4", (3,)),
+                "a_hydro": ("<f4", (3,)), "rot_v": ("<f4", (3,)),
+                "time_bin": ("i1", ()), "depth_h": ("i1", ()),
+                "min_ngb_time_bin": ("i1", ())}
+
+
+def field(parts_u8, layout, name):
+    """Strided numpy view of one field of the AoS `struct part` byte array."""
+    L = layout.as_dict() if hasattr(layout, "as_dict") else dict(layout)
+    off, size = L[name], L["size"]
+    if off < 0:
+        raise KeyError(f"field {name} not present in this scheme's struct part")
+    fmt, shape = _FIELD_TYPES.get(name, ("<f4", ()))
+    dt = np.dtype(fmt)
+    n = parts_u8.size // size
+    strides = (size,) + tuple(dt.itemsize for _ in shape)
+    return np.ndarray(shape=(n,) + shape, dtype=dt, buffer=parts_u8, offset=off, strides=strides)
+
+
+def has_field(layout, name):
+    L = layout.as_dict() if hasattr(layout, "as_dict") else dict(layout)
+    return L.get(name, -1) >= 0
+
+
+class Tree:
+    def __init__(self, cells, top, perm, depth_h):
+        self.cells, self.top, self.perm, self.depth_h = cells, top, perm, depth_h
+
+
+def build_tree(x, h, time_bin, dim, cdim, max_active_bin, ti_current,
+               splitsize=400, rank_grid=(1, 1, 1)):
+    """space_regrid + space_split equivalent. Returns Tree; tree.perm[new]=old."""
+    host = abi.load_host()
+    n = x.shape[0]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    h = np.ascontiguousarray(h, dtype=np.float32)
+    tb = np.ascontiguousarray(time_bin, dtype=np.int8)
+    perm = np.empty(n, dtype=np.int64)
+    depth_h = np.empty(n, dtype=np.int8)
+    dim_a = (C.c_double * 3)(*dim)
+    cdim_a = (C.c_int * 3)(*cdim)
+    rg = (C.c_int * 3)(*rank_grid)
+    t = host.swifthost_build_tree(x.ctypes.data, h.ctypes.data, tb.ctypes.data, n,
+                                  C.addressof(dim_a), C.addressof(cdim_a), splitsize,
+                                  max_active_bin, ti_current, C.addressof(rg),
+                                  perm.ctypes.data, depth_h.ctypes.data)
+    nc, nt = host.swifthost_tree_ncells(t), host.swifthost_tree_ntop(t)
+    cells = np.zeros(nc, dtype=abi.cell_dtype())
+    top = np.zeros(nt, dtype=np.int32)
+    host.swifthost_tree_copy(t, cells.ctypes.data, top.ctypes.data)
+    host.swifthost_tree_free(t)
+    assert cells.dtype.itemsize == C.sizeof(abi.Cell)
+    return Tree(cells, top, perm, depth_h)
+
+
+def pack_parts(layout, scheme, tree, ic):
+    """AoS struct part[] in cell order (what space->parts holds)."""
+    host = abi.load_host()
+    n = ic["x"].shape[0]
+    out = np.zeros(n * layout.size, dtype=np.uint8)
+
+    def p(a, dt):
+        if a is None:
+            return None, None
+        a = np.ascontiguousarray(a, dtype=dt)
+        return a, a.ctypes.data
+    keep = []
+    args = []
+    for key, dt in (("x", np.float64), ("v", np.float32), ("mass", np.float32),
+                    ("h", np.float32), ("u", np.float32), ("id", np.int64),
+                    ("time_bin", np.int8)):
+        a, ptr = p(ic.get(key), dt); keep.append(a); args.append(ptr)
+    a, ptr = p(tree.depth_h, np.int8); keep.append(a); args.append(ptr)
+    for key in ("visc_alpha", "diff_alpha", "div_v_previous_step", "rho"):
+        a, ptr = p(ic.get(key), np.float32); keep.append(a); args.append(ptr)
+    perm = np.ascontiguousarray(tree.perm)
+    host.swifthost_pack_parts(C.byref(layout), scheme, n, perm.ctypes.data, *args, out.ctypes.data)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# Synthetic initial conditions. Everything f32 except positions.
+# `u` holds the thermal variable of the scheme: internal energy (Minimal,
+# SPHENIX) or entropic function A = P / rho^gamma (Gadget2).
+# ---------------------------------------------------------------------------
+
+def _finish(ic, scheme, n, time_bin=None):
+    ic["id"] = np.arange(1, n + 1, dtype=np.int64)
+    ic["time_bin"] = np.full(n, 1, dtype=np.int8) if time_bin is None else time_bin.astype(np.int8)
+    if scheme == abi.SCHEME_GADGET2:
+        # gas_entropy_from_internal_energy (ideal_gas/equation_of_state.h)
+        rho0 = ic["_rho0"]
+        ic["u"] = ((HYDRO_GAMMA - 1.0) * ic["u"].astype(np.float64) * rho0 ** (1.0 - HYDRO_GAMMA)).astype(np.float32)
+    if scheme == abi.SCHEME_SPHENIX:
+        # hydro_first_init_part + hydro_convert_quantities (SPHENIX/hydro.h:1163-1226)
+        ic["visc_alpha"] = np.full(n, 0.1, dtype=np.float32)
+        ic["diff_alpha"] = np.zeros(n, dtype=np.float32)
+        ic["div_v_previous_step"] = np.zeros(n, dtype=np.float32)
+    return ic
+
+
+def uniform_box(L=32, scheme=abi.SCHEME_MINIMAL, rho=2.0, P=1.0, eta=1.2349, box=1.0):
+    """examples/HydroTests/UniformBox_3D/makeIC.py:28-105: lattice at cell
+    centres, rho=2, P=1, v=0, h = eta * spacing."""
+    n = L ** 3
+    g = (np.arange(L) + 0.5) / L * box
+    x = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(n, 3)
+    ic = {"x": x, "v": np.zeros((n, 3), np.float32),
+          "mass": np.full(n, rho * box ** 3 / n, np.float32),
+          "h": np.full(n, eta * box / L, np.float32),
+          "u": np.full(n, P / ((HYDRO_GAMMA - 1.0) * rho), np.float32), "_rho0": rho}
+    return _finish(ic, scheme, n)
+
+
+def jittered_box(L, scheme, jitter=0.2, seed=42, eta=1.2348, box=1.0, rho=1.0,
+                 u0=1.0, vamp=0.05, h_scatter=0.0, active_fraction=1.0):
+    """Lattice + uniform jitter (+-jitter spacing); smooth solenoidal-ish
+    velocity field; optionally scattered h (to exercise the ghost) and a
+    multi-time-step active subset clustered in space."""
+    rng = np.random.default_rng(seed)
+    n = L ** 3
+    g = (np.arange(L) + 0.5) / L
+    x = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(n, 3)
+    x = x + rng.uniform(-jitter, jitter, size=(n, 3)) / L
+    x = np.mod(x, 1.0) * box
+    k = 2 * np.pi / box
+    v = np.stack([np.sin(k * x[:, 1]) + 0.5 * np.cos(2 * k * x[:, 2]),
+                  np.sin(k * x[:, 2]) + 0.5 * np.cos(2 * k * x[:, 0]),
+                  np.sin(k * x[:, 0]) + 0.5 * np.cos(2 * k * x[:, 1])], axis=1) * vamp
+    h = np.full(n, eta * box / L)
+    if h_scatter > 0:
+        h = h * np.exp(rng.uniform(-h_scatter, h_scatter, size=n))
+    u = u0 * (1.0 + 0.1 * np.sin(k * x[:, 0]) * np.cos(k * x[:, 1]))
+    ic = {"x": x, "v": v.astype(np.float32), "mass": np.full(n, rho * box ** 3 / n, np.float32),
+          "h": h.astype(np.float32), "u": u.astype(np.float32), "_rho0": rho}
+    tb = None
+    if active_fraction < 1.0:
+        # active fraction clustered in space: a smooth field picks the region
+        f = np.sin(k * x[:, 0]) * np.sin(k * x[:, 1]) * np.sin(k * x[:, 2])
+        thr = np.quantile(f, 1.0 - active_fraction)
+        tb = np.where(f >= thr, 1, 3)
+    return _finish(ic, scheme, n, tb)
+
+
+def sedov_box(L=128, scheme=abi.SCHEME_GADGET2, seed=1234, eta=1.2348, E0=1.0, P0=1e-6, rho0=1.0):
+    """SedovBlast_3D/makeIC.py:24-58 on a perturbed lattice: E0 shared by the
+    15 particles nearest the centre."""
+    ic = jittered_box(L, abi.SCHEME_MINIMAL, jitter=0.1, seed=seed, eta=eta, rho=rho0, vamp=0.0)
+    n = L ** 3
+    u = np.full(n, P0 / ((HYDRO_GAMMA - 1.0) * rho0))
+    r2 = ((ic["x"] - 0.5) ** 2).sum(axis=1)
+    centre = np.argsort(r2)[:15]
+    u[centre] = E0 / (15 * ic["mass"][0])
+    ic["u"] = u.astype(np.float32)
+    ic["v"][:] = 0
+    ic["_rho0"] = rho0
+    for k in ("visc_alpha", "diff_alpha", "div_v_previous_step"):
+        ic.pop(k, None)
+    return _finish(ic, scheme, n)
+
+
+def clustered_box(L=256, scheme=abi.SCHEME_SPHENIX, seed=2025, sigma=1.5, eta=1.2348):
+    """Lognormal-clustered box: lattice displaced along the gradient of a
+    Gaussian random potential (P(k) ~ k^-2 density field, sigma_ln(rho) ~ sigma);
+    h from the local density estimate, deliberately imperfect so the ghost has
+    to iterate."""
+    rng = np.random.default_rng(seed)
+    n = L ** 3
+    ng = min(L, 64)
+    kf = np.fft.fftfreq(ng) * ng
+    kx, ky, kz = np.meshgrid(kf, kf, np.fft.rfftfreq(ng) * ng, indexing="ij")
+    k2 = kx ** 2 + ky ** 2 + kz ** 2
+    k2[0, 0, 0] = 1.0
+    delta_k = (rng.normal(size=k2.shape) + 1j * rng.normal(size=k2.shape)) / k2 ** 0.5
+    delta_k[0, 0, 0] = 0
+    delta_k *= np.exp(-k2 / (0.25 * ng) ** 2)
+    delta = np.fft.irfftn(delta_k, s=(ng, ng, ng))
+    delta *= sigma / delta.std()
+    # displacement field psi = -grad(phi), lap(phi) = delta
+    psi = [np.fft.irfftn(-1j * kk * delta_k / k2, s=(ng, ng, ng)) for kk in (kx, ky, kz)]
+    scale = sigma / (np.fft.irfftn(delta_k, s=(ng, ng, ng)).std() + 1e-30)
+    g = (np.arange(L) + 0.5) / L
+    x = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(n, 3)
+    gi = np.minimum((x * ng).astype(np.int64), ng - 1)
+    disp = np.stack([p[gi[:, 0], gi[:, 1], gi[:, 2]] for p in psi], axis=1) * scale
+    disp *= 0.35 / (2 * np.pi)   # keep shell crossing mild
+    x = np.mod(x + disp + rng.uniform(-0.2, 0.2, size=(n, 3)) / L, 1.0)
+    # local density from a CIC-like count on a grid of ~8 particles per cell
+    nb = max(L // 2, 4)
+    bi = np.minimum((x * nb).astype(np.int64), nb - 1)
+    cnt = np.zeros((nb, nb, nb))
+    np.add.at(cnt, (bi[:, 0], bi[:, 1], bi[:, 2]), 1.0)
+    dens = np.maximum(cnt[bi[:, 0], bi[:, 1], bi[:, 2]], 1.0) * nb ** 3 / n
+    h = eta / L * dens ** (-1.0 / 3.0) * np.exp(rng.uniform(-0.15, 0.15, size=n))
+    k = 2 * np.pi
+    v = 0.05 * np.stack([np.sin(k * x[:, 1]), np.sin(k * x[:, 2]), np.sin(k * x[:, 0])], axis=1)
+    ic = {"x": x, "v": v.astype(np.float32), "mass": np.full(n, 1.0 / n, np.float32),
+          "h": h.astype(np.float32), "u": np.ones(n, np.float32), "_rho0": 1.0}
+    return _finish(ic, scheme, n)
+
+
+def default_top_grid(L, max_top=32):
+    """Top-level grid: cells at least 2*gamma*h*space_stretch wide
+    (space_regrid.c:50-127) and at least 3 per axis; prefer ~4096 parts/cell."""
+    c = max(3, min(max_top, L // 16))
+    return (c, c, c)
+
+
+def step_scalars(max_active_bin=56):
+    """ti_current such that exactly the bins <= max_active_bin end their step
+    now (timeline.h:126): an odd multiple of 2^(bin+1)."""
+    if max_active_bin >= 56:
+        return dict(ti_current=8, max_active_bin=56, time_base=1e-6)
+    return dict(ti_current=3 * (1 << (max_active_bin + 1)), max_active_bin=max_active_bin, time_base=1e-6)
