@@ -1,0 +1,1500 @@
+/*
+ * swiftgpu.cu - libswiftgpu: C ABI (include/swiftgpu.h), device state and the
+ * per-particle kernels (AoS<->SoA transposes, 13-axis sort, ghost, extra ghost,
+ * end force). The neighbour loops live in loops.cuh.
+ *
+ * Device state is SoA, particles in the host's cell order (every cell is a
+ * contiguous index range, progeny partition their parent's range):
+ *   x[3n] f64 | mv[n] f32x4 (m,vx,vy,vz) | h,u,rho f32 | time_bin,depth_h i8
+ *   density sums dA (rho,rho_dh,wcount,wcount_dh), dB (div_v,rot_v)
+ *   loop inputs  fq1 (rho,P,f,cs), fq2 (balsara,h,u,time_bin), fq3 (alpha,alpha_diff)
+ *   force sums   fo1 (a_hydro,u_dt|entropy_dt), h_dt, v_sig, min_ngb_time_bin
+ * No CPU fallback exists: every entry point runs CUDA kernels or fails.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/swiftgpu.h"
+#include "loops.cuh"
+
+using namespace swiftgpu;
+
+#define CK(call)                                                                   \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess)                                                         \
+      return h->fail("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+/* ======================================================================== */
+/* Device-side worklist of one loop family                                   */
+/* ======================================================================== */
+struct DevList {
+  Item *items = nullptr;
+  Group *groups = nullptr;
+  int32_t *task_group = nullptr, *task_chunk = nullptr;
+  int32_t *tgt_first = nullptr, *tgt_count = nullptr, *tgt_list = nullptr;
+  int ngroups = 0, ntasks = 0;
+  size_t nitems = 0;
+  int64_t tgt_total = 0;
+  void release() {
+    cudaFree(items); cudaFree(groups); cudaFree(task_group); cudaFree(task_chunk);
+    cudaFree(tgt_first); cudaFree(tgt_count); cudaFree(tgt_list);
+    items = nullptr; groups = nullptr; task_group = task_chunk = nullptr;
+    tgt_first = tgt_count = tgt_list = nullptr;
+    ngroups = ntasks = 0; nitems = 0; tgt_total = 0;
+  }
+};
+
+struct SortSeg {
+  int32_t cell;
+  int32_t sid;
+  int64_t off;
+};
+
+struct swiftgpu_handle {
+  swiftgpu_config cfg;
+  swiftgpu_step step;
+  std::string err;
+  int has_step = 0;
+
+  std::vector<swiftgpu_cell> cells;
+  std::vector<float> up_hmax, up_hmax_active; /* values as uploaded */
+  float cells_uploaded_hmax(int c) const { return up_hmax[c]; }
+  float cells_uploaded_hmax_active(int c) const { return up_hmax_active[c]; }
+  std::vector<int32_t> top;
+  std::vector<uint8_t> force_bits; /* recursion predicate bits the force list was built with */
+  int64_t n = 0;
+  int ncells = 0;
+
+  /* device */
+  DevCell *d_cells = nullptr;
+  DevCell *d_cells_init = nullptr; /* pristine copy: the ghost raises h_max in d_cells */
+  float *d_dmin = nullptr, *d_dxp = nullptr;
+  std::vector<uint64_t> req_density, req_subset; /* sort requests of the static lists */
+  char *d_aos = nullptr;
+  size_t aos_bytes = 0;
+  double *x = nullptr;
+  float4 *mv = nullptr, *dA = nullptr, *dB = nullptr, *fq1 = nullptr, *fq2 = nullptr, *fq3 = nullptr,
+         *fo1 = nullptr;
+  float *hh = nullptr, *u = nullptr, *rho = nullptr, *f_hdt = nullptr, *f_vsig = nullptr,
+        *g_vsig = nullptr, *g_lap = nullptr, *g_amax = nullptr, *alpha = nullptr,
+        *alpha_diff = nullptr, *div_v_prev = nullptr, *div_v_dt = nullptr, *div_v = nullptr,
+        *gleft = nullptr, *gright = nullptr;
+  int8_t *time_bin = nullptr, *depth_h = nullptr;
+  int32_t *f_minngb = nullptr, *nd = nullptr, *ng = nullptr, *nf = nullptr;
+  uint32_t *sort_idx = nullptr;
+  int64_t sort_total = 0;
+  SortSeg *d_segs = nullptr;
+  int nsegs = 0;
+  unsigned long long *d_counters = nullptr; /* [0] density [1] gradient [2] force [3] redo */
+  int32_t *d_flag = nullptr;
+  uint8_t *d_force_bits = nullptr;
+
+  DevList L_density, L_subset, L_force;
+  bool lists_built = false;
+  bool sorted = false;
+  uint32_t phases_done = 0;
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  swiftgpu_stats stats;
+
+  int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return 1;
+  }
+};
+typedef swiftgpu_handle H;
+
+static thread_local std::string g_err;
+
+/* ======================================================================== */
+/* Kernels: AoS <-> SoA                                                      */
+/* ======================================================================== */
+struct DevLayout {
+  swiftgpu_part_layout L;
+  int scheme;
+};
+
+template <typename T>
+__device__ __forceinline__ T rd(const char *p, int off) {
+  return *(const T *)(p + off);
+}
+template <typename T>
+__device__ __forceinline__ void wr(char *p, int off, T v) {
+  *(T *)(p + off) = v;
+}
+
+struct Soa {
+  double *x;
+  float4 *mv, *dA, *dB, *fq1, *fq2, *fq3, *fo1;
+  float *h, *u, *rho, *f_hdt, *f_vsig, *g_vsig, *g_lap, *g_amax, *alpha, *alpha_diff, *div_v_prev,
+      *div_v_dt, *div_v;
+  int8_t *time_bin, *depth_h;
+  int32_t *f_minngb;
+};
+
+__global__ void k_aos_to_soa(const char *aos, DevLayout D, Soa S, int64_t n) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const swiftgpu_part_layout &L = D.L;
+  const char *b = aos + (size_t)L.size * p;
+  S.x[3 * p + 0] = rd<double>(b, L.x);
+  S.x[3 * p + 1] = rd<double>(b, L.x + 8);
+  S.x[3 * p + 2] = rd<double>(b, L.x + 16);
+  const float m = rd<float>(b, L.mass);
+  S.mv[p] = make_float4(m, rd<float>(b, L.v), rd<float>(b, L.v + 4), rd<float>(b, L.v + 8));
+  const float h = rd<float>(b, L.h);
+  S.h[p] = h;
+  const float u = rd<float>(b, D.scheme == SCH_GADGET2 ? L.entropy : L.u);
+  S.u[p] = u;
+  const float rho = rd<float>(b, L.rho);
+  S.rho[p] = rho;
+  const int8_t tb = rd<int8_t>(b, L.time_bin);
+  S.time_bin[p] = tb;
+  S.depth_h[p] = rd<int8_t>(b, L.depth_h);
+  /* The density/force union holds the force members of the last step the
+   * particle was active in: they are what inactive neighbours contribute. */
+  const float P = rd<float>(b, D.scheme == SCH_GADGET2 ? L.P_over_rho2 : L.pressure);
+  S.fq1[p] = make_float4(rho, P, rd<float>(b, L.f), rd<float>(b, L.soundspeed));
+  S.fq2[p] = make_float4(rd<float>(b, L.balsara), h, u, __int_as_float((int)tb));
+  S.f_hdt[p] = rd<float>(b, L.h_dt);
+  S.f_vsig[p] = rd<float>(b, L.v_sig);
+  S.f_minngb[p] = rd<int8_t>(b, L.min_ngb_time_bin);
+  S.fo1[p] = make_float4(rd<float>(b, L.a_hydro), rd<float>(b, L.a_hydro + 4),
+                         rd<float>(b, L.a_hydro + 8),
+                         rd<float>(b, D.scheme == SCH_GADGET2 ? L.entropy_dt : L.u_dt));
+  if (D.scheme == SCH_SPHENIX) {
+    const float al = rd<float>(b, L.visc_alpha), ad = rd<float>(b, L.diff_alpha);
+    S.alpha[p] = al;
+    S.alpha_diff[p] = ad;
+    S.fq3[p] = make_float4(al, ad, 0.f, 0.f);
+    S.div_v_prev[p] = rd<float>(b, L.div_v_previous_step);
+    S.div_v_dt[p] = rd<float>(b, L.div_v_dt);
+    S.div_v[p] = rd<float>(b, L.div_v);
+    S.g_vsig[p] = rd<float>(b, L.v_sig);
+    S.g_lap[p] = rd<float>(b, L.laplace_u);
+    S.g_amax[p] = rd<float>(b, L.alpha_visc_max_ngb);
+  }
+}
+
+/* Writes back the fields the phases run so far have made valid, for ACTIVE
+ * particles only (inactive particles are read-only on this path). */
+__global__ void k_soa_to_aos(char *aos, DevLayout D, Soa S, int64_t n, int max_active_bin,
+                             int density_only) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (S.time_bin[p] > max_active_bin) return;
+  const swiftgpu_part_layout &L = D.L;
+  char *b = aos + (size_t)L.size * p;
+  wr<float>(b, L.h, S.h[p]);
+  wr<int8_t>(b, L.depth_h, S.depth_h[p]);
+  const float4 a = S.dA[p], c = S.dB[p];
+  if (density_only) {
+    wr<float>(b, L.rho, a.x);
+    wr<float>(b, L.rho_dh, a.y);
+    wr<float>(b, L.wcount, a.z);
+    wr<float>(b, L.wcount_dh, a.w);
+    wr<float>(b, L.div_v, c.x);
+    wr<float>(b, L.rot_v, c.y);
+    wr<float>(b, L.rot_v + 4, c.z);
+    wr<float>(b, L.rot_v + 8, c.w);
+    return;
+  }
+  const float4 q1 = S.fq1[p], q2 = S.fq2[p], o = S.fo1[p];
+  wr<float>(b, L.rho, q1.x);
+  wr<float>(b, D.scheme == SCH_GADGET2 ? L.P_over_rho2 : L.pressure, q1.y);
+  wr<float>(b, L.f, q1.z);
+  wr<float>(b, L.soundspeed, q1.w);
+  wr<float>(b, L.balsara, q2.x);
+  wr<float>(b, L.h_dt, S.f_hdt[p]);
+  wr<float>(b, L.a_hydro, o.x);
+  wr<float>(b, L.a_hydro + 4, o.y);
+  wr<float>(b, L.a_hydro + 8, o.z);
+  wr<float>(b, D.scheme == SCH_GADGET2 ? L.entropy_dt : L.u_dt, o.w);
+  wr<int8_t>(b, L.min_ngb_time_bin, (int8_t)S.f_minngb[p]);
+  if (D.scheme == SCH_SPHENIX) {
+    wr<float>(b, L.div_v, S.div_v[p]);
+    wr<float>(b, L.v_sig, S.g_vsig[p]);
+    wr<float>(b, L.laplace_u, S.g_lap[p]);
+    wr<float>(b, L.alpha_visc_max_ngb, S.g_amax[p]);
+    wr<float>(b, L.visc_alpha, S.alpha[p]);
+    wr<float>(b, L.diff_alpha, S.alpha_diff[p]);
+    wr<float>(b, L.div_v_previous_step, S.div_v_prev[p]);
+    wr<float>(b, L.div_v_dt, S.div_v_dt[p]);
+  } else {
+    wr<float>(b, L.v_sig, S.f_vsig[p]);
+  }
+}
+
+/* ======================================================================== */
+/* Kernel: 13-axis sort (runner_do_hydro_sort, runner_sort.c:203)            */
+/* One CTA per (cell, sid) segment. Keys are (float)(x . runner_shift[sid])  */
+/* of absolute double positions (:411-413); the order of equal keys is       */
+/* irrelevant to the neighbour sets. All-ascending bitonic network with      */
+/* virtual +inf padding.                                                     */
+/* ======================================================================== */
+#define SORT_SMEM_MAX 2048
+__global__ void __launch_bounds__(256)
+    k_sort(const SortSeg *segs, const DevCell *cells, const double *x, uint32_t *sort_idx,
+           float *gkeys /* scratch for segments larger than SORT_SMEM_MAX, may be null */) {
+  __shared__ float skey[SORT_SMEM_MAX];
+  __shared__ uint32_t sidx[SORT_SMEM_MAX];
+  const SortSeg seg = segs[blockIdx.x];
+  const DevCell c = cells[seg.cell];
+  const int n = c.count;
+  uint32_t *out = sort_idx + seg.off;
+  int N = 1;
+  while (N < n) N <<= 1;
+  const bool in_smem = n <= SORT_SMEM_MAX;
+  float *keys = in_smem ? skey : gkeys + seg.off;
+  uint32_t *idx = in_smem ? sidx : out;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const size_t p = (size_t)c.first + i;
+    keys[i] = sort_key(x[3 * p], x[3 * p + 1], x[3 * p + 2], seg.sid);
+    idx[i] = (uint32_t)i;
+  }
+  __syncthreads();
+  for (int size = 2; size <= N; size <<= 1) {
+    for (int stride = size >> 1, first = 1; stride > 0; stride >>= 1, first = 0) {
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int j = first ? (i ^ (size - 1)) : (i ^ stride);
+        if (j > i && j < n) {
+          const float ki = keys[i], kj = keys[j];
+          if (kj < ki) {
+            keys[i] = kj;
+            keys[j] = ki;
+            const uint32_t t = idx[i];
+            idx[i] = idx[j];
+            idx[j] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (in_smem)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = sidx[i];
+}
+
+/* ======================================================================== */
+/* Kernel: target lists (active particles of each group's cell)              */
+/* ======================================================================== */
+__global__ void k_build_targets(const Group *groups, int ngroups, const DevCell *cells,
+                                const int8_t *time_bin, int max_active_bin, const int32_t *tgt_first,
+                                int32_t *tgt_count, int32_t *tgt_list) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= ngroups) return;
+  const DevCell c = cells[groups[g].tcell];
+  int32_t *out = tgt_list + tgt_first[g];
+  int nout = 0;
+  for (int base = 0; base < c.count; base += 32) {
+    const int k = base + lane;
+    const bool act = (k < c.count) && (time_bin[c.first + k] <= max_active_bin);
+    const unsigned m = __ballot_sync(FULL_MASK, act);
+    if (act) out[nout + __popc(m & ((1u << lane) - 1u))] = c.first + k;
+    nout += __popc(m);
+  }
+  if (lane == 0) tgt_count[g] = nout;
+}
+
+/* ======================================================================== */
+/* Per-particle finalisers                                                   */
+/* ======================================================================== */
+struct GhostArgs {
+  const Group *groups; /* subset groups: one per active local leaf */
+  int ngroups;
+  DevCell *cells;
+  int32_t *redo_list;  /* L_subset.tgt_list, indexed by particle slot */
+  int32_t *redo_count; /* L_subset.tgt_count */
+  Soa S;
+  float *left, *right;
+  int32_t *nd, *ng, *nf;
+  unsigned long long *n_redo;
+  int first_pass;
+  int max_active_bin;
+  float h_max, h_min, eps, eta_dim;
+  int use_mass_weighted;
+  float visc_alpha; /* hydro_props->viscosity.alpha (Minimal/Gadget2 Balsara prefactor) */
+  float H, a;
+  float num_reruns;
+};
+
+/* cell_set_part_h_depth, cell.h:1787-1815 */
+__device__ __forceinline__ int part_h_depth(const DevCell *cells, int leaf, float h, int current) {
+  const DevCell *c = &cells[leaf];
+  if (h < c->h_min_allowed) return c->depth;
+  int ci = leaf;
+  while (ci >= 0) {
+    c = &cells[ci];
+    if (h >= c->h_min_allowed && h < c->h_max_allowed) return c->depth;
+    ci = c->parent;
+  }
+  return current;
+}
+
+/* hydro_prepare_force + hydro_reset_acceleration (Minimal hydro.h:669-766,
+ * Gadget2 hydro.h:648-744) or hydro_prepare_gradient + hydro_reset_gradient
+ * (SPHENIX hydro.h:671-755), from the finished density sums. */
+template <int SCHEME>
+__device__ __forceinline__ void ghost_finalise(const GhostArgs &G, int p, float h, float rho,
+                                               float rho_dh, float wcount, float wcount_dh,
+                                               float div_v, float rx, float ry, float rz) {
+  const Soa &S = G.S;
+  const float u = S.u[p];
+  const int tb = S.time_bin[p];
+  const float curl_v = sqrtf(rx * rx + ry * ry + rz * rz);
+  float f, P, cs, balsara;
+  if (SCHEME == SCH_GADGET2) {
+    const float rho_inv = 1.f / rho;
+    const float h_inv = 1.f / h;
+    const float abs_div = fabsf(div_v + HYDRO_DIMENSION * G.H);
+    const float cb = cbrtf(rho);
+    const float pressure = u * (cb * cb * rho); /* entropy * pow_gamma(rho) */
+    cs = sqrtf(HYDRO_GAMMA * pressure / rho);
+    P = pressure * rho_inv * rho_inv;
+    balsara = G.visc_alpha * abs_div / (abs_div + curl_v + 0.0001f * cs * h_inv);
+    float rdh = rho_dh;
+    if (h > 0.9999f * G.h_max) rdh = 0.f;
+    const float grad_rho_term = HYDRO_DIMENSION_INV * h * rdh * rho_inv;
+    f = (grad_rho_term < -0.9999f) ? 1.f : 1.f / (1.f + grad_rho_term);
+  } else {
+    P = HYDRO_GAMMA_MINUS_ONE * u * rho;
+    cs = sqrtf(HYDRO_GAMMA * P / rho);
+    const float common_factor = h * HYDRO_DIMENSION_INV / wcount;
+    if (h > 0.9999f * G.h_max) {
+      f = 0.f;
+    } else {
+      const float grad_W_term = common_factor * wcount_dh;
+      f = (grad_W_term < -0.9999f) ? 0.f : common_factor * rho_dh / (1.f + grad_W_term);
+    }
+    if (SCHEME == SCH_MINIMAL) {
+      const float h_inv = 1.f / h;
+      const float abs_div = fabsf(div_v + HYDRO_DIMENSION * G.H);
+      balsara = G.visc_alpha * abs_div / (abs_div + curl_v + 0.0001f * cs * h_inv);
+    } else {
+      const float abs_div = fabsf(div_v);
+      balsara = abs_div / (abs_div + curl_v + 0.0001f * cs * 1.f / h);
+    }
+  }
+  S.rho[p] = rho;
+  S.fq1[p] = make_float4(rho, P, f, cs);
+  S.fq2[p] = make_float4(balsara, h, u, __int_as_float(tb));
+  if (SCHEME == SCH_SPHENIX) {
+    const float al = S.alpha[p];
+    S.fq3[p] = make_float4(al, S.alpha_diff[p], 0.f, 0.f);
+    S.div_v[p] = div_v;
+    S.g_vsig[p] = 2.f * cs; /* hydro_reset_gradient */
+    S.g_amax[p] = al;
+    G.ng[p] = 0;
+  } else {
+    S.fo1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    S.f_hdt[p] = 0.f;
+    S.f_vsig[p] = 2.f * cs;
+    S.f_minngb[p] = NUM_TIME_BINS + 1; /* timestep_limiter_prepare_force */
+    G.nf[p] = 0;
+  }
+  /* keep the finished density members for a density-level download */
+  S.dA[p] = make_float4(rho, rho_dh, wcount, wcount_dh);
+  S.dB[p] = make_float4(div_v, rx, ry, rz);
+}
+
+/* runner_do_ghost leaf loop, runner_ghost.c:1197-1538. One warp per leaf. */
+template <int SCHEME>
+__global__ void __launch_bounds__(128) k_ghost(const GhostArgs G) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= G.ngroups) return;
+  const int leaf = G.groups[g].tcell;
+  const DevCell c = G.cells[leaf];
+  const Soa &S = G.S;
+  const int n_in = G.first_pass ? c.count : G.redo_count[g];
+  int32_t *list = G.redo_list + c.first;
+  int nout = 0;
+  float hmax_conv = 0.f;
+  bool any_conv = false;
+  for (int base = 0; base < n_in; base += 32) {
+    const int k = base + lane;
+    bool valid = k < n_in;
+    int p = -1;
+    if (valid) p = G.first_pass ? c.first + k : list[k];
+    if (valid && G.first_pass) valid = S.time_bin[p] <= G.max_active_bin;
+    bool redo = false;
+    if (valid) {
+      float left = G.first_pass ? 0.f : G.left[p];
+      float right = G.first_pass ? G.h_max : G.right[p];
+      const float h_old = S.h[p];
+      const float h_old_dim = h_old * h_old * h_old;
+      const float h_old_dim_minus_one = h_old * h_old;
+      const float4 a = S.dA[p], b = S.dB[p];
+      const float m = S.mv[p].x;
+      float rho = a.x, rho_dh = a.y, wcount = a.z, wcount_dh = a.w;
+      float div_v = b.x, rx = b.y, ry = b.z, rz = b.w;
+      float h_new = 0.f;
+      bool has_no_ngb = false;
+      bool done_early = false;
+      if (wcount < 1.e-5 * (double)KERNEL_ROOT) {
+        has_no_ngb = true;
+        h_new = 2.f * h_old;
+      } else {
+        /* hydro_end_density: Minimal :543, Gadget2 :526, SPHENIX :613 */
+        const float h_inv = 1.0f / h_old;
+        const float h_inv_dim = h_inv * h_inv * h_inv;
+        const float h_inv_dim_plus_one = h_inv_dim * h_inv;
+        rho += m * KERNEL_ROOT;
+        rho_dh -= HYDRO_DIMENSION * m * KERNEL_ROOT;
+        wcount += KERNEL_ROOT;
+        wcount_dh -= HYDRO_DIMENSION * KERNEL_ROOT;
+        rho *= h_inv_dim;
+        rho_dh *= h_inv_dim_plus_one;
+        wcount *= h_inv_dim;
+        wcount_dh *= h_inv_dim_plus_one;
+        const float rho_inv = 1.f / rho;
+        const float a_inv2 = 1.f / (G.a * G.a);
+        const float fac = h_inv_dim_plus_one * a_inv2 * rho_inv;
+        rx *= fac;
+        ry *= fac;
+        rz *= fac;
+        if (SCHEME == SCH_SPHENIX) {
+          div_v *= h_inv_dim_plus_one * rho_inv * a_inv2;
+          div_v += G.H * HYDRO_DIMENSION;
+        } else {
+          div_v *= fac;
+        }
+        if (G.use_mass_weighted) {
+          const float inv_mass = 1.f / m;
+          wcount = rho * inv_mass;
+          wcount_dh = rho_dh * inv_mass;
+        }
+        const float n_sum = wcount * h_old_dim;
+        const float n_target = G.eta_dim;
+        const float f = n_sum - n_target;
+        const float f_prime = wcount_dh * h_old_dim + HYDRO_DIMENSION * wcount * h_old_dim_minus_one;
+        if (n_sum < n_target)
+          left = fmaxf(left, h_old);
+        else if (n_sum > n_target)
+          right = fminf(right, h_old);
+        if (((h_old >= G.h_max) && (f < 0.f)) || ((h_old <= G.h_min) && (f > 0.f))) {
+          /* already at the limit: tidy up as if converged (:1271-1352) */
+          ghost_finalise<SCHEME>(G, p, h_old, rho, rho_dh, wcount, wcount_dh, div_v, rx, ry, rz);
+          hmax_conv = fmaxf(hmax_conv, h_old);
+          any_conv = true;
+          done_early = true;
+        } else {
+          h_new = h_old - f / (f_prime + 1.17549435e-38f);
+          h_new = fminf(h_new, 2.f * h_old);
+          h_new = fmaxf(h_new, 0.5f * h_old);
+          h_new = fmaxf(h_new, left);
+          h_new = fminf(h_new, right);
+        }
+      }
+      if (!done_early) {
+        float h_final = h_old;
+        if (fabsf(h_new - h_old) > G.eps * h_old) {
+          float h_set;
+          if ((h_new == left && h_old == right) || (h_old == left && h_new == right)) {
+            h_set = cbrtf(0.5f * (left * left * left + right * right * right));
+          } else {
+            h_set = h_new;
+          }
+          if (h_set < G.h_max && h_set > G.h_min) {
+            redo = true;
+            S.h[p] = h_set;
+            G.left[p] = left;
+            G.right[p] = right;
+            /* hydro_init_part */
+            S.dA[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            S.dB[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (SCHEME == SCH_SPHENIX) S.g_lap[p] = 0.f;
+            G.nd[p] = 0;
+          } else if (h_set <= G.h_min) {
+            h_final = G.h_min;
+          } else {
+            h_final = G.h_max;
+            if (has_no_ngb) {
+              /* hydro_part_has_no_neighbours */
+              const float h_inv = 1.0f / h_final;
+              const float h_inv_dim = h_inv * h_inv * h_inv;
+              rho = m * KERNEL_ROOT * h_inv_dim;
+              wcount = KERNEL_ROOT * h_inv_dim;
+              rho_dh = wcount_dh = div_v = rx = ry = rz = 0.f;
+            }
+          }
+        }
+        if (!redo) {
+          S.h[p] = h_final;
+          S.depth_h[p] = (int8_t)part_h_depth(G.cells, leaf, h_final, S.depth_h[p]);
+          hmax_conv = fmaxf(hmax_conv, h_final);
+          any_conv = true;
+          ghost_finalise<SCHEME>(G, p, h_final, rho, rho_dh, wcount, wcount_dh, div_v, rx, ry, rz);
+        }
+      }
+    }
+    __syncwarp();
+    const unsigned m = __ballot_sync(FULL_MASK, redo);
+    if (redo) list[nout + __popc(m & ((1u << lane) - 1u))] = p;
+    nout += __popc(m);
+    __syncwarp();
+  }
+  hmax_conv = warp_max(hmax_conv);
+  const bool anyc = __any_sync(FULL_MASK, any_conv);
+  if (lane == 0) {
+    G.redo_count[g] = nout;
+    if (nout) atomicAdd(G.n_redo, (unsigned long long)nout);
+    if (anyc) {
+      /* atomic_max_f on the leaf and all its parents (:1621-1632) */
+      for (int ci = leaf; ci >= 0; ci = G.cells[ci].parent) {
+        atomic_max_pos(&G.cells[ci].h_max, hmax_conv);
+        atomic_max_pos(&G.cells[ci].h_max_active, hmax_conv);
+      }
+    }
+  }
+}
+
+/* runner_do_extra_ghost (runner_ghost.c:1016): hydro_end_gradient +
+ * hydro_prepare_force + hydro_reset_acceleration, SPHENIX hydro.h:762-972. */
+struct ExtraArgs {
+  const Group *groups;
+  int ngroups;
+  const DevCell *cells;
+  Soa S;
+  int32_t *nf;
+  int max_active_bin;
+  double time_base;
+  float a;
+  float alpha_max, alpha_min, length, beta, diff_alpha_max, diff_alpha_min;
+};
+__global__ void __launch_bounds__(128) k_extra_ghost(const ExtraArgs E) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= E.ngroups) return;
+  const DevCell c = E.cells[E.groups[g].tcell];
+  const Soa &S = E.S;
+  for (int k = lane; k < c.count; k += 32) {
+    const int p = c.first + k;
+    const int bin = S.time_bin[p];
+    if (bin > E.max_active_bin) continue;
+    const float h = S.h[p];
+    const float h_inv = 1.0f / h;
+    const float h_inv_dim_plus_one = h_inv * h_inv * h_inv * h_inv;
+    float laplace_u = S.g_lap[p] * (2.f * h_inv_dim_plus_one);
+    /* get_timestep (timeline.h:91), passed as a float argument */
+    const float dt_alpha = (float)((double)(bin <= 0 ? 0LL : 1LL << (bin + 1)) * E.time_base);
+    const float4 q1 = S.fq1[p];
+    const float rho = q1.x;
+    const float u = S.u[p];
+    const float div_v = S.div_v[p];
+    const float kernel_support_physical = h * E.a * KERNEL_GAMMA;
+    const float kernel_support_physical_inv = 1.f / kernel_support_physical;
+    const float v_sig_physical = S.g_vsig[p];
+    const float pressure = HYDRO_GAMMA_MINUS_ONE * u * rho;
+    const float soundspeed_physical = sqrtf(HYDRO_GAMMA * pressure / rho);
+    const float sound_crossing_time_inverse = soundspeed_physical * kernel_support_physical_inv;
+    const float div_v_dt = dt_alpha == 0.f ? 0.f : (div_v - S.div_v_prev[p]) / dt_alpha;
+    const float Sterm = div_v < 0.f ? kernel_support_physical * kernel_support_physical *
+                                          fmaxf(0.f, -1.f * div_v_dt)
+                                    : 0.f;
+    const float soundspeed_square = soundspeed_physical * soundspeed_physical;
+    const float alpha_loc = E.alpha_max * Sterm / (soundspeed_square + Sterm);
+    float alpha = S.alpha[p];
+    if (alpha_loc > alpha) {
+      alpha = alpha_loc;
+    } else {
+      const float timescale_ratio = dt_alpha * sound_crossing_time_inverse * E.length;
+      alpha += alpha_loc * timescale_ratio;
+      alpha /= (1.f + timescale_ratio);
+    }
+    alpha = fmaxf(alpha, E.alpha_min);
+    S.alpha[p] = alpha;
+    S.div_v_prev[p] = div_v;
+    S.div_v_dt[p] = div_v_dt;
+    const float diffusion_timescale_physical_inverse = v_sig_physical * kernel_support_physical_inv;
+    const float sqrt_u_inv = 1.f / sqrtf(u);
+    float alpha_diff_dt = E.beta * kernel_support_physical * laplace_u * sqrt_u_inv * (1.f / (E.a * E.a));
+    const float ad = S.alpha_diff[p];
+    alpha_diff_dt -= (ad - E.diff_alpha_min) * diffusion_timescale_physical_inverse;
+    float new_ad = ad + alpha_diff_dt * dt_alpha;
+    new_ad = fmaxf(new_ad, E.diff_alpha_min);
+    const float viscous_diffusion_limit = E.diff_alpha_max * (1.f - S.g_amax[p] / E.alpha_max);
+    new_ad = fminf(new_ad, viscous_diffusion_limit);
+    S.alpha_diff[p] = new_ad;
+    S.g_lap[p] = laplace_u;
+    S.fq3[p] = make_float4(alpha, new_ad, 0.f, 0.f);
+    /* hydro_reset_acceleration + timestep_limiter_prepare_force */
+    S.fo1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    S.f_hdt[p] = 0.f;
+    S.f_minngb[p] = NUM_TIME_BINS + 1;
+    E.nf[p] = 0;
+  }
+}
+
+/* runner_do_end_hydro_force (runner_others.c:815): hydro_end_force */
+__global__ void __launch_bounds__(128)
+    k_end_force(const Group *groups, int ngroups, const DevCell *cells, Soa S, int max_active_bin,
+                int scheme) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= ngroups) return;
+  const DevCell c = cells[groups[g].tcell];
+  for (int k = lane; k < c.count; k += 32) {
+    const int p = c.first + k;
+    if (S.time_bin[p] > max_active_bin) continue;
+    S.f_hdt[p] *= S.h[p] * HYDRO_DIMENSION_INV;
+    if (scheme == SCH_GADGET2) {
+      /* 0.5 * gas_entropy_from_internal_energy(rho, entropy_dt) */
+      const float cbrt_inv = 1.f / cbrtf(S.rho[p]);
+      float4 o = S.fo1[p];
+      o.w = 0.5f * (HYDRO_GAMMA_MINUS_ONE * o.w * (cbrt_inv * cbrt_inv));
+      S.fo1[p] = o;
+    }
+  }
+}
+
+/* hydro_init_part for the active particles (cell_drift.c:361) */
+__global__ void k_init_parts(Soa S, int32_t *nd, int64_t n, int max_active_bin, int scheme) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (S.time_bin[p] > max_active_bin) return;
+  S.dA[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  S.dB[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (scheme == SCH_SPHENIX) S.g_lap[p] = 0.f;
+  nd[p] = 0;
+}
+
+/* Which h_max-dependent recursion predicates does each cell satisfy NOW?
+ * (cell.h:966 subpair2, :1007 subself2). Compared with the bits the force
+ * worklist was built with; a mismatch triggers a rebuild on the host. */
+__global__ void k_force_bits(const DevCell *cells, const float *dmin, const float *dx_max_part,
+                             const uint8_t *bits, int ncells, int32_t *flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const float hm = cells[c].h_max;
+  const float gh = __fmul_rn(KERNEL_GAMMA, hm);
+  const float half = __fmul_rn(0.5f, dmin[c]);
+  const uint8_t b = (uint8_t)((__fadd_rn(gh, dx_max_part[c]) < half) ? 1 : 0) |
+                    (uint8_t)((((cells[c].flags >> 2) & 1) && (gh < half)) ? 2 : 0);
+  if (b != bits[c]) *flag = 1;
+}
+
+__global__ void k_get_cell_hmax(const DevCell *cells, int ncells, float *h_max, float *h_max_active) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  h_max[c] = cells[c].h_max;
+  h_max_active[c] = cells[c].h_max_active;
+}
+
+/* ======================================================================== */
+/* Host side                                                                 */
+/* ======================================================================== */
+static Soa soa_of(H *h) {
+  Soa S;
+  S.x = h->x; S.mv = h->mv; S.dA = h->dA; S.dB = h->dB; S.fq1 = h->fq1; S.fq2 = h->fq2;
+  S.fq3 = h->fq3; S.fo1 = h->fo1; S.h = h->hh; S.u = h->u; S.rho = h->rho; S.f_hdt = h->f_hdt;
+  S.f_vsig = h->f_vsig; S.g_vsig = h->g_vsig; S.g_lap = h->g_lap; S.g_amax = h->g_amax;
+  S.alpha = h->alpha; S.alpha_diff = h->alpha_diff; S.div_v_prev = h->div_v_prev;
+  S.div_v_dt = h->div_v_dt; S.div_v = h->div_v; S.time_bin = h->time_bin; S.depth_h = h->depth_h;
+  S.f_minngb = h->f_minngb;
+  return S;
+}
+
+static const int32_t kLayouts[3][33] = {
+    /* offsetof() of the reference's default builds (tests/golden/part_layouts.json) */
+    {128, 0, 16, 40, 52, 64, 68, 72, 76, -1, -1, 80, 84, 88, 92, 100, 96, 84, 88, -1, 92, 96, 100,
+     104, -1, -1, -1, -1, -1, -1, 113, 114, 116},
+    {128, 0, 16, 40, 52, 68, 64, -1, -1, 76, 80, 72, 84, 88, 92, 96, 108, 88, -1, 92, 96, 100, 104,
+     84, -1, -1, -1, -1, -1, -1, 113, 114, 116},
+    {160, 0, 16, 40, 52, 64, 68, 72, 76, -1, -1, 80, 112, 116, 120, 124, 84, 112, 116, -1, 120, 100,
+     124, 128, 88, 92, 96, 104, 108, 132, 138, 137, 140}};
+
+extern "C" int swiftgpu_default_layout(int scheme, swiftgpu_part_layout *out) {
+  if (scheme < 0 || scheme > 2 || !out) return 1;
+  static_assert(sizeof(swiftgpu_part_layout) == 33 * sizeof(int32_t), "layout struct");
+  memcpy(out, kLayouts[scheme], sizeof(*out));
+  return 0;
+}
+
+extern "C" int swiftgpu_default_config(int scheme, swiftgpu_config *cfg) {
+  if (scheme < 0 || scheme > 2 || !cfg) return 1;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = SWIFTGPU_ABI_VERSION;
+  cfg->scheme = scheme;
+  cfg->periodic = 1;
+  cfg->dim[0] = cfg->dim[1] = cfg->dim[2] = 1.0;
+  cfg->eta_neighbours = 1.2348f;   /* hydro_props_init_no_hydro */
+  cfg->h_tolerance = 1e-4f;        /* hydro_properties.c:45 */
+  cfg->h_max = 3.402823466e+38f;   /* hydro_props_default_h_max = FLT_MAX */
+  cfg->h_min = 0.f;
+  cfg->max_smoothing_iterations = 30; /* hydro_properties.c:42 */
+  cfg->CFL_condition = 0.1f;
+  cfg->viscosity_alpha = scheme == SWIFTGPU_SCHEME_SPHENIX ? 0.1f : 0.8f;
+  cfg->viscosity_alpha_max = 2.0f;
+  cfg->viscosity_alpha_min = 0.0f;
+  cfg->viscosity_length = 0.05f;
+  cfg->diffusion_alpha = 0.0f;
+  cfg->diffusion_beta = 1.0f;
+  cfg->diffusion_alpha_max = 1.0f;
+  cfg->diffusion_alpha_min = 0.0f;
+  cfg->rank = 0;
+  cfg->nranks = 1;
+  return swiftgpu_default_layout(scheme, &cfg->layout);
+}
+
+extern "C" const char *swiftgpu_last_error(const swiftgpu_t *h) {
+  return h ? h->err.c_str() : g_err.c_str();
+}
+
+extern "C" int swiftgpu_init(swiftgpu_t **out, const swiftgpu_config *cfg) {
+  if (!out || !cfg) return 1;
+  *out = nullptr;
+  if (cfg->abi_version != SWIFTGPU_ABI_VERSION) {
+    g_err = "ABI version mismatch";
+    return 1;
+  }
+  if (cfg->scheme < 0 || cfg->scheme > 2) {
+    g_err = "unknown scheme";
+    return 1;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_err = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+            " (libswiftgpu has no CPU fallback)";
+    return 2;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_err = "bad device ordinal";
+    return 1;
+  }
+  H *h = new H();
+  h->cfg = *cfg;
+  memset(&h->stats, 0, sizeof(h->stats));
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreate(&h->stream) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&h->d_flag, sizeof(int32_t)) != cudaSuccess) {
+    g_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete h;
+    return 2;
+  }
+  cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
+  *out = h;
+  return 0;
+}
+
+static void free_parts(H *h) {
+  cudaFree(h->d_aos); cudaFree(h->x); cudaFree(h->mv); cudaFree(h->dA); cudaFree(h->dB);
+  cudaFree(h->fq1); cudaFree(h->fq2); cudaFree(h->fq3); cudaFree(h->fo1); cudaFree(h->hh);
+  cudaFree(h->u); cudaFree(h->rho); cudaFree(h->f_hdt); cudaFree(h->f_vsig); cudaFree(h->g_vsig);
+  cudaFree(h->g_lap); cudaFree(h->g_amax); cudaFree(h->alpha); cudaFree(h->alpha_diff);
+  cudaFree(h->div_v_prev); cudaFree(h->div_v_dt); cudaFree(h->div_v); cudaFree(h->gleft);
+  cudaFree(h->gright); cudaFree(h->time_bin); cudaFree(h->depth_h); cudaFree(h->f_minngb);
+  cudaFree(h->nd); cudaFree(h->ng); cudaFree(h->nf);
+  h->d_aos = nullptr; h->x = nullptr;
+  h->n = 0;
+}
+
+extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  free_parts(h);
+  h->L_density.release(); h->L_subset.release(); h->L_force.release();
+  cudaFree(h->d_cells); cudaFree(h->d_cells_init); cudaFree(h->d_dmin); cudaFree(h->d_dxp); cudaFree(h->sort_idx); cudaFree(h->d_segs); cudaFree(h->d_counters);
+  cudaFree(h->d_flag); cudaFree(h->d_force_bits);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int swiftgpu_set_step(swiftgpu_t *h, const swiftgpu_step *step) {
+  if (!h || !step) return 1;
+  if (step->with_cosmology) return h->fail("cosmological time integration is not supported");
+  if (h->has_step && (h->step.ti_current != step->ti_current ||
+                      h->step.max_active_bin != step->max_active_bin))
+    h->lists_built = false; /* activity changed: the worklists depend on it */
+  h->step = *step;
+  h->has_step = 1;
+  return 0;
+}
+
+extern "C" int swiftgpu_upload_cells(swiftgpu_t *h, const swiftgpu_cell *cells, int32_t ncells,
+                                     const int32_t *top, int32_t ntop) {
+  if (!h || !cells || !top || ncells <= 0 || ntop <= 0) return 1;
+  cudaSetDevice(h->cfg.device);
+  h->cells.assign(cells, cells + ncells);
+  h->up_hmax.resize(ncells);
+  h->up_hmax_active.resize(ncells);
+  for (int c = 0; c < ncells; c++) {
+    h->up_hmax[c] = cells[c].h_max;
+    h->up_hmax_active[c] = cells[c].h_max_active;
+  }
+  h->top.assign(top, top + ntop);
+  h->ncells = ncells;
+  h->lists_built = false;
+  h->sorted = false;
+  return 0;
+}
+
+template <class T>
+static cudaError_t to_device(T **dst, const std::vector<T> &v) {
+  cudaFree(*dst);
+  *dst = nullptr;
+  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void **)dst, bytes);
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
+  D.release();
+  D.ngroups = (int)W.groups.size();
+  D.nitems = W.items.size();
+  std::vector<int32_t> tg, tc, tfirst(std::max<size_t>(W.groups.size(), 1));
+  /* Heaviest groups first (LPT) so that the tail of the launch is short. */
+  std::vector<int32_t> order(W.groups.size());
+  for (size_t g = 0; g < order.size(); g++) order[g] = (int32_t)g;
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int32_t a, int32_t b) { return W.groups[a].cost > W.groups[b].cost; });
+  int64_t tot = 0;
+  for (size_t g = 0; g < W.groups.size(); g++) {
+    const swiftgpu_cell &c = h->cells[W.groups[g].tcell];
+    /* subset lists address the redo list by the leaf's own particle range */
+    tfirst[g] = subset ? (int32_t)c.first_part : (int32_t)tot;
+    tot += c.count;
+  }
+  for (int32_t g : order) {
+    const swiftgpu_cell &c = h->cells[W.groups[g].tcell];
+    const int nch = (c.count + 31) / 32;
+    for (int k = 0; k < nch; k++) {
+      tg.push_back(g);
+      tc.push_back(k);
+    }
+  }
+  D.ntasks = (int)tg.size();
+  D.tgt_total = subset ? h->n : tot;
+  CK(to_device(&D.items, W.items));
+  CK(to_device(&D.groups, W.groups));
+  CK(to_device(&D.task_group, tg));
+  CK(to_device(&D.task_chunk, tc));
+  CK(to_device(&D.tgt_first, tfirst));
+  CK(cudaMalloc((void **)&D.tgt_count, std::max(D.ngroups, 1) * sizeof(int32_t)));
+  CK(cudaMemset(D.tgt_count, 0, std::max(D.ngroups, 1) * sizeof(int32_t)));
+  CK(cudaMalloc((void **)&D.tgt_list, std::max<int64_t>(D.tgt_total, 1) * sizeof(int32_t)));
+  return 0;
+}
+
+/* Builds worklists, the device cell table and the sort segments. */
+static int build_lists(H *h, bool force_only) {
+  if (!h->has_step) return h->fail("swiftgpu_set_step must be called before running a phase");
+  if (h->cells.empty()) return h->fail("no cells uploaded");
+  if (h->n <= 0) return h->fail("no particles uploaded");
+  cudaSetDevice(h->cfg.device);
+  Flattener F(h->cells.data(), h->ncells, h->top.data(), (int)h->top.size(), h->cfg.dim,
+              h->cfg.periodic, h->cfg.rank, h->step.ti_current);
+  WorkList Wd, Ws, Wf;
+  if (!force_only) {
+    F.build_loop(0, Wd);
+    std::vector<int32_t> aux;
+    F.build_subset(Ws, aux);
+    h->req_density = Wd.sort_requests;
+    h->req_subset = Ws.sort_requests;
+  }
+  F.build_loop(2, Wf);
+  h->force_bits.resize(h->ncells);
+  for (int c = 0; c < h->ncells; c++)
+    h->force_bits[c] = (uint8_t)((Flattener::subpair2(h->cells[c]) ? 1 : 0) |
+                                 (Flattener::subself2(h->cells[c]) ? 2 : 0));
+
+  /* sort segments: union of the requests of the three lists */
+  std::vector<uint64_t> req(h->req_density);
+  req.insert(req.end(), h->req_subset.begin(), h->req_subset.end());
+  req.insert(req.end(), Wf.sort_requests.begin(), Wf.sort_requests.end());
+  std::sort(req.begin(), req.end());
+  req.erase(std::unique(req.begin(), req.end()), req.end());
+
+  std::vector<DevCell> dc(h->ncells);
+  for (int c = 0; c < h->ncells; c++) {
+    const swiftgpu_cell &s = h->cells[c];
+    DevCell &d = dc[c];
+    memset(&d, 0, sizeof(d));
+    for (int k = 0; k < 3; k++) d.loc[k] = s.loc[k];
+    if (s.first_part + s.count > 0x7fffffffLL) return h->fail("more than 2^31 particles per GPU");
+    d.first = (int32_t)s.first_part;
+    d.count = s.count;
+    d.h_max = s.h_max;
+    d.h_max_active = s.h_max_active;
+    d.dx_max_sort = s.dx_max_sort;
+    d.h_max_allowed = s.h_max_allowed;
+    d.h_min_allowed = s.h_min_allowed;
+    d.parent = s.parent;
+    d.sort_base = -1;
+    d.sort_mask = 0;
+    d.depth = (int8_t)s.depth;
+    d.flags = (uint8_t)((s.ti_end_min == h->step.ti_current ? 1 : 0) |
+                        (s.nodeID == h->cfg.rank ? 2 : 0) | (s.split ? 4 : 0));
+  }
+  std::vector<SortSeg> segs;
+  segs.reserve(req.size());
+  int64_t off = 0;
+  int max_seg = 0;
+  for (uint64_t r : req) {
+    const int c = (int)(r >> 4), sid = (int)(r & 15);
+    if (dc[c].sort_base < 0) dc[c].sort_base = off;
+    dc[c].sort_mask |= (uint16_t)(1u << sid);
+    SortSeg s;
+    s.cell = c;
+    s.sid = sid;
+    s.off = off;
+    segs.push_back(s);
+    off += dc[c].count;
+    max_seg = std::max(max_seg, dc[c].count);
+  }
+  /* If the force list was rebuilt after the ghost, keep the h_max the device
+   * already holds (it is newer than the host copy). */
+  if (force_only && h->d_cells) {
+    std::vector<float> hm(h->ncells), hma(h->ncells);
+    float *d_tmp = nullptr;
+    CK(cudaMalloc((void **)&d_tmp, 2 * sizeof(float) * h->ncells));
+    k_get_cell_hmax<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->ncells, d_tmp,
+                                                                    d_tmp + h->ncells);
+    CK(cudaMemcpyAsync(hm.data(), d_tmp, sizeof(float) * h->ncells, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hma.data(), d_tmp + h->ncells, sizeof(float) * h->ncells,
+                       cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_tmp);
+    for (int c = 0; c < h->ncells; c++) {
+      dc[c].h_max = hm[c];
+      dc[c].h_max_active = hma[c];
+    }
+  }
+  {
+    /* pristine table first (uploaded h_max), then the live one */
+    std::vector<DevCell> dc0(dc);
+    for (int c = 0; c < h->ncells; c++) {
+      dc0[c].h_max = h->cells_uploaded_hmax(c);
+      dc0[c].h_max_active = h->cells_uploaded_hmax_active(c);
+    }
+    CK(to_device(&h->d_cells_init, dc0));
+    std::vector<float> dmin(h->ncells), dxp(h->ncells);
+    for (int c = 0; c < h->ncells; c++) {
+      dmin[c] = h->cells[c].dmin;
+      dxp[c] = h->cells[c].dx_max_part;
+    }
+    CK(to_device(&h->d_dmin, dmin));
+    CK(to_device(&h->d_dxp, dxp));
+  }
+  CK(to_device(&h->d_cells, dc));
+  CK(to_device(&h->d_segs, segs));
+  h->nsegs = (int)segs.size();
+  if (off != h->sort_total || !h->sort_idx) {
+    cudaFree(h->sort_idx);
+    h->sort_idx = nullptr;
+    CK(cudaMalloc((void **)&h->sort_idx, std::max<int64_t>(off, 1) * sizeof(uint32_t)));
+    h->sort_total = off;
+  }
+  h->sorted = false;
+  (void)max_seg;
+
+  if (!force_only) {
+    if (upload_list(h, Wd, h->L_density, false)) return 1;
+    if (upload_list(h, Ws, h->L_subset, true)) return 1;
+  }
+  if (upload_list(h, Wf, h->L_force, false)) return 1;
+  CK(to_device(&h->d_force_bits, h->force_bits));
+  h->lists_built = true;
+  return 0;
+}
+
+static int ensure_lists(H *h) {
+  if (h->lists_built) return 0;
+  return build_lists(h, false);
+}
+
+static int alloc_parts(H *h, int64_t n) {
+  if (h->n == n && h->x) return 0;
+  free_parts(h);
+  const swiftgpu_part_layout &L = h->cfg.layout;
+  h->aos_bytes = (size_t)L.size * n;
+#define AL(ptr, T, count) CK(cudaMalloc((void **)&(ptr), sizeof(T) * (size_t)(count)))
+  AL(h->d_aos, char, h->aos_bytes);
+  AL(h->x, double, 3 * n);
+  AL(h->mv, float4, n); AL(h->dA, float4, n); AL(h->dB, float4, n); AL(h->fq1, float4, n);
+  AL(h->fq2, float4, n); AL(h->fq3, float4, n); AL(h->fo1, float4, n);
+  AL(h->hh, float, n); AL(h->u, float, n); AL(h->rho, float, n); AL(h->f_hdt, float, n);
+  AL(h->f_vsig, float, n); AL(h->g_vsig, float, n); AL(h->g_lap, float, n); AL(h->g_amax, float, n);
+  AL(h->alpha, float, n); AL(h->alpha_diff, float, n); AL(h->div_v_prev, float, n);
+  AL(h->div_v_dt, float, n); AL(h->div_v, float, n); AL(h->gleft, float, n); AL(h->gright, float, n);
+  AL(h->time_bin, int8_t, n); AL(h->depth_h, int8_t, n);
+  AL(h->f_minngb, int32_t, n); AL(h->nd, int32_t, n); AL(h->ng, int32_t, n); AL(h->nf, int32_t, n);
+#undef AL
+  h->n = n;
+  h->lists_built = false;
+  return 0;
+}
+
+static int transpose_in(H *h) {
+  const int64_t n = h->n;
+  DevLayout D;
+  D.L = h->cfg.layout;
+  D.scheme = h->cfg.scheme;
+  CK(cudaMemsetAsync(h->nd, 0, sizeof(int32_t) * n, h->stream));
+  CK(cudaMemsetAsync(h->ng, 0, sizeof(int32_t) * n, h->stream));
+  CK(cudaMemsetAsync(h->nf, 0, sizeof(int32_t) * n, h->stream));
+  CK(cudaMemsetAsync(h->dA, 0, sizeof(float4) * n, h->stream));
+  CK(cudaMemsetAsync(h->dB, 0, sizeof(float4) * n, h->stream));
+  CK(cudaMemsetAsync(h->fq3, 0, sizeof(float4) * n, h->stream));
+  k_aos_to_soa<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_aos, D, soa_of(h), n);
+  h->stats.n_launches++;
+  CK(cudaGetLastError());
+  h->phases_done = 0;
+  h->sorted = false;
+  /* h may have changed: the cell table keeps the uploaded h_max values; the
+   * worklists only depend on cells + step. The ghost state restarts. */
+  return 0;
+}
+
+extern "C" int swiftgpu_upload_parts(swiftgpu_t *h, const void *parts_aos, int64_t nparts) {
+  if (!h || !parts_aos || nparts <= 0) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (alloc_parts(h, nparts)) return 1;
+  CK(cudaMemcpyAsync(h->d_aos, parts_aos, h->aos_bytes, cudaMemcpyHostToDevice, h->stream));
+  return transpose_in(h);
+}
+
+extern "C" int swiftgpu_upload_parts_device(swiftgpu_t *h, const void *d_parts_aos, int64_t nparts) {
+  if (!h || !d_parts_aos || nparts <= 0) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (alloc_parts(h, nparts)) return 1;
+  CK(cudaMemcpyAsync(h->d_aos, d_parts_aos, h->aos_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  return transpose_in(h);
+}
+
+static int phase_begin(H *h) {
+  cudaSetDevice(h->cfg.device);
+  if (ensure_lists(h)) return 1;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  return 0;
+}
+static int phase_end(H *h, double *ms_out) {
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_out = ms;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int swiftgpu_run_sort(swiftgpu_t *h) {
+  if (!h) return 1;
+  if (phase_begin(h)) return 1;
+  if (h->nsegs > 0) {
+    /* segments larger than the shared-memory sorter need a key scratch */
+    float *gkeys = nullptr;
+    bool need = false;
+    for (const swiftgpu_cell &c : h->cells)
+      if (c.count > SORT_SMEM_MAX) need = true; /* conservative: any big cell */
+    if (need) CK(cudaMalloc((void **)&gkeys, sizeof(float) * std::max<int64_t>(h->sort_total, 1)));
+    k_sort<<<h->nsegs, 256, 0, h->stream>>>(h->d_segs, h->d_cells, h->x, h->sort_idx, gkeys);
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+    if (need) {
+      CK(cudaStreamSynchronize(h->stream));
+      cudaFree(gkeys);
+    }
+  }
+  h->sorted = true;
+  h->phases_done |= SWIFTGPU_PHASE_SORT;
+  return phase_end(h, &h->stats.ms_sort);
+}
+
+static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
+  LoopArgs A;
+  memset(&A, 0, sizeof(A));
+  A.cells = h->d_cells;
+  A.items = D.items;
+  A.groups = D.groups;
+  A.task_group = D.task_group;
+  A.task_chunk = D.task_chunk;
+  A.ntasks = D.ntasks;
+  A.tgt_list = D.tgt_list;
+  A.tgt_first = D.tgt_first;
+  A.tgt_count = D.tgt_count;
+  A.sort_idx = h->sort_idx;
+  A.x = h->x; A.mv = h->mv; A.h = h->hh; A.depth_h = h->depth_h; A.time_bin = h->time_bin;
+  A.fq1 = h->fq1; A.fq2 = h->fq2; A.fq3 = h->fq3;
+  A.dA = h->dA; A.dB = h->dB; A.g_vsig = h->g_vsig; A.g_lap = h->g_lap; A.g_amax = h->g_amax;
+  A.fo1 = h->fo1; A.f_hdt = h->f_hdt; A.f_vsig = h->f_vsig; A.f_minngb = h->f_minngb;
+  A.count = count;
+  A.total = h->d_counters + counter;
+  for (int k = 0; k < 3; k++) A.dim[k] = h->cfg.dim[k];
+  A.a2_Hubble = h->step.a * h->step.a * h->step.H;
+  A.max_active_bin = h->step.max_active_bin;
+  return A;
+}
+
+static int build_targets(H *h, DevList &D) {
+  if (D.ngroups == 0) return 0;
+  k_build_targets<<<(D.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(
+      D.groups, D.ngroups, h->d_cells, h->time_bin, h->step.max_active_bin, D.tgt_first, D.tgt_count,
+      D.tgt_list);
+  h->stats.n_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int read_counter(H *h, int k, int64_t *out) {
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, h->d_counters + k, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *out = (int64_t)v;
+  return 0;
+}
+
+extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
+  if (!h) return 1;
+  if (ensure_lists(h)) return 1;
+  if (!h->sorted && swiftgpu_run_sort(h)) return 1;
+  if (phase_begin(h)) return 1;
+  const int64_t n = h->n;
+  /* the previous ghost raised h_max / h_max_active: start from the uploaded values */
+  CK(cudaMemcpyAsync(h->d_cells, h->d_cells_init, sizeof(DevCell) * h->ncells,
+                     cudaMemcpyDeviceToDevice, h->stream));
+  k_init_parts<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(soa_of(h), h->nd, n,
+                                                                  h->step.max_active_bin, h->cfg.scheme);
+  h->stats.n_launches++;
+  CK(cudaMemsetAsync(h->d_counters + 0, 0, sizeof(unsigned long long), h->stream));
+  if (build_targets(h, h->L_density)) return 1;
+  if (h->L_density.ntasks > 0) {
+    LoopArgs A = loop_args(h, h->L_density, h->nd, 0);
+    k_loop1<LOOP_DENSITY><<<(A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, 0,
+                            h->stream>>>(A);
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+  }
+  h->phases_done |= SWIFTGPU_PHASE_DENSITY;
+  h->phases_done &= ~(uint32_t)(SWIFTGPU_PHASE_GHOST | SWIFTGPU_PHASE_GRADIENT |
+                                SWIFTGPU_PHASE_EXTRA_GHOST | SWIFTGPU_PHASE_FORCE |
+                                SWIFTGPU_PHASE_END_FORCE);
+  if (phase_end(h, &h->stats.ms_density)) return 1;
+  return read_counter(h, 0, &h->stats.n_density);
+}
+
+template <int SCHEME>
+static int ghost_launch(H *h, const GhostArgs &G) {
+  k_ghost<SCHEME><<<(G.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(G);
+  h->stats.n_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
+  if (!h) return 1;
+  if (!(h->phases_done & SWIFTGPU_PHASE_DENSITY)) return h->fail("run_ghost before run_density");
+  if (phase_begin(h)) return 1;
+  DevList &D = h->L_subset;
+  GhostArgs G;
+  memset(&G, 0, sizeof(G));
+  G.groups = D.groups;
+  G.ngroups = D.ngroups;
+  G.cells = h->d_cells;
+  G.redo_list = D.tgt_list;
+  G.redo_count = D.tgt_count;
+  G.S = soa_of(h);
+  G.left = h->gleft;
+  G.right = h->gright;
+  G.nd = h->nd; G.ng = h->ng; G.nf = h->nf;
+  G.n_redo = h->d_counters + 3;
+  G.max_active_bin = h->step.max_active_bin;
+  G.h_max = h->cfg.h_max;
+  G.h_min = h->cfg.h_min;
+  G.eps = h->cfg.h_tolerance;
+  G.eta_dim = h->cfg.eta_neighbours * h->cfg.eta_neighbours * h->cfg.eta_neighbours;
+  G.use_mass_weighted = h->cfg.use_mass_weighted_num_ngb;
+  G.visc_alpha = h->cfg.viscosity_alpha;
+  G.H = h->step.H;
+  G.a = h->step.a;
+  int iter = 0;
+  int64_t redo = 0;
+  int64_t extra_density = 0;
+  const int max_iter = h->cfg.max_smoothing_iterations;
+  if (D.ngroups > 0) {
+    for (iter = 0; iter < max_iter; iter++) {
+      G.first_pass = iter == 0;
+      CK(cudaMemsetAsync(h->d_counters + 3, 0, sizeof(unsigned long long), h->stream));
+      int rc = 0;
+      switch (h->cfg.scheme) {
+        case SCH_MINIMAL: rc = ghost_launch<SCH_MINIMAL>(h, G); break;
+        case SCH_GADGET2: rc = ghost_launch<SCH_GADGET2>(h, G); break;
+        default: rc = ghost_launch<SCH_SPHENIX>(h, G); break;
+      }
+      if (rc) return 1;
+      if (read_counter(h, 3, &redo)) return 1;
+      if (redo == 0) {
+        iter++;
+        break;
+      }
+      if (iter + 1 >= max_iter) {
+        iter++;
+        break;
+      }
+      /* re-run the density loop for the unconverged particles
+       * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
+      CK(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long), h->stream));
+      LoopArgs A = loop_args(h, D, h->nd, 4);
+      k_loop1<LOOP_DENSITY><<<(A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK,
+                              0, h->stream>>>(A);
+      h->stats.n_launches++;
+      CK(cudaGetLastError());
+      int64_t nn = 0;
+      if (read_counter(h, 4, &nn)) return 1;
+      extra_density += nn;
+    }
+  }
+  h->stats.ghost_iterations = iter;
+  h->stats.ghost_unconverged = (int32_t)redo;
+  h->stats.n_density += extra_density;
+  h->phases_done |= SWIFTGPU_PHASE_GHOST;
+  if (phase_end(h, &h->stats.ms_ghost)) return 1;
+  if (redo > 0)
+    return h->fail("Smoothing length failed to converge on %lld particles.", (long long)redo);
+  return 0;
+}
+
+extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
+  if (!h) return 1;
+  if (h->cfg.scheme != SCH_SPHENIX) return 0;
+  if (!(h->phases_done & SWIFTGPU_PHASE_GHOST)) return h->fail("run_gradient before run_ghost");
+  if (phase_begin(h)) return 1;
+  CK(cudaMemsetAsync(h->d_counters + 1, 0, sizeof(unsigned long long), h->stream));
+  if (h->L_density.ntasks > 0) {
+    LoopArgs A = loop_args(h, h->L_density, h->ng, 1);
+    k_loop1<LOOP_GRADIENT><<<(A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK,
+                             0, h->stream>>>(A);
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+  }
+  h->phases_done |= SWIFTGPU_PHASE_GRADIENT;
+  if (phase_end(h, &h->stats.ms_gradient)) return 1;
+  return read_counter(h, 1, &h->stats.n_gradient);
+}
+
+extern "C" int swiftgpu_run_extra_ghost(swiftgpu_t *h) {
+  if (!h) return 1;
+  if (h->cfg.scheme != SCH_SPHENIX) return 0;
+  if (!(h->phases_done & SWIFTGPU_PHASE_GRADIENT)) return h->fail("run_extra_ghost before run_gradient");
+  if (phase_begin(h)) return 1;
+  ExtraArgs E;
+  memset(&E, 0, sizeof(E));
+  E.groups = h->L_subset.groups;
+  E.ngroups = h->L_subset.ngroups;
+  E.cells = h->d_cells;
+  E.S = soa_of(h);
+  E.nf = h->nf;
+  E.max_active_bin = h->step.max_active_bin;
+  E.time_base = h->step.time_base;
+  E.a = h->step.a;
+  E.alpha_max = h->cfg.viscosity_alpha_max;
+  E.alpha_min = h->cfg.viscosity_alpha_min;
+  E.length = h->cfg.viscosity_length;
+  E.beta = h->cfg.diffusion_beta;
+  E.diff_alpha_max = h->cfg.diffusion_alpha_max;
+  E.diff_alpha_min = h->cfg.diffusion_alpha_min;
+  if (E.ngroups > 0) {
+    k_extra_ghost<<<(E.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(E);
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+  }
+  h->phases_done |= SWIFTGPU_PHASE_EXTRA_GHOST;
+  return phase_end(h, &h->stats.ms_extra_ghost);
+}
+
+extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
+  if (!h) return 1;
+  const uint32_t need = h->cfg.scheme == SCH_SPHENIX ? SWIFTGPU_PHASE_EXTRA_GHOST : SWIFTGPU_PHASE_GHOST;
+  if (!(h->phases_done & need)) return h->fail("run_force before the ghost phases");
+  if (phase_begin(h)) return 1;
+  /* Has the ghost changed a recursion predicate the force list depends on? */
+  {
+    CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int32_t), h->stream));
+    k_force_bits<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->d_dmin, h->d_dxp,
+                                                                 h->d_force_bits, h->ncells, h->d_flag);
+    h->stats.n_launches++;
+    int32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flag) {
+      /* pull the new h_max into the host cells and rebuild the force list */
+      std::vector<float> hm(h->ncells), hma(h->ncells);
+      float *d_tmp = nullptr;
+      CK(cudaMalloc((void **)&d_tmp, 2 * sizeof(float) * h->ncells));
+      k_get_cell_hmax<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->ncells, d_tmp,
+                                                                      d_tmp + h->ncells);
+      CK(cudaMemcpyAsync(hm.data(), d_tmp, sizeof(float) * h->ncells, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(hma.data(), d_tmp + h->ncells, sizeof(float) * h->ncells,
+                         cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      cudaFree(d_tmp);
+      std::vector<swiftgpu_cell> saved(h->cells);
+      for (int c = 0; c < h->ncells; c++) {
+        h->cells[c].h_max = hm[c];
+        h->cells[c].h_max_active = hma[c];
+      }
+      const int rc = build_lists(h, true);
+      /* the host copy keeps the uploaded (pre-ghost) values for the density
+       * and subset recursions of a later re-run */
+      for (int c = 0; c < h->ncells; c++) {
+        h->cells[c].h_max = saved[c].h_max;
+        h->cells[c].h_max_active = saved[c].h_max_active;
+      }
+      if (rc) return 1;
+      /* new (cell, sid) segments may exist: sort again */
+      if (h->nsegs > 0) {
+        float *gkeys = nullptr;
+        bool big = false;
+        for (const swiftgpu_cell &c : h->cells)
+          if (c.count > SORT_SMEM_MAX) big = true;
+        if (big) CK(cudaMalloc((void **)&gkeys, sizeof(float) * std::max<int64_t>(h->sort_total, 1)));
+        k_sort<<<h->nsegs, 256, 0, h->stream>>>(h->d_segs, h->d_cells, h->x, h->sort_idx, gkeys);
+        h->stats.n_launches++;
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(gkeys);
+      }
+      h->sorted = true;
+    }
+  }
+  CK(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), h->stream));
+  if (build_targets(h, h->L_force)) return 1;
+  if (h->L_force.ntasks > 0) {
+    LoopArgs A = loop_args(h, h->L_force, h->nf, 2);
+    const unsigned grid = (A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    switch (h->cfg.scheme) {
+      case SCH_MINIMAL: k_loop2<SCH_MINIMAL><<<grid, 32 * WARPS_PER_BLOCK, 0, h->stream>>>(A); break;
+      case SCH_GADGET2: k_loop2<SCH_GADGET2><<<grid, 32 * WARPS_PER_BLOCK, 0, h->stream>>>(A); break;
+      default: k_loop2<SCH_SPHENIX><<<grid, 32 * WARPS_PER_BLOCK, 0, h->stream>>>(A); break;
+    }
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+  }
+  h->phases_done |= SWIFTGPU_PHASE_FORCE;
+  if (phase_end(h, &h->stats.ms_force)) return 1;
+  return read_counter(h, 2, &h->stats.n_force);
+}
+
+extern "C" int swiftgpu_run_end_force(swiftgpu_t *h) {
+  if (!h) return 1;
+  if (!(h->phases_done & SWIFTGPU_PHASE_FORCE)) return h->fail("run_end_force before run_force");
+  if (phase_begin(h)) return 1;
+  if (h->L_subset.ngroups > 0) {
+    k_end_force<<<(h->L_subset.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(
+        h->L_subset.groups, h->L_subset.ngroups, h->d_cells, soa_of(h), h->step.max_active_bin,
+        h->cfg.scheme);
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+  }
+  h->phases_done |= SWIFTGPU_PHASE_END_FORCE;
+  return phase_end(h, &h->stats.ms_end_force);
+}
+
+extern "C" int swiftgpu_run_step(swiftgpu_t *h, uint32_t mask) {
+  if (!h) return 1;
+  if ((mask & SWIFTGPU_PHASE_SORT) && swiftgpu_run_sort(h)) return 1;
+  if ((mask & SWIFTGPU_PHASE_DENSITY) && swiftgpu_run_density(h)) return 1;
+  if ((mask & SWIFTGPU_PHASE_GHOST) && swiftgpu_run_ghost(h)) return 1;
+  if ((mask & SWIFTGPU_PHASE_GRADIENT) && swiftgpu_run_gradient(h)) return 1;
+  if ((mask & SWIFTGPU_PHASE_EXTRA_GHOST) && swiftgpu_run_extra_ghost(h)) return 1;
+  if ((mask & SWIFTGPU_PHASE_FORCE) && swiftgpu_run_force(h)) return 1;
+  if ((mask & SWIFTGPU_PHASE_END_FORCE) && swiftgpu_run_end_force(h)) return 1;
+  return 0;
+}
+
+static int transpose_out(H *h) {
+  DevLayout D;
+  D.L = h->cfg.layout;
+  D.scheme = h->cfg.scheme;
+  const int density_only = (h->phases_done & SWIFTGPU_PHASE_GHOST) ? 0 : 1;
+  k_soa_to_aos<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(
+      h->d_aos, D, soa_of(h), h->n, h->step.max_active_bin, density_only);
+  h->stats.n_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int swiftgpu_download_parts(swiftgpu_t *h, void *parts_aos, int64_t nparts) {
+  if (!h || !parts_aos || nparts != h->n) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (transpose_out(h)) return 1;
+  CK(cudaMemcpyAsync(parts_aos, h->d_aos, h->aos_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int swiftgpu_download_parts_device(swiftgpu_t *h, void *d_parts_aos, int64_t nparts) {
+  if (!h || !d_parts_aos || nparts != h->n) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (transpose_out(h)) return 1;
+  CK(cudaMemcpyAsync(d_parts_aos, h->d_aos, h->aos_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int swiftgpu_download_cells(swiftgpu_t *h, swiftgpu_cell *cells, int32_t ncells) {
+  if (!h || !cells || ncells != h->ncells || !h->d_cells) return 1;
+  cudaSetDevice(h->cfg.device);
+  std::vector<float> hm(ncells), hma(ncells);
+  float *d_tmp = nullptr;
+  CK(cudaMalloc((void **)&d_tmp, 2 * sizeof(float) * ncells));
+  k_get_cell_hmax<<<(ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, ncells, d_tmp, d_tmp + ncells);
+  h->stats.n_launches++;
+  CK(cudaMemcpyAsync(hm.data(), d_tmp, sizeof(float) * ncells, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(hma.data(), d_tmp + ncells, sizeof(float) * ncells, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_tmp);
+  for (int c = 0; c < ncells; c++) {
+    cells[c].h_max = hm[c];
+    cells[c].h_max_active = hma[c];
+  }
+  return 0;
+}
+
+extern "C" int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density, int32_t *n_gradient,
+                                        int32_t *n_force, int64_t nparts) {
+  if (!h || nparts != h->n) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (n_density) CK(cudaMemcpy(n_density, h->nd, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
+  if (n_gradient) CK(cudaMemcpy(n_gradient, h->ng, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
+  if (n_force) CK(cudaMemcpy(n_force, h->nf, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int swiftgpu_get_stats(swiftgpu_t *h, swiftgpu_stats *out) {
+  if (!h || !out) return 1;
+  *out = h->stats;
+  return 0;
+}
+
+extern "C" int swiftgpu_halo_setup(swiftgpu_t *h, void *nccl_comm) {
+  if (!h) return 1;
+  (void)nccl_comm;
+  return h->fail("halo exchange: not built in this version (single-GPU build)");
+}
+extern "C" int swiftgpu_halo_exchange(swiftgpu_t *h, int phase) {
+  if (!h) return 1;
+  (void)phase;
+  return h->fail("halo exchange: not built in this version (single-GPU build)");
+}

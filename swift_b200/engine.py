@@ -1,0 +1,118 @@
+"""Thin host-side mirror of the C ABI: `SwiftGPU` owns one libswiftgpu handle.
+
+Method names follow the reference's task types (sort, density, ghost,
+gradient, extra_ghost, force, end_force; src/runner_main.c:214-375). Every
+call goes through the C ABI of libswiftgpu.so; failures raise RuntimeError
+with swiftgpu_last_error(), like the reference's error() macro.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class SwiftGPU:
+    def __init__(self, cfg):
+        self.lib = abi.load()
+        self.cfg = cfg
+        self.h = abi.VP()
+        rc = self.lib.swiftgpu_init(C.byref(self.h), C.byref(cfg))
+        if rc != 0:
+            msg = self.lib.swiftgpu_last_error(None)
+            raise RuntimeError(f"swiftgpu_init failed ({rc}): {msg.decode() if msg else ''}")
+        self.nparts = 0
+        self.ncells = 0
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self.lib.swiftgpu_last_error(self.h)
+            raise RuntimeError(f"{what} failed: {msg.decode() if msg else rc}")
+
+    def upload_cells(self, cells, top):
+        self._cells = np.ascontiguousarray(cells)
+        top = np.ascontiguousarray(top, dtype=np.int32)
+        self.ncells = self._cells.shape[0]
+        self._ck(self.lib.swiftgpu_upload_cells(self.h, self._cells.ctypes.data, self.ncells,
+                                                top.ctypes.data, top.shape[0]), "upload_cells")
+
+    def upload_parts(self, parts_u8):
+        assert parts_u8.dtype == np.uint8 and parts_u8.flags.c_contiguous
+        self.nparts = parts_u8.size // self.cfg.layout.size
+        self._ck(self.lib.swiftgpu_upload_parts(self.h, parts_u8.ctypes.data, self.nparts), "upload_parts")
+
+    def upload_parts_ptr(self, host_ptr, nparts):
+        self.nparts = nparts
+        self._ck(self.lib.swiftgpu_upload_parts(self.h, host_ptr, nparts), "upload_parts")
+
+    def upload_parts_device(self, dev_ptr, nparts):
+        self.nparts = nparts
+        self._ck(self.lib.swiftgpu_upload_parts_device(self.h, dev_ptr, nparts), "upload_parts_device")
+
+    def set_step(self, step):
+        self._ck(self.lib.swiftgpu_set_step(self.h, C.byref(step)), "set_step")
+
+    def run_sort(self):
+        self._ck(self.lib.swiftgpu_run_sort(self.h), "run_sort")
+
+    def run_density(self):
+        self._ck(self.lib.swiftgpu_run_density(self.h), "run_density")
+
+    def run_ghost(self):
+        self._ck(self.lib.swiftgpu_run_ghost(self.h), "run_ghost")
+
+    def run_gradient(self):
+        self._ck(self.lib.swiftgpu_run_gradient(self.h), "run_gradient")
+
+    def run_extra_ghost(self):
+        self._ck(self.lib.swiftgpu_run_extra_ghost(self.h), "run_extra_ghost")
+
+    def run_force(self):
+        self._ck(self.lib.swiftgpu_run_force(self.h), "run_force")
+
+    def run_end_force(self):
+        self._ck(self.lib.swiftgpu_run_end_force(self.h), "run_end_force")
+
+    def run_step(self, mask=abi.PHASE_ALL):
+        self._ck(self.lib.swiftgpu_run_step(self.h, mask), "run_step")
+
+    def download_parts(self, out=None):
+        if out is None:
+            out = np.zeros(self.nparts * self.cfg.layout.size, dtype=np.uint8)
+        self._ck(self.lib.swiftgpu_download_parts(self.h, out.ctypes.data, self.nparts), "download_parts")
+        return out
+
+    def download_parts_ptr(self, host_ptr):
+        self._ck(self.lib.swiftgpu_download_parts(self.h, host_ptr, self.nparts), "download_parts")
+
+    def download_parts_device(self, dev_ptr):
+        self._ck(self.lib.swiftgpu_download_parts_device(self.h, dev_ptr, self.nparts), "download_parts_device")
+
+    def download_cells(self):
+        out = self._cells.copy()
+        self._ck(self.lib.swiftgpu_download_cells(self.h, out.ctypes.data, self.ncells), "download_cells")
+        return out
+
+    def download_counts(self):
+        nd = np.zeros(self.nparts, np.int32)
+        ng = np.zeros_like(nd)
+        nf = np.zeros_like(nd)
+        self._ck(self.lib.swiftgpu_download_counts(self.h, nd.ctypes.data, ng.ctypes.data, nf.ctypes.data,
+                                                   self.nparts), "download_counts")
+        return nd, ng, nf
+
+    def stats(self):
+        s = abi.Stats()
+        self._ck(self.lib.swiftgpu_get_stats(self.h, C.byref(s)), "get_stats")
+        return s
+
+    def close(self):
+        if self.h:
+            self.lib.swiftgpu_destroy(self.h)
+            self.h = abi.VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
