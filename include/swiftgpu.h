@@ -166,6 +166,9 @@ typedef struct swiftgpu_stats {
   int64_t n_gradient; /* directed gradient interactions */
   int64_t n_force;    /* directed force interactions */
   int64_t n_launches; /* kernel launches by the library */
+  /* distance tests (candidate pairs examined) of the same loops: the
+   * pruning efficiency is n_x / t_x */
+  int64_t t_density, t_gradient, t_force;
   int32_t ghost_iterations;
   int32_t ghost_unconverged;
 } swiftgpu_stats;
@@ -199,6 +202,13 @@ int swiftgpu_upload_parts_device(swiftgpu_t *h, const void *d_parts_aos,
                                  int64_t nparts);
 
 int swiftgpu_set_step(swiftgpu_t *h, const swiftgpu_step *step);
+
+/* Run all further work of this handle on the caller's CUDA stream
+ * (`cuda_stream` is a cudaStream_t; NULL = the handle's own stream). The
+ * reference has no equivalent: it is what lets an engine that already owns
+ * streams (or a benchmark timing with events on its stream) order the GPU
+ * phases against its own copies. */
+int swiftgpu_set_stream(swiftgpu_t *h, void *cuda_stream);
 
 /* runner_do_hydro_sort (runner.h:107) for every cell and every sid the
  * density/force work lists need. */
@@ -239,6 +249,19 @@ int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density,
                              int32_t *n_gradient, int32_t *n_force,
                              int64_t nparts);
 int swiftgpu_get_stats(swiftgpu_t *h, swiftgpu_stats *out);
+
+/* Host-only (no CUDA call): flattens the reference's recursive task functions
+ * (DOSUB_SELF1/PAIR1 for loop 0 = density/gradient, DOSUB_SELF2/PAIR2 for loop
+ * 2 = force, DOSUB_*_SUBSET for loop 3 = ghost re-runs) over the given tree and
+ * reports out[0] = directed leaf-level items, out[1] = target-cell groups,
+ * out[2] = sum over items of count(target cell) * count(source cell),
+ * out[3] = (cell, sid) sorted arrays requested, out[4] = self items,
+ * out[5] = items restricted by depth_h (limit_min_h / limit_max_h). Used by
+ * the host-logic tests and to size device buffers. */
+int swiftgpu_worklist_stats(const swiftgpu_config *cfg, const swiftgpu_step *step,
+                            const swiftgpu_cell *cells, int32_t ncells,
+                            const int32_t *top, int32_t ntop, int loop,
+                            int64_t out[6]);
 
 /* Multi-GPU halo exchange (replaces send/recv xv, rho, gradient tasks,
  * scheduler.c:977-988,1088-1112). `nccl_comm` is an ncclComm_t created by the

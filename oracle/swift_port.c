@@ -1228,10 +1228,26 @@ port_t *port_create(const swiftgpu_config *cfg, const swiftgpu_step *step,
     s->rho[p] = RD(float, L->rho, p);
     s->time_bin[p] = RD(signed char, L->time_bin, p);
     s->depth_h[p] = RD(signed char, L->depth_h, p);
+    /* The density/force union holds the force members of the last step the
+     * particle was active in: that is what an INACTIVE neighbour contributes
+     * to the force loop (functions_hydro.h:1757-1849). */
+    s->f[p] = RD(float, L->f, p);
+    s->P[p] = RD(float, PORT_SCHEME == SCH_GADGET2 ? L->P_over_rho2 : L->pressure, p);
+    s->cs[p] = RD(float, L->soundspeed, p);
+    s->balsara[p] = RD(float, L->balsara, p);
+    s->v_sig[p] = RD(float, L->v_sig, p);
+    s->h_dt[p] = RD(float, L->h_dt, p);
+    for (int k = 0; k < 3; k++) s->a[3 * p + k] = RD(float, L->a_hydro + 4 * k, p);
+    s->u_dt[p] = RD(float, PORT_SCHEME == SCH_GADGET2 ? L->entropy_dt : L->u_dt, p);
+    s->min_ngb[p] = RD(signed char, L->min_ngb_time_bin, p);
 #if PORT_SCHEME == SCH_SPHENIX
     s->alpha[p] = RD(float, L->visc_alpha, p);
     s->alpha_diff[p] = RD(float, L->diff_alpha, p);
     s->div_v_prev[p] = RD(float, L->div_v_previous_step, p);
+    s->div_v[p] = RD(float, L->div_v, p);
+    s->div_v_dt[p] = RD(float, L->div_v_dt, p);
+    s->laplace_u[p] = RD(float, L->laplace_u, p);
+    s->alpha_max_ngb[p] = RD(float, L->alpha_visc_max_ngb, p);
 #endif
   }
   return s;
@@ -1310,6 +1326,7 @@ void port_get_parts(const port_t *s, unsigned mask, void *parts_aos) {
   /* Once the ghost ran, the density/force union holds the force members. */
   const int force_valid = (mask & ~(unsigned)(SWIFTGPU_PHASE_SORT | SWIFTGPU_PHASE_DENSITY)) != 0;
   for (long long p = 0; p < s->n; p++) {
+    if (!part_active(s, p)) continue; /* inactive particles are read-only */
     WR(float, L->h, p) = s->h[p];
     WR(float, L->rho, p) = s->rho[p];
     WR(signed char, L->depth_h, p) = s->depth_h[p];

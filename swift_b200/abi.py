@@ -89,6 +89,7 @@ class Stats(C.Structure):
         ("ms_end_force", C.c_double),
         ("n_density", C.c_int64), ("n_gradient", C.c_int64),
         ("n_force", C.c_int64), ("n_launches", C.c_int64),
+        ("t_density", C.c_int64), ("t_gradient", C.c_int64), ("t_force", C.c_int64),
         ("ghost_iterations", C.c_int32), ("ghost_unconverged", C.c_int32),
     ]
 
@@ -119,6 +120,7 @@ EXPORTS = [
     ("swiftgpu_upload_parts", C.c_int, [VP, VP, I64]),
     ("swiftgpu_upload_parts_device", C.c_int, [VP, VP, I64]),
     ("swiftgpu_set_step", C.c_int, [VP, C.POINTER(Step)]),
+    ("swiftgpu_set_stream", C.c_int, [VP, VP]),
     ("swiftgpu_run_sort", C.c_int, [VP]),
     ("swiftgpu_run_density", C.c_int, [VP]),
     ("swiftgpu_run_ghost", C.c_int, [VP]),
@@ -132,6 +134,7 @@ EXPORTS = [
     ("swiftgpu_download_cells", C.c_int, [VP, VP, I32]),
     ("swiftgpu_download_counts", C.c_int, [VP, VP, VP, VP, I64]),
     ("swiftgpu_get_stats", C.c_int, [VP, C.POINTER(Stats)]),
+    ("swiftgpu_worklist_stats", C.c_int, [C.POINTER(Config), C.POINTER(Step), VP, I32, VP, I32, C.c_int, VP]),
     ("swiftgpu_halo_setup", C.c_int, [VP, VP]),
     ("swiftgpu_halo_exchange", C.c_int, [VP, C.c_int]),
 ]

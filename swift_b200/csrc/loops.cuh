@@ -90,6 +90,7 @@ struct LoopArgs {
   int32_t *f_minngb;
   int32_t *count; /* per-particle directed interaction counter of this loop */
   unsigned long long *total; /* global interaction counter */
+  unsigned long long *tests; /* global distance-test counter */
   double dim[3];
   float a2_Hubble;
   int max_active_bin;
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
   gacc.laplace_u = 0.f;
   gacc.alpha_max = 0.f;
   int nhit = 0;
+  int nchunks = 0;
 
   for (int it = 0; it < G.item_count; it++) {
     const Item I = A.items[G.item_first + it];
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
       }
 
       /* ---- test ---- */
+      nchunks++;
       unsigned mask = 0u;
       if (!dbl_mode) {
 #pragma unroll 8
@@ -432,6 +435,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL_MASK, tot, o);
   if (lane == 0 && tot) atomicAdd(A.total, (unsigned long long)tot);
+  if (lane == 0 && nchunks) atomicAdd(A.tests, (unsigned long long)nchunks * 1024ull);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -492,6 +496,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
   acc.v_sig = 0.f;
   acc.min_ngb = NUM_TIME_BINS + 1;
   int nhit = 0;
+  int nchunks = 0;
 
   for (int it = 0; it < G.item_count; it++) {
     const Item I = A.items[G.item_first + it];
@@ -526,6 +531,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
         }
         T.idx[lane] = sj;
         __syncwarp();
+        nchunks++;
         unsigned mask = 0u;
 #pragma unroll 4
         for (int q = 0; q < 32; q++) {
@@ -674,6 +680,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
         }
       }
 
+      nchunks++;
       unsigned mask = 0u;
 #pragma unroll 4
       for (int q = 0; q < 32; q++) {
@@ -736,6 +743,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL_MASK, tot, o);
   if (lane == 0 && tot) atomicAdd(A.total, (unsigned long long)tot);
+  if (lane == 0 && nchunks) atomicAdd(A.tests, (unsigned long long)nchunks * 1024ull);
 }
 
 }  // namespace swiftgpu

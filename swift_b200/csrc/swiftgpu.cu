@@ -104,6 +104,7 @@ struct swiftgpu_handle {
   uint32_t phases_done = 0;
 
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   swiftgpu_stats stats;
 
@@ -782,15 +783,16 @@ extern "C" int swiftgpu_init(swiftgpu_t **out, const swiftgpu_config *cfg) {
   H *h = new H();
   h->cfg = *cfg;
   memset(&h->stats, 0, sizeof(h->stats));
-  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreate(&h->stream) != cudaSuccess ||
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreate(&h->own_stream) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
-      cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&h->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&h->d_flag, sizeof(int32_t)) != cudaSuccess) {
     g_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
     delete h;
     return 2;
   }
-  cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
+  h->stream = h->own_stream;
+  cudaMemset(h->d_counters, 0, 16 * sizeof(unsigned long long));
   *out = h;
   return 0;
 }
@@ -816,7 +818,7 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   cudaFree(h->d_flag); cudaFree(h->d_force_bits);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
 
@@ -828,6 +830,14 @@ extern "C" int swiftgpu_set_step(swiftgpu_t *h, const swiftgpu_step *step) {
     h->lists_built = false; /* activity changed: the worklists depend on it */
   h->step = *step;
   h->has_step = 1;
+  return 0;
+}
+
+extern "C" int swiftgpu_set_stream(swiftgpu_t *h, void *cuda_stream) {
+  if (!h) return 1;
+  cudaSetDevice(h->cfg.device);
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
   return 0;
 }
 
@@ -1142,6 +1152,7 @@ static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
   A.fo1 = h->fo1; A.f_hdt = h->f_hdt; A.f_vsig = h->f_vsig; A.f_minngb = h->f_minngb;
   A.count = count;
   A.total = h->d_counters + counter;
+  A.tests = h->d_counters + 8 + counter;
   for (int k = 0; k < 3; k++) A.dim[k] = h->cfg.dim[k];
   A.a2_Hubble = h->step.a * h->step.a * h->step.H;
   A.max_active_bin = h->step.max_active_bin;
@@ -1179,6 +1190,7 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
                                                                   h->step.max_active_bin, h->cfg.scheme);
   h->stats.n_launches++;
   CK(cudaMemsetAsync(h->d_counters + 0, 0, sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->d_counters + 8, 0, sizeof(unsigned long long), h->stream));
   if (build_targets(h, h->L_density)) return 1;
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->nd, 0);
@@ -1192,6 +1204,7 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
                                 SWIFTGPU_PHASE_EXTRA_GHOST | SWIFTGPU_PHASE_FORCE |
                                 SWIFTGPU_PHASE_END_FORCE);
   if (phase_end(h, &h->stats.ms_density)) return 1;
+  if (read_counter(h, 8, &h->stats.t_density)) return 1;
   return read_counter(h, 0, &h->stats.n_density);
 }
 
@@ -1282,6 +1295,7 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   if (!(h->phases_done & SWIFTGPU_PHASE_GHOST)) return h->fail("run_gradient before run_ghost");
   if (phase_begin(h)) return 1;
   CK(cudaMemsetAsync(h->d_counters + 1, 0, sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->ng, 1);
     k_loop1<LOOP_GRADIENT><<<(A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK,
@@ -1291,6 +1305,7 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   }
   h->phases_done |= SWIFTGPU_PHASE_GRADIENT;
   if (phase_end(h, &h->stats.ms_gradient)) return 1;
+  if (read_counter(h, 9, &h->stats.t_gradient)) return 1;
   return read_counter(h, 1, &h->stats.n_gradient);
 }
 
@@ -1379,6 +1394,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
     }
   }
   CK(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(unsigned long long), h->stream));
   if (build_targets(h, h->L_force)) return 1;
   if (h->L_force.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_force, h->nf, 2);
@@ -1393,6 +1409,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   }
   h->phases_done |= SWIFTGPU_PHASE_FORCE;
   if (phase_end(h, &h->stats.ms_force)) return 1;
+  if (read_counter(h, 10, &h->stats.t_force)) return 1;
   return read_counter(h, 2, &h->stats.n_force);
 }
 
@@ -1485,6 +1502,33 @@ extern "C" int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density, int32
 extern "C" int swiftgpu_get_stats(swiftgpu_t *h, swiftgpu_stats *out) {
   if (!h || !out) return 1;
   *out = h->stats;
+  return 0;
+}
+
+extern "C" int swiftgpu_worklist_stats(const swiftgpu_config *cfg, const swiftgpu_step *step,
+                                       const swiftgpu_cell *cells, int32_t ncells,
+                                       const int32_t *top, int32_t ntop, int loop,
+                                       int64_t out[6]) {
+  if (!cfg || !step || !cells || !top || !out || ncells <= 0 || ntop <= 0) return 1;
+  Flattener F(cells, ncells, top, ntop, cfg->dim, cfg->periodic, cfg->rank, step->ti_current);
+  WorkList W;
+  if (loop == 3) {
+    std::vector<int32_t> aux;
+    F.build_subset(W, aux);
+  } else if (loop == 0 || loop == 1 || loop == 2) {
+    F.build_loop(loop, W);
+  } else {
+    return 1;
+  }
+  for (int k = 0; k < 6; k++) out[k] = 0;
+  out[0] = (int64_t)W.items.size();
+  out[1] = (int64_t)W.groups.size();
+  out[3] = (int64_t)W.sort_requests.size();
+  for (const Item &it : W.items) {
+    out[2] += (int64_t)cells[it.tcell].count * cells[it.scell].count;
+    if (it.mode == MODE_SELF || it.mode == MODE_SUB_SELF) out[4]++;
+    if (it.min_depth > 0 || it.max_depth < 127) out[5]++;
+  }
   return 0;
 }
 

@@ -52,6 +52,10 @@ class SwiftGPU:
     def set_step(self, step):
         self._ck(self.lib.swiftgpu_set_step(self.h, C.byref(step)), "set_step")
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ck(self.lib.swiftgpu_set_stream(self.h, cuda_stream), "set_stream")
+
     def run_sort(self):
         self._ck(self.lib.swiftgpu_run_sort(self.h), "run_sort")
 

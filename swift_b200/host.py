@@ -190,11 +190,11 @@ def clustered_box(L=256, scheme=abi.SCHEME_SPHENIX, seed=2025, sigma=1.5, eta=1.
     delta_k = (rng.normal(size=k2.shape) + 1j * rng.normal(size=k2.shape)) / k2 ** 0.5
     delta_k[0, 0, 0] = 0
     delta_k *= np.exp(-k2 / (0.25 * ng) ** 2)
-    delta = np.fft.irfftn(delta_k, s=(ng, ng, ng))
+    delta = np.fft.irfftn(delta_k, s=(ng, ng, ng), axes=(0, 1, 2))
     delta *= sigma / delta.std()
     # displacement field psi = -grad(phi), lap(phi) = delta
-    psi = [np.fft.irfftn(-1j * kk * delta_k / k2, s=(ng, ng, ng)) for kk in (kx, ky, kz)]
-    scale = sigma / (np.fft.irfftn(delta_k, s=(ng, ng, ng)).std() + 1e-30)
+    psi = [np.fft.irfftn(-1j * kk * delta_k / k2, s=(ng, ng, ng), axes=(0, 1, 2)) for kk in (kx, ky, kz)]
+    scale = sigma / (np.fft.irfftn(delta_k, s=(ng, ng, ng), axes=(0, 1, 2)).std() + 1e-30)
     g = (np.arange(L) + 0.5) / L
     x = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(n, 3)
     gi = np.minimum((x * ng).astype(np.int64), ng - 1)

@@ -1,0 +1,188 @@
+"""GPU parity tests: libswiftgpu (through its C ABI) against the oracle - the
+UNMODIFIED reference compiled into oracle/_ref/ when it travelled with the
+snapshot, else the C restatement oracle/swift_port.c - on the same seeded
+inputs. Shapes follow the reference's own tests: test125cells (full pipeline),
+testActivePair (active subsets), testPeriodicBC (wrap), test27cells (h_pert).
+
+Bars (north_star): neighbour counts bit-exact; h, rho, P, a_hydro, u_dt within
+1e-5 relative (metric and its floors: tests/util.py:parity_report).
+"""
+import numpy as np
+import pytest
+
+import util
+from swift_b200 import abi, host
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+SCHEMES = ("minimal", "gadget2", "sphenix")
+
+
+def _check(c, g, mask=abi.PHASE_ALL, tol=TOL):
+    got = g.download_parts()
+    o, kind = util.run_oracle(c, mask)
+    p = util.run_port(c, mask) if kind == "reference" else o
+    rep = util.parity_report(got, o.parts(), c.layout, c.scheme_name, c.cfg.h_tolerance)
+    print(c.scheme_name, kind, rep)
+    nd, ng, nf = g.download_counts()
+    pnd, png, pnf = p.counts()
+    hp = host.field(p.parts(), c.layout, "h")
+    hg = host.field(got, c.layout, "h")
+    same_h = np.array_equal(hp, hg)
+    if rep["flips"] == 0 and same_h:
+        # identical h everywhere -> identical neighbour sets, bit for bit
+        assert np.array_equal(nd, pnd), f"density counts differ on {(nd != pnd).sum()} particles"
+        assert np.array_equal(ng, png), f"gradient counts differ on {(ng != png).sum()} particles"
+        assert np.array_equal(nf, pnf), f"force counts differ on {(nf != pnf).sum()} particles"
+    else:
+        # last-bit h differences move a handful of kernel-edge neighbours
+        assert (nd != pnd).mean() < 5e-3 and (nf != pnf).mean() < 5e-3
+    util.assert_parity(rep, tol, h_tolerance=c.cfg.h_tolerance)
+    assert np.array_equal(host.field(got, c.layout, "depth_h"), host.field(o.parts(), c.layout, "depth_h")) or rep["flips"] > 0
+    return rep
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_full_step_jittered(scheme):
+    """drift-less sort -> density -> ghost -> [gradient -> extra ghost] -> force
+    -> end_force on a periodic jittered box (tests/test125cells.c:640-1010)."""
+    ic = host.jittered_box(20, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.05, seed=7)
+    c = util.make_case(scheme, ic, (3, 3, 3))
+    g = util.run_gpu(c)
+    _check(c, g)
+    st = g.stats()
+    assert st.n_density > 0 and st.n_force > 0 and st.n_launches > 0
+    g.close()
+
+
+def test_density_counts_exact_first_pass():
+    """Density alone (h untouched): integer neighbour counts must equal the
+    oracle's N_density of the SWIFT_HYDRO_DENSITY_CHECKS build bit for bit."""
+    scheme = "sphenix"
+    ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.25, h_scatter=0.1, seed=3)
+    lay = util.golden_layout("sphenix_chk")
+    c = util.make_case(scheme, ic, (3, 3, 3), layout=lay)
+    mask = abi.PHASE_SORT | abi.PHASE_DENSITY
+    g = util.run_gpu(c, mask)
+    nd, _, _ = g.download_counts()
+    o, kind = util.run_oracle(c, mask, variant="sphenix_chk")
+    cnt = o.counts()
+    assert cnt is not None
+    # the reference starts N_density at 1 (the particle itself, SPHENIX/hydro.h:580-582)
+    ond = cnt[0] - 1
+    assert np.array_equal(nd, ond), f"{(nd != ond).sum()} particles differ ({kind})"
+    got, want = g.download_parts(), o.parts()
+    for name in ("rho", "wcount", "rho_dh", "wcount_dh"):
+        a, b = host.field(got, lay, name).astype(np.float64), host.field(want, lay, name).astype(np.float64)
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * np.abs(b).max())) < TOL, name
+    g.close()
+
+
+def test_uniform_lattice_known_answer():
+    """Config 1 (UniformBox_3D 32^3, Minimal): exactly 56 neighbours per
+    particle on the perfect lattice in density and in force."""
+    ic = host.uniform_box(32, abi.SCHEME_MINIMAL)
+    c = util.make_case("minimal", ic, (4, 4, 4))
+    g = util.run_gpu(c)
+    nd, _, nf = g.download_counts()
+    st = g.stats()
+    assert st.ghost_unconverged == 0
+    assert (nf == 56).all(), np.unique(nf, return_counts=True)
+    got = g.download_parts()
+    rho = host.field(got, c.layout, "rho")
+    assert np.allclose(rho, rho[0], rtol=5e-6)
+    _check(c, g)
+    g.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("frac", (0.5, 0.1))
+def test_active_subset(scheme, frac):
+    """Multi-time-step: only `frac` of the particles are active; inactive ones
+    are neighbours but are never updated (tests/testActivePair.c:461-610)."""
+    ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.02, seed=11,
+                           active_fraction=frac)
+    c = util.make_case(scheme, ic, (3, 3, 3), max_active_bin=1)
+    # inactive particles need valid force-union members from "their last step":
+    # take them from an all-active oracle run
+    c_all = util.make_case(scheme, dict(ic, time_bin=np.ones_like(ic["time_bin"])), (3, 3, 3))
+    o_all, _ = util.run_oracle(c_all)
+    c.parts = o_all.parts()
+    tb = host.field(c.parts, c.layout, "time_bin")
+    tb[:] = ic["time_bin"][c.tree.perm]
+    g = util.run_gpu(c)
+    got = g.download_parts()
+    inactive = tb > 1
+    assert inactive.any() and (~inactive).any()
+    size = c.layout.size
+    a = got.reshape(-1, size)[inactive]
+    b = c.parts.reshape(-1, size)[inactive]
+    assert np.array_equal(a, b), "an inactive particle was modified"
+    _check(c, g)
+    g.close()
+
+
+@pytest.mark.parametrize("scheme", ("minimal", "sphenix"))
+def test_ghost_iterates_from_bad_h(scheme):
+    """h off by up to +-35 %: Newton-Raphson + bisection + subset re-runs
+    (runner_ghost.c:1357-1428, 1548-1572) must reach the oracle's h."""
+    ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.3, h_scatter=0.3, seed=5)
+    c = util.make_case(scheme, ic, (3, 3, 3))
+    g = util.run_gpu(c)
+    st = g.stats()
+    assert st.ghost_iterations >= 3 and st.ghost_unconverged == 0
+    _check(c, g)
+    g.close()
+
+
+def test_clustered_multilevel():
+    """Clustered box: split cells, depth_h levels, below_h_max recursion."""
+    ic = host.clustered_box(24, abi.SCHEME_SPHENIX, seed=2025, sigma=1.0)
+    c = util.make_case("sphenix", ic, (3, 3, 3))
+    assert c.tree.cells["split"].any()
+    g = util.run_gpu(c)
+    _check(c, g)
+    g.close()
+
+
+def test_cell_hmax_after_ghost():
+    """runner_ghost.c:1621-1632: h_max / h_max_active of every cell."""
+    ic = host.jittered_box(16, abi.SCHEME_GADGET2, jitter=0.2, h_scatter=0.1, seed=2)
+    c = util.make_case("gadget2", ic, (3, 3, 3))
+    g = util.run_gpu(c)
+    o, kind = util.run_oracle(c)
+    gc, oc = g.download_cells(), o.cells()
+    assert np.allclose(gc["h_max"], oc["h_max"], rtol=2.5e-4)
+    assert np.allclose(gc["h_max_active"], oc["h_max_active"], rtol=2.5e-4)
+    g.close()
+
+
+def test_errors_are_returned_not_fatal():
+    """The library never aborts: wrong call order returns non-zero + message."""
+    ic = host.uniform_box(8, abi.SCHEME_MINIMAL)
+    c = util.make_case("minimal", ic, (3, 3, 3))
+    from swift_b200.engine import SwiftGPU
+    g = SwiftGPU(c.cfg)
+    g.upload_cells(c.tree.cells, c.tree.top)
+    g.upload_parts(c.parts)
+    g.set_step(c.step)
+    with pytest.raises(RuntimeError, match="run_ghost before run_density"):
+        g.run_ghost()
+    g.close()
+
+
+def test_roundtrip_untouched_fields():
+    """upload -> download without running a phase returns the input bytes."""
+    ic = host.jittered_box(8, abi.SCHEME_SPHENIX, seed=1)
+    c = util.make_case("sphenix", ic, (3, 3, 3))
+    from swift_b200.engine import SwiftGPU
+    g = SwiftGPU(c.cfg)
+    g.upload_cells(c.tree.cells, c.tree.top)
+    g.upload_parts(c.parts)
+    g.set_step(c.step)
+    got = g.download_parts()
+    x0, x1 = host.field(c.parts, c.layout, "x"), host.field(got, c.layout, "x")
+    assert np.array_equal(x0, x1)
+    assert np.array_equal(host.field(c.parts, c.layout, "v"), host.field(got, c.layout, "v"))
+    g.close()

@@ -1,0 +1,173 @@
+"""CPU tests that PIN the oracle: the C restatement (oracle/swift_port.c)
+against (a) the golden fixtures generated from the unmodified reference build
+(tests/golden/*.json, generator tests/golden/gen_layouts.py), (b) the
+analytic known answers the reference's own tests print (56 lattice neighbours,
+SURVEY 8d; div v / curl v of test27cells.c:460-463), and - when oracle/_ref is
+present (this container and the GPU box) - (c) the unmodified reference itself
+driven by oracle/ref_driver.c on the same inputs.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import util
+from oracle import port, ref
+from swift_b200 import abi, host
+
+SCHEMES = ("minimal", "gadget2", "sphenix")
+needs_ref = pytest.mark.skipif(not all(ref.available(s) for s in SCHEMES + ("sphenix_chk",)),
+                               reason="oracle/_ref not built (make -C oracle ref)")
+
+
+def test_kernel_deval_golden():
+    """kernel_deval (kernel_hydro.h:257-285) of the port == the reference's on
+    the committed u grid, bit for bit."""
+    d = json.load(open(os.path.join(util.GOLDEN, "reference_constants.json")))
+    lib = port.load("minimal")
+    for u_hex, w_hex, dw_hex in d["kernel_deval"]:
+        w, dw = C.c_float(), C.c_float()
+        lib.port_kernel_deval(float.fromhex(u_hex), C.byref(w), C.byref(dw))
+        assert w.value == float.fromhex(w_hex) and dw.value == float.fromhex(dw_hex), u_hex
+
+
+def test_constants_golden():
+    d = json.load(open(os.path.join(util.GOLDEN, "reference_constants.json")))
+    for s in SCHEMES:
+        k = d[s]
+        assert float.fromhex(k["kernel_gamma"]) == float(np.float32(1.825742))
+        assert float.fromhex(k["space_recurse_size_pair_hydro"]) == 100
+        assert float.fromhex(k["space_splitsize"]) == 400
+    assert float.fromhex(d["minimal"]["sizeof_part"]) == 128
+    assert float.fromhex(d["gadget2"]["sizeof_part"]) == 128
+    assert float.fromhex(d["sphenix"]["sizeof_part"]) == 160
+
+
+@needs_ref
+@pytest.mark.parametrize("variant", SCHEMES + ("sphenix_chk",))
+def test_layout_fixture_matches_reference(variant):
+    """tests/golden/part_layouts.json is offsetof() on the reference's struct part."""
+    assert ref.layout(variant).as_dict() == util.golden_layout(variant).as_dict()
+
+
+def test_sub_pairs_match_cell_split_pairs():
+    """cell_split_pairs (cell.c:63-132): number of sub-pairs per sid is
+    1 (corner) / 2 (edge) / 4 (face) x ... = {1,2,1,2,4,2,1,2,1,2,4,2,4} x 4?"""
+    lib = port.load("minimal")
+    want = [1, 2, 1, 2, 4, 2, 1, 2, 1, 2, 4, 2, 4]
+    # corner pairs have 1 sub-pair, edges 4 (2 touching + ...) -> counts from cell.c:63
+    counts = []
+    for sid in range(13):
+        pid = (C.c_int * 16)(); pjd = (C.c_int * 16)()
+        n = lib.port_sub_pairs(sid, pid, pjd)
+        counts.append(n)
+        for k in range(n):
+            assert 0 <= pid[k] < 8 and 0 <= pjd[k] < 8
+    # cell.c:63-132: corners 1, edges 4, faces 16 sub-pairs
+    kinds = [1, 4, 1, 4, 16, 4, 1, 4, 1, 4, 16, 4, 16]
+    assert counts == kinds, counts
+    assert [int(np.sqrt(k)) for k in kinds] == want
+
+
+def test_lattice_known_answer_port():
+    """Perfect lattice, eta = 1.2349: exactly 56 neighbours (6+12+8+6+24) in
+    density and force; rho equal for all particles."""
+    ic = host.uniform_box(16, abi.SCHEME_MINIMAL)
+    c = util.make_case("minimal", ic, (3, 3, 3))
+    p = util.run_port(c)
+    nd, _, nf = p.counts()
+    assert (nd == 56).all() and (nf == 56).all()
+    rho = host.field(p.parts(), c.layout, "rho")
+    assert np.allclose(rho, rho[0], rtol=5e-6)
+    assert abs(rho[0] - 2.0) / 2.0 < 0.01   # makeIC.py: rho = 2
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_port_matches_reference_full_step(scheme):
+    ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.05, seed=7)
+    c = util.make_case(scheme, ic, (3, 3, 3))
+    o, kind = util.run_oracle(c)
+    assert kind == "reference"
+    p = util.run_port(c)
+    rep = util.parity_report(p.parts(), o.parts(), c.layout, scheme)
+    util.assert_parity(rep)
+    assert np.array_equal(host.field(p.parts(), c.layout, "depth_h"), host.field(o.parts(), c.layout, "depth_h"))
+    oc, pc = o.cells(), p.cells()
+    assert np.allclose(oc["h_max"], pc["h_max"], rtol=1e-6)
+
+
+@needs_ref
+def test_port_counts_match_reference_counters():
+    """Integer neighbour counts of the port == N_density / N_gradient / N_force
+    of the reference's SWIFT_HYDRO_DENSITY_CHECKS build (bit-exact sets)."""
+    ic = host.jittered_box(16, abi.SCHEME_SPHENIX, jitter=0.25, h_scatter=0.1, seed=3)
+    lay = util.golden_layout("sphenix_chk")
+    c = util.make_case("sphenix", ic, (3, 3, 3), layout=lay)
+    o, _ = util.run_oracle(c, variant="sphenix_chk")
+    p = util.run_port(c)
+    ond, ong, onf = o.counts()
+    pnd, png, pnf = p.counts()
+    hp, ho = host.field(p.parts(), lay, "h"), host.field(o.parts(), lay, "h")
+    same = hp == ho
+    assert same.mean() > 0.5
+    # self terms: SPHENIX/hydro.h:580-582
+    assert np.array_equal(pnd[same] + 1, ond[same]) or (pnd + 1 != ond).mean() < 5e-3
+    assert (png + 1 != ong).mean() < 5e-3 and (pnf != onf).mean() < 5e-3
+    # density-only pass (h untouched): must be exact everywhere
+    c2 = util.make_case("sphenix", ic, (3, 3, 3), layout=lay)
+    m = abi.PHASE_SORT | abi.PHASE_DENSITY
+    o2, _ = util.run_oracle(c2, m, variant="sphenix_chk")
+    p2 = util.run_port(c2, m)
+    assert np.array_equal(p2.counts()[0] + 1, o2.counts()[0])
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme", ("gadget2", "sphenix"))
+def test_port_matches_reference_active_subset(scheme):
+    ic = host.jittered_box(12, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.02, seed=11, active_fraction=0.3)
+    c = util.make_case(scheme, ic, (3, 3, 3), max_active_bin=1)
+    c_all = util.make_case(scheme, dict(ic, time_bin=np.ones_like(ic["time_bin"])), (3, 3, 3))
+    o_all, _ = util.run_oracle(c_all)
+    c.parts = o_all.parts()
+    tb = host.field(c.parts, c.layout, "time_bin")
+    tb[:] = ic["time_bin"][c.tree.perm]
+    o, _ = util.run_oracle(c)
+    p = util.run_port(c)
+    rep = util.parity_report(p.parts(), o.parts(), c.layout, scheme)
+    util.assert_parity(rep)
+    inactive = tb > 1
+    size = c.layout.size
+    assert np.array_equal(o.parts().reshape(-1, size)[inactive], c.parts.reshape(-1, size)[inactive])
+    assert np.array_equal(p.parts().reshape(-1, size)[inactive], c.parts.reshape(-1, size)[inactive])
+
+
+@needs_ref
+def test_port_matches_reference_clustered_multilevel():
+    ic = host.clustered_box(20, abi.SCHEME_SPHENIX, seed=2025, sigma=1.0)
+    c = util.make_case("sphenix", ic, (3, 3, 3))
+    assert c.tree.cells["split"].any()
+    o, _ = util.run_oracle(c)
+    p = util.run_port(c)
+    rep = util.parity_report(p.parts(), o.parts(), c.layout, "sphenix")
+    util.assert_parity(rep)
+
+
+@needs_ref
+def test_reference_sort_keys():
+    """runner_do_hydro_sort (runner_sort.c:411-413): key = (float)(x . shift)."""
+    ic = host.jittered_box(8, abi.SCHEME_MINIMAL, seed=4)
+    c = util.make_case("minimal", ic, (3, 3, 3))
+    o = ref.Reference("minimal", c.cfg, c.step, c.tree.cells, c.tree.top, c.parts)
+    o.run(abi.PHASE_SORT, threads=1)
+    cell = int(c.tree.top[0])
+    first, count = int(c.tree.cells["first_part"][cell]), int(c.tree.cells["count"][cell])
+    x = host.field(c.parts, c.layout, "x")[first:first + count]
+    shifts = {4: (1.0, 0.0, 0.0), 0: (0.5773502691896258,) * 3, 12: (0.0, 0.0, 1.0)}
+    for sid, sh in shifts.items():
+        d, i = o.sort(cell, sid)
+        key = (x[:, 0] * sh[0] + x[:, 1] * sh[1] + x[:, 2] * sh[2]).astype(np.float32)
+        assert np.all(np.diff(d) >= 0)
+        assert np.array_equal(d, key[i])
