@@ -91,6 +91,7 @@ struct swiftgpu_handle {
   int8_t *time_bin = nullptr, *depth_h = nullptr;
   int32_t *f_minngb = nullptr, *nd = nullptr, *ng = nullptr, *nf = nullptr;
   uint32_t *sort_idx = nullptr;
+  float *d_sort_keys = nullptr; /* key scratch, only when a requested segment exceeds SORT_SMEM_MAX */
   int64_t sort_total = 0;
   SortSeg *d_segs = nullptr;
   int nsegs = 0;
@@ -814,7 +815,7 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   cudaSetDevice(h->cfg.device);
   free_parts(h);
   h->L_density.release(); h->L_subset.release(); h->L_force.release();
-  cudaFree(h->d_cells); cudaFree(h->d_cells_init); cudaFree(h->d_dmin); cudaFree(h->d_dxp); cudaFree(h->sort_idx); cudaFree(h->d_segs); cudaFree(h->d_counters);
+  cudaFree(h->d_cells); cudaFree(h->d_cells_init); cudaFree(h->d_dmin); cudaFree(h->d_dxp); cudaFree(h->sort_idx); cudaFree(h->d_sort_keys); cudaFree(h->d_segs); cudaFree(h->d_counters);
   cudaFree(h->d_flag); cudaFree(h->d_force_bits);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1016,9 +1017,12 @@ static int build_lists(H *h, bool force_only) {
     h->sort_idx = nullptr;
     CK(cudaMalloc((void **)&h->sort_idx, std::max<int64_t>(off, 1) * sizeof(uint32_t)));
     h->sort_total = off;
+    cudaFree(h->d_sort_keys);
+    h->d_sort_keys = nullptr;
   }
+  if (max_seg > SORT_SMEM_MAX && !h->d_sort_keys)
+    CK(cudaMalloc((void **)&h->d_sort_keys, std::max<int64_t>(off, 1) * sizeof(float)));
   h->sorted = false;
-  (void)max_seg;
 
   if (!force_only) {
     if (upload_list(h, Wd, h->L_density, false)) return 1;
@@ -1110,24 +1114,19 @@ static int phase_end(H *h, double *ms_out) {
   return 0;
 }
 
+static int launch_sort(H *h) {
+  if (h->nsegs > 0) {
+    k_sort<<<h->nsegs, 256, 0, h->stream>>>(h->d_segs, h->d_cells, h->x, h->sort_idx, h->d_sort_keys);
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
 extern "C" int swiftgpu_run_sort(swiftgpu_t *h) {
   if (!h) return 1;
   if (phase_begin(h)) return 1;
-  if (h->nsegs > 0) {
-    /* segments larger than the shared-memory sorter need a key scratch */
-    float *gkeys = nullptr;
-    bool need = false;
-    for (const swiftgpu_cell &c : h->cells)
-      if (c.count > SORT_SMEM_MAX) need = true; /* conservative: any big cell */
-    if (need) CK(cudaMalloc((void **)&gkeys, sizeof(float) * std::max<int64_t>(h->sort_total, 1)));
-    k_sort<<<h->nsegs, 256, 0, h->stream>>>(h->d_segs, h->d_cells, h->x, h->sort_idx, gkeys);
-    h->stats.n_launches++;
-    CK(cudaGetLastError());
-    if (need) {
-      CK(cudaStreamSynchronize(h->stream));
-      cudaFree(gkeys);
-    }
-  }
+  if (launch_sort(h)) return 1;
   h->sorted = true;
   h->phases_done |= SWIFTGPU_PHASE_SORT;
   return phase_end(h, &h->stats.ms_sort);
@@ -1379,17 +1378,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
       }
       if (rc) return 1;
       /* new (cell, sid) segments may exist: sort again */
-      if (h->nsegs > 0) {
-        float *gkeys = nullptr;
-        bool big = false;
-        for (const swiftgpu_cell &c : h->cells)
-          if (c.count > SORT_SMEM_MAX) big = true;
-        if (big) CK(cudaMalloc((void **)&gkeys, sizeof(float) * std::max<int64_t>(h->sort_total, 1)));
-        k_sort<<<h->nsegs, 256, 0, h->stream>>>(h->d_segs, h->d_cells, h->x, h->sort_idx, gkeys);
-        h->stats.n_launches++;
-        CK(cudaStreamSynchronize(h->stream));
-        cudaFree(gkeys);
-      }
+      if (launch_sort(h)) return 1;
       h->sorted = true;
     }
   }
