@@ -2,26 +2,40 @@
  * loops.cuh - the neighbour-loop kernels (K1/K2/K3 of SURVEY 2.1).
  *
  * One warp owns up to 32 TARGET particles of one target cell (a "task") and
- * walks every directed item of that cell's group (worklist.hpp). Per item it
- * streams the SOURCE cell in chunks of 32 particles through a warp-private
- * shared-memory tile (positions already converted to the item's float frame,
- * plus the sort key), and every lane tests its own target against the 32
- * staged sources with the reference's exact arithmetic, recording hits in a
- * 32-bit mask. The hits are then drained lane-parallel with the (FMA) non-
- * symmetric interaction; accumulators stay in registers for the whole group
- * and are flushed once per task (no atomics in the inner loop).
+ * walks every directed item of that cell's group (worklist.hpp). The work is
+ * split in two phases so that both run at full SIMT efficiency:
  *
- * Pseudo-Verlet pruning: pair items stream the source cell in sorted-axis
- * order and stop as soon as the first key of a chunk is beyond the reach of
- * every lane (a warp max / min taken with shuffles); inside a chunk the
- * reference's `sort_j[pjd].d < di` test is a single float compare against a
- * per-lane threshold rounded towards +inf (equivalent for float keys).
+ *  TEST   The source cells of the items are streamed, in sorted-axis order, in
+ *         chunks of 32 particles into a warp-private shared-memory tile that
+ *         SPANS ITEMS (up to SCAP slots). Every lane tests its own target
+ *         against the 32 freshly staged sources with a cheap conservative
+ *         prefilter (FMA r2 against an inflated h^2 gamma^2, broadcast LDS,
+ *         ~9 instructions per pair) and appends the slot numbers of the
+ *         candidates to its private hit list in shared memory. Pseudo-Verlet
+ *         pruning: a chunk whose first sort key is beyond the reach of every
+ *         lane (warp max/min by shuffles) ends the item.
+ *
+ *  INTERACT  When the tile or a list is full (and at the end of the task) the
+ *         lists are drained lane-parallel: lane t pops its k-th candidate,
+ *         re-evaluates the reference's EXACT arithmetic for that pair (frame
+ *         positions from doubles, un-fused r2, sorted-axis key conditions) and
+ *         applies the non-symmetric interaction. Because a drain covers many
+ *         items, lanes hold similar numbers of candidates (mean/max ~0.75
+ *         instead of ~0.3 when draining per 32-source chunk).
+ *
+ * Accumulators stay in registers for the whole task and are flushed once (no
+ * atomics in the inner loops).
  *
  * Reference semantics reproduced (runner_doiact_functions_hydro.h):
  *   MODE_SELF      DOSELF1 :2299 / DOSELF2 :2624   dx = (float)(x_t - x_s) on doubles
  *   MODE_PAIR_L/R  DOPAIR1 :1234 / DOPAIR2 :1601   floats in the frame cj->loc (+shift)
  *   MODE_SUB_SELF  DOSELF_SUBSET :1108             floats relative to c->loc
  *   MODE_SUB_PAIR  DOPAIR_SUBSET :855              (float)((x_t - shift) - x_s) on doubles
+ * Both dx forms are evaluated by ONE branch-free expression in the drain:
+ *   dx = (float)((x_t - ot) - xs_d) - xs_f
+ * with (ot, xs_d, xs_f) = (frame origin, 0, staged frame float) for the float
+ * modes and (shift or 0, source double, 0) for the double modes; subtracting
+ * an exact zero does not round, so both reproduce the reference bit for bit.
  */
 #ifndef SWIFTGPU_LOOPS_CUH
 #define SWIFTGPU_LOOPS_CUH
@@ -32,9 +46,8 @@
 namespace swiftgpu {
 
 #define FULL_MASK 0xffffffffu
-#define WARPS_PER_BLOCK 4
 
-/* Device view of one cell (64 bytes). */
+/* Device view of one cell (72 bytes). */
 struct DevCell {
   double loc[3];
   int32_t first;
@@ -49,7 +62,7 @@ struct DevCell {
   uint16_t sort_mask; /* which sids are present */
   int8_t depth;
   uint8_t flags; /* bit0 active, bit1 local, bit2 split */
-  int32_t pad_;
+  float width;   /* max_k width[k] */
 };
 static_assert(sizeof(DevCell) == 72, "DevCell layout");
 
@@ -96,19 +109,6 @@ struct LoopArgs {
   int max_active_bin;
 };
 
-/* warp-private staging tile */
-struct __align__(16) SrcTile {
-  float4 pos[32];   /* frame floats + key (float modes) */
-  double xd[32][3]; /* absolute / shifted doubles (double modes) */
-  float4 f0[32];    /* (m, vx, vy, vz) */
-  float4 f1[32];    /* loop-dependent source fields */
-  float4 f2[32];
-  float4 f3[32];
-  double dB[32];    /* force pass-B threshold of the source */
-  double dA[32];    /* force: di of the source (MODE_PAIR_R) */
-  int32_t idx[32];
-};
-
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
@@ -135,28 +135,110 @@ __device__ __forceinline__ void atomic_max_pos(float *addr, float v) {
   atomicMax((int *)addr, __float_as_int(v));
 }
 
+/* Relative inflation of the prefilter radius^2: covers the difference between
+ * the fused r2 of the prefilter and the reference's un-fused r2 (~2^-22). */
+#define PREFILTER_REL 1.00001f
+#define LCAP 96 /* hit-list capacity per lane */
+
+/* What the drain needs to know about a staged chunk of 32 slots. */
+struct __align__(16) ChunkInfo {
+  double ot[3]; /* subtracted from the target's double position */
+  int32_t dbl;  /* 1: dx from doubles (MODE_SELF, MODE_SUB_PAIR*) */
+  int32_t item; /* index into the item array (force: pair constants) */
+};
+
+/* Type-2 (force) chunks also carry the constants of their pair item
+ * (DOPAIR2 :1601-1735), so that the drain does not have to re-derive them. */
+struct __align__(16) ChunkInfoF {
+  double ot[3];
+  double rshift, hi_max_g, hj_max_g, dx_max, di_max_sh, dj_min;
+  int32_t dbl;   /* 1: MODE_SELF */
+  int32_t sid;   /* bit 8: targets are in the left cell (MODE_PAIR_L) */
+};
+
+/* Shared-memory tile of one warp. NP = payload float4 per source. */
+template <int SCAP, int NP, bool STAGE_D, bool KEYS, typename CIT>
+struct Tile {
+  static constexpr int kF = 0;
+  static constexpr int kP = kF + SCAP * 16;
+  static constexpr int kGI = kP + NP * SCAP * 16;
+  static constexpr int kK = kGI + SCAP * 4;
+  static constexpr int kD = kK + (KEYS ? SCAP * 4 : 0);
+  static constexpr int kList = kD + (STAGE_D ? SCAP * 24 : 0);
+  static constexpr int kChunk = kList + LCAP * 32 * 2;
+  static constexpr int kBytes = kChunk + (SCAP / 32) * (int)sizeof(CIT);
+  char *base;
+  __device__ __forceinline__ float4 *F() const { return (float4 *)(base + kF); }
+  __device__ __forceinline__ float4 *P(int k) const { return (float4 *)(base + kP) + k * SCAP; }
+  __device__ __forceinline__ int32_t *GI() const { return (int32_t *)(base + kGI); }
+  __device__ __forceinline__ float *K() const { return (float *)(base + kK); }
+  __device__ __forceinline__ double *D() const { return (double *)(base + kD); }
+  __device__ __forceinline__ uint16_t *list() const { return (uint16_t *)(base + kList); }
+  __device__ __forceinline__ CIT *chunk() const { return (CIT *)(base + kChunk); }
+};
+
+/* The prefilter over one freshly staged chunk: lane-private target against 32
+ * broadcast sources. KC: 0 no key condition, 1 key < thr, 2 key > thr,
+ * 3 type-2 (radius^2 = max(target, source)). */
+template <int KC>
+__device__ __forceinline__ void test_chunk(const float4 *__restrict__ F, int nst, float tpx,
+                                           float tpy, float tpz, float r2e, float thr,
+                                           uint16_t *&lp, int &nlist) {
+  unsigned mask = 0u;
+#pragma unroll
+  for (int qq = 0; qq < 32; qq += 8) {
+    float4 s[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s[j] = F[nst + qq + j];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float dx = tpx - s[j].x, dy = tpy - s[j].y, dz = tpz - s[j].z;
+      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      bool ok;
+      if (KC == 3)
+        ok = r2 < fmaxf(r2e, s[j].w);
+      else
+        ok = r2 < r2e;
+      if (KC == 1) ok = ok && (s[j].w < thr);
+      if (KC == 2) ok = ok && (s[j].w > thr);
+      if (ok) mask |= 1u << (qq + j);
+    }
+  }
+  /* decode the (sparse) mask into the lane's hit list */
+  while (mask) {
+    const int q = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    *lp = (uint16_t)(nst + q);
+    lp += 32;
+    nlist++;
+  }
+}
+
 /* ------------------------------------------------------------------------ */
-/* Type-1 loops: density (all schemes), gradient (SPHENIX), and the density
- * subset re-runs of the ghost. Hit criterion r2 < h_t^2 gamma^2.            */
+/* Type-1 loops: density (all schemes), gradient (SPHENIX), and (SUBSET) the  */
+/* density re-runs of the ghost. Hit criterion r2 < h_t^2 gamma^2.            */
 /* ------------------------------------------------------------------------ */
-template <int LOOP>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
-    k_loop1(const LoopArgs A) {
-  __shared__ SrcTile tiles[WARPS_PER_BLOCK];
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int task = blockIdx.x * WARPS_PER_BLOCK + wib;
-  if (task >= A.ntasks) return;
-  SrcTile &T = tiles[wib];
+#define SCAP1 384
+template <int LOOP, bool SUBSET>
+struct Tile1 : Tile<SCAP1, (LOOP == LOOP_GRADIENT ? 2 : 1), SUBSET, false, ChunkInfo> {};
+
+template <int LOOP, bool SUBSET>
+__global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
+  extern __shared__ __align__(16) char smem_raw[];
+  typedef Tile1<LOOP, SUBSET> TT;
+  TT T;
+  T.base = smem_raw;
+  const int lane = threadIdx.x;
+  const int task = blockIdx.x;
 
   const int g = A.task_group[task];
   const int chunk = A.task_chunk[task];
   const int nt = A.tgt_count[g];
   if (chunk * 32 >= nt) return;
   const Group G = A.groups[g];
-  const int slot = chunk * 32 + lane;
-  const bool tvalid = slot < nt;
-  const int ti = tvalid ? A.tgt_list[A.tgt_first[g] + slot] : -1;
+  const int slot_t = chunk * 32 + lane;
+  const bool tvalid = slot_t < nt;
+  const int ti = tvalid ? A.tgt_list[A.tgt_first[g] + slot_t] : -1;
 
   /* target state */
   double tx = 0., ty = 0., tz = 0.;
@@ -191,6 +273,62 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
   int nhit = 0;
   int nchunks = 0;
 
+  /* tile state */
+  int nst = 0;   /* staged slots */
+  int nlist = 0; /* lane-private number of queued candidates */
+  uint16_t *const list0 = T.list() + lane;
+  uint16_t *lp = list0;
+
+  /* ---- INTERACT: drain the hit lists ---- */
+  auto drain = [&]() {
+    __syncwarp();
+    const int maxn = __reduce_max_sync(FULL_MASK, nlist);
+    const float4 *F = T.F();
+    const int32_t *GI = T.GI();
+    const ChunkInfo *CI = T.chunk();
+    for (int k = 0; k < maxn; k++) {
+      const bool act = k < nlist;
+      const int slot = act ? (int)list0[k * 32] : 0;
+      const ChunkInfo ci = CI[slot >> 5];
+      const int gi = GI[slot];
+      const float4 s = F[slot];
+      const bool dbl = ci.dbl != 0;
+      double sxd = 0., syd = 0., szd = 0.;
+      if (act && dbl) {
+        if (SUBSET) {
+          const double *D = T.D();
+          sxd = D[slot];
+          syd = D[SCAP1 + slot];
+          szd = D[2 * SCAP1 + slot];
+        } else {
+          sxd = A.x[3 * (size_t)gi];
+          syd = A.x[3 * (size_t)gi + 1];
+          szd = A.x[3 * (size_t)gi + 2];
+        }
+      }
+      const float spx = dbl ? 0.f : s.x, spy = dbl ? 0.f : s.y, spz = dbl ? 0.f : s.z;
+      const float dx = __fsub_rn(dsubf(__dsub_rn(tx, ci.ot[0]), sxd), spx);
+      const float dy = __fsub_rn(dsubf(__dsub_rn(ty, ci.ot[1]), syd), spy);
+      const float dz = __fsub_rn(dsubf(__dsub_rn(tz, ci.ot[2]), szd), spz);
+      const float r2 = r2_exact(dx, dy, dz);
+      if (act && (r2 < thg2) && (gi != ti)) {
+        const float4 f0 = T.P(0)[slot];
+        if (LOOP == LOOP_DENSITY) {
+          iact_density(dacc, r2, dx, dy, dz, th_inv, tvx, tvy, tvz, f0.x, f0.y, f0.z, f0.w);
+        } else {
+          const float4 f1 = T.P(1)[slot];
+          iact_gradient(gacc, r2, dx, dy, dz, th, tvx, tvy, tvz, tu, tcs, f0.x, f0.y, f0.z, f0.w,
+                        f1.x, f1.y, f1.z, f1.w, A.a2_Hubble);
+        }
+        nhit++;
+      }
+    }
+    nlist = 0;
+    nst = 0;
+    lp = list0;
+    __syncwarp();
+  };
+
   for (int it = 0; it < G.item_count; it++) {
     const Item I = A.items[G.item_first + it];
     const DevCell sc = A.cells[I.scell];
@@ -200,11 +338,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 
     /* per-lane participation and frame */
     bool part = tvalid && tdepth >= I.min_depth && tdepth <= I.max_depth;
-    float tpx = 0.f, tpy = 0.f, tpz = 0.f; /* float-frame position */
-    double tdx = tx, tdy = ty, tdz = tz;   /* double position (minus shift) */
+    float tpx = 0.f, tpy = 0.f, tpz = 0.f; /* prefilter position of the target */
     float thr = 0.f;                       /* pruning threshold on the source key */
     bool ascending = true;
-    double fsx = 0., fsy = 0., fsz = 0.; /* frame origin of the sources */
+    double fsx = 0., fsy = 0., fsz = 0.; /* frame origin of the staged source floats */
+    double otx = 0., oty = 0., otz = 0.; /* subtracted from the target double in the drain */
     const bool dbl_mode = (mode == MODE_SELF || mode == MODE_SUB_PAIR || mode == MODE_SUB_PAIR_F);
     const bool sorted = (mode == MODE_PAIR_L || mode == MODE_PAIR_R || mode == MODE_SUB_PAIR ||
                          mode == MODE_SUB_PAIR_F);
@@ -212,6 +350,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
                  shz = I.shift[2] * A.dim[2];
     int64_t soff = 0;
     if (sorted) soff = sort_offset(sc, sid);
+    float r2e = __fmul_rn(thg2, PREFILTER_REL);
 
     if (mode == MODE_PAIR_L || mode == MODE_PAIR_R) {
       /* oriented pair: ci = left cell, cj = right cell */
@@ -239,9 +378,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
         const double di = __dsub_rn((double)__fadd_rn(__fadd_rn(tkey, thg), dx_max), rshift);
         part = part && in_loop && !(di < dj_min);
         thr = __double2float_ru(di); /* key < di  <=>  key < ru(di) for float keys */
-        tpx = dsubf(tx, oix);
-        tpy = dsubf(ty, oiy);
-        tpz = dsubf(tz, oiz);
+        otx = oix;
+        oty = oiy;
+        otz = oiz;
         fsx = cj.loc[0];
         fsy = cj.loc[1];
         fsz = cj.loc[2];
@@ -257,53 +396,64 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
         const double dj = __dadd_rn((double)__fsub_rn(__fsub_rn(tkey, thg), dx_max), rshift);
         part = part && in_loop && !(__dsub_rn(dj, rshift) > di_max);
         thr = __double2float_rd(dj); /* key > dj  <=>  key > rd(dj) */
-        tpx = dsubf(tx, cj.loc[0]);
-        tpy = dsubf(ty, cj.loc[1]);
-        tpz = dsubf(tz, cj.loc[2]);
+        otx = cj.loc[0];
+        oty = cj.loc[1];
+        otz = cj.loc[2];
         fsx = oix;
         fsy = oiy;
         fsz = oiz;
         ascending = false;
       }
+      tpx = dsubf(tx, otx);
+      tpy = dsubf(ty, oty);
+      tpz = dsubf(tz, otz);
     } else if (mode == MODE_SUB_SELF) {
       /* DOSELF_SUBSET :1127-1129: floats relative to c->loc (c = scell) */
-      tpx = dsubf(tx, sc.loc[0]);
-      tpy = dsubf(ty, sc.loc[1]);
-      tpz = dsubf(tz, sc.loc[2]);
+      otx = fsx = sc.loc[0];
+      oty = fsy = sc.loc[1];
+      otz = fsz = sc.loc[2];
+      tpx = dsubf(tx, otx);
+      tpy = dsubf(ty, oty);
+      tpz = dsubf(tz, otz);
+    } else {
+      /* Double modes. MODE_SELF: dx = (float)(x_t - x_s). MODE_SUB_PAIR*:
+       * (float)((x_t - shift) - x_s), DOPAIR_SUBSET :885-897 / :955-967. The
+       * prefilter works on floats relative to the source cell; its radius is
+       * widened by the rounding of those floats. */
+      if (mode != MODE_SELF) {
+        otx = shx;
+        oty = shy;
+        otz = shz;
+      }
+      const double tdx = __dsub_rn(tx, otx), tdy = __dsub_rn(ty, oty), tdz = __dsub_rn(tz, otz);
       fsx = sc.loc[0];
       fsy = sc.loc[1];
       fsz = sc.loc[2];
-    } else if (mode == MODE_SUB_PAIR || mode == MODE_SUB_PAIR_F) {
-      /* DOPAIR_SUBSET :885-897 / :955-967 */
-      tdx = __dsub_rn(tx, shx);
-      tdy = __dsub_rn(ty, shy);
-      tdz = __dsub_rn(tz, shz);
-      const double proj = __dadd_rn(
-          __dadd_rn(__dmul_rn(tdx, c_runner_shift[sid][0]), __dmul_rn(tdy, c_runner_shift[sid][1])),
-          __dmul_rn(tdz, c_runner_shift[sid][2]));
-      /* di = hi*kernel_gamma + dxj + pix*rs0 + piy*rs1 + piz*rs2, left to right */
-      double di;
-      const float dxj = sc.dx_max_sort;
-      if (mode == MODE_SUB_PAIR) {
-        const float f0 = __fadd_rn(thg, dxj);
-        di = __dadd_rn(__dadd_rn(__dadd_rn((double)f0, __dmul_rn(tdx, c_runner_shift[sid][0])),
-                                 __dmul_rn(tdy, c_runner_shift[sid][1])),
-                       __dmul_rn(tdz, c_runner_shift[sid][2]));
-        thr = __double2float_ru(di);
-        ascending = true;
-      } else {
-        const float f0 = __fsub_rn(-thg, dxj);
-        di = __dadd_rn(__dadd_rn(__dadd_rn((double)f0, __dmul_rn(tdx, c_runner_shift[sid][0])),
-                                 __dmul_rn(tdy, c_runner_shift[sid][1])),
-                       __dmul_rn(tdz, c_runner_shift[sid][2]));
-        thr = __double2float_rd(di);
-        ascending = false;
+      tpx = dsubf(tdx, fsx);
+      tpy = dsubf(tdy, fsy);
+      tpz = dsubf(tdz, fsz);
+      const float re = fmaf(thg, PREFILTER_REL, 4.0e-6f * sc.width);
+      r2e = re * re;
+      if (mode != MODE_SELF) {
+        /* di = hi*kernel_gamma + dxj + pix*rs0 + piy*rs1 + piz*rs2, left to right */
+        const float dxj = sc.dx_max_sort;
+        const float f0 = (mode == MODE_SUB_PAIR) ? __fadd_rn(thg, dxj) : __fsub_rn(-thg, dxj);
+        const double di =
+            __dadd_rn(__dadd_rn(__dadd_rn((double)f0, __dmul_rn(tdx, c_runner_shift[sid][0])),
+                                __dmul_rn(tdy, c_runner_shift[sid][1])),
+                      __dmul_rn(tdz, c_runner_shift[sid][2]));
+        if (mode == MODE_SUB_PAIR) {
+          thr = __double2float_ru(di);
+          ascending = true;
+        } else {
+          thr = __double2float_rd(di);
+          ascending = false;
+        }
       }
-      (void)proj;
     }
 
     if (!__any_sync(FULL_MASK, part)) continue;
-    const float my_hg2 = part ? thg2 : -1.f;
+    if (!part) tpx = 3.0e30f; /* never passes the prefilter */
     /* reach of the warp along the axis, for the sorted early exit */
     float reach = 0.f;
     if (sorted) reach = ascending ? warp_max(part ? thr : -3.0e38f) : warp_min(part ? thr : 3.0e38f);
@@ -313,102 +463,65 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
       const int k = base + lane;
       int sj = -1;
       float skey = ascending ? 3.0e38f : -3.0e38f; /* padding never passes the prune */
-      __syncwarp();
+      double sx = 0., sy = 0., sz = 0.;
       if (k < scount) {
         int local = k;
         if (sorted) local = (int)A.sort_idx[soff + (ascending ? k : scount - 1 - k)];
         sj = sc.first + local;
-        const double sx = A.x[3 * (size_t)sj], sy = A.x[3 * (size_t)sj + 1],
-                     sz = A.x[3 * (size_t)sj + 2];
+        sx = A.x[3 * (size_t)sj];
+        sy = A.x[3 * (size_t)sj + 1];
+        sz = A.x[3 * (size_t)sj + 2];
         if (sorted) skey = sort_key(sx, sy, sz, sid);
-        if (dbl_mode) {
-          T.xd[lane][0] = sx;
-          T.xd[lane][1] = sy;
-          T.xd[lane][2] = sz;
-          T.pos[lane] = make_float4(0.f, 0.f, 0.f, skey);
-        } else {
-          T.pos[lane] = make_float4(dsubf(sx, fsx), dsubf(sy, fsy), dsubf(sz, fsz), skey);
-        }
-        T.f0[lane] = A.mv[sj];
+      }
+      /* sorted early exit: first key of the chunk already out of everyone's reach */
+      if (sorted) {
+        const float first_key = __shfl_sync(FULL_MASK, skey, 0);
+        if (ascending ? !(first_key < reach) : !(first_key > reach)) break;
+      }
+      if (nst + 32 > SCAP1 || __any_sync(FULL_MASK, nlist > LCAP - 32)) drain();
+      const int slot = nst + lane;
+      if (k < scount) {
+        T.F()[slot] = make_float4(dsubf(sx, fsx), dsubf(sy, fsy), dsubf(sz, fsz), skey);
+        T.P(0)[slot] = A.mv[sj];
         if (LOOP == LOOP_GRADIENT) {
           const float4 q1 = A.fq1[sj];
           const float4 q2 = A.fq2[sj];
           const float4 q3 = A.fq3[sj];
-          T.f1[lane] = make_float4(q2.z /*u*/, q1.x /*rho*/, q1.w /*cs*/, q3.x /*alpha*/);
+          T.P(1)[slot] = make_float4(q2.z /*u*/, q1.x /*rho*/, q1.w /*cs*/, q3.x /*alpha*/);
+        }
+        if (SUBSET) {
+          double *D = T.D();
+          D[slot] = sx;
+          D[SCAP1 + slot] = sy;
+          D[2 * SCAP1 + slot] = sz;
         }
       } else {
-        T.pos[lane] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, skey);
-        if (dbl_mode) T.xd[lane][0] = T.xd[lane][1] = T.xd[lane][2] = 1.0e300;
+        T.F()[slot] = make_float4(-3.0e30f, -3.0e30f, -3.0e30f, skey);
       }
-      T.idx[lane] = sj;
+      T.GI()[slot] = sj;
+      if (lane == 0) {
+        ChunkInfo ci;
+        ci.ot[0] = otx;
+        ci.ot[1] = oty;
+        ci.ot[2] = otz;
+        ci.dbl = dbl_mode ? 1 : 0;
+        ci.item = G.item_first + it;
+        T.chunk()[nst >> 5] = ci;
+      }
       __syncwarp();
-
-      /* sorted early exit: first key of the chunk already out of everyone's reach */
-      if (sorted) {
-        const float first_key = T.pos[0].w;
-        if (ascending ? !(first_key < reach) : !(first_key > reach)) break;
-      }
 
       /* ---- test ---- */
       nchunks++;
-      unsigned mask = 0u;
-      if (!dbl_mode) {
-#pragma unroll 8
-        for (int q = 0; q < 32; q++) {
-          const float4 s = T.pos[q];
-          const float dx = __fsub_rn(tpx, s.x), dy = __fsub_rn(tpy, s.y), dz = __fsub_rn(tpz, s.z);
-          const float r2 = r2_exact(dx, dy, dz);
-          bool ok = r2 < my_hg2;
-          if (mode == MODE_PAIR_L) ok = ok && (s.w < thr);
-          if (mode == MODE_PAIR_R) ok = ok && (s.w > thr);
-          if (mode == MODE_SUB_SELF) ok = ok && (T.idx[q] != ti);
-          mask |= (ok ? 1u : 0u) << q;
-        }
-      } else {
-#pragma unroll 4
-        for (int q = 0; q < 32; q++) {
-          const float dx = dsubf(tdx, T.xd[q][0]), dy = dsubf(tdy, T.xd[q][1]),
-                      dz = dsubf(tdz, T.xd[q][2]);
-          const float r2 = r2_exact(dx, dy, dz);
-          bool ok = r2 < my_hg2;
-          const float key = T.pos[q].w;
-          if (mode == MODE_SELF) ok = ok && (T.idx[q] != ti) && (T.idx[q] >= 0);
-          if (mode == MODE_SUB_PAIR) ok = ok && (key < thr);
-          if (mode == MODE_SUB_PAIR_F) ok = ok && (key > thr);
-          mask |= (ok ? 1u : 0u) << q;
-        }
-      }
-
-      /* ---- drain ---- */
-      while (__any_sync(FULL_MASK, mask != 0u)) {
-        if (mask) {
-          const int q = __ffs(mask) - 1;
-          mask &= mask - 1u;
-          float dx, dy, dz;
-          if (!dbl_mode) {
-            const float4 s = T.pos[q];
-            dx = __fsub_rn(tpx, s.x);
-            dy = __fsub_rn(tpy, s.y);
-            dz = __fsub_rn(tpz, s.z);
-          } else {
-            dx = dsubf(tdx, T.xd[q][0]);
-            dy = dsubf(tdy, T.xd[q][1]);
-            dz = dsubf(tdz, T.xd[q][2]);
-          }
-          const float r2 = r2_exact(dx, dy, dz);
-          const float4 f0 = T.f0[q];
-          if (LOOP == LOOP_DENSITY) {
-            iact_density(dacc, r2, dx, dy, dz, th_inv, tvx, tvy, tvz, f0.x, f0.y, f0.z, f0.w);
-          } else {
-            const float4 f1 = T.f1[q];
-            iact_gradient(gacc, r2, dx, dy, dz, th, tvx, tvy, tvz, tu, tcs, f0.x, f0.y, f0.z, f0.w,
-                          f1.x, f1.y, f1.z, f1.w, A.a2_Hubble);
-          }
-          nhit++;
-        }
-      }
+      if (!sorted)
+        test_chunk<0>(T.F(), nst, tpx, tpy, tpz, r2e, thr, lp, nlist);
+      else if (ascending)
+        test_chunk<1>(T.F(), nst, tpx, tpy, tpz, r2e, thr, lp, nlist);
+      else
+        test_chunk<2>(T.F(), nst, tpx, tpy, tpz, r2e, thr, lp, nlist);
+      nst += 32;
     }
   }
+  drain();
 
   /* ---- flush (once per task) ---- */
   if (tvalid) {
@@ -442,26 +555,31 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 /* Type-2 loop: force. Hit criterion r2 < max(h_t, h_s)^2 gamma^2, with the
  * two-pass pruning of DOPAIR2 restated per (i in ci, j in cj):
  *   pass A (:1737-1975): i in A-range, key_j < di_i, r2 < hig2
- *   pass B (:1978-2230): j in B-range, key_i - rshift > dj_j, hig2 <= r2 < hjg2 */
+ *   pass B (:1978-2230): j in B-range, key_i - rshift > dj_j, hig2 <= r2 < hjg2
+ * The prefilter only applies the radius; the pass conditions (doubles) are
+ * evaluated per candidate in the drain.                                      */
 /* ------------------------------------------------------------------------ */
+#define SCAP2 256
 template <int SCHEME>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
-    k_loop2(const LoopArgs A) {
-  __shared__ SrcTile tiles[WARPS_PER_BLOCK];
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int task = blockIdx.x * WARPS_PER_BLOCK + wib;
-  if (task >= A.ntasks) return;
-  SrcTile &T = tiles[wib];
+struct Tile2 : Tile<SCAP2, (SCHEME == SCH_SPHENIX ? 4 : 3), false, true, ChunkInfoF> {};
+
+template <int SCHEME>
+__global__ void __launch_bounds__(32) k_loop2(const LoopArgs A) {
+  extern __shared__ __align__(16) char smem_raw[];
+  typedef Tile2<SCHEME> TT;
+  TT T;
+  T.base = smem_raw;
+  const int lane = threadIdx.x;
+  const int task = blockIdx.x;
 
   const int g = A.task_group[task];
   const int chunk = A.task_chunk[task];
   const int nt = A.tgt_count[g];
   if (chunk * 32 >= nt) return;
   const Group G = A.groups[g];
-  const int slot = chunk * 32 + lane;
-  const bool tvalid = slot < nt;
-  const int ti = tvalid ? A.tgt_list[A.tgt_first[g] + slot] : -1;
+  const int slot_t = chunk * 32 + lane;
+  const bool tvalid = slot_t < nt;
+  const int ti = tvalid ? A.tgt_list[A.tgt_first[g] + slot_t] : -1;
 
   double tx = 0., ty = 0., tz = 0.;
   ForceQ tq;
@@ -498,6 +616,103 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
   int nhit = 0;
   int nchunks = 0;
 
+  int nst = 0;
+  int nlist = 0;
+  uint16_t *const list0 = T.list() + lane;
+  uint16_t *lp = list0;
+
+  /* ---- INTERACT ---- */
+  auto drain = [&]() {
+    __syncwarp();
+    const int maxn = __reduce_max_sync(FULL_MASK, nlist);
+    const float4 *F = T.F();
+    const int32_t *GI = T.GI();
+    const float *K = T.K();
+    const ChunkInfoF *CI = T.chunk();
+    for (int k = 0; k < maxn; k++) {
+      const bool act = k < nlist;
+      const int slot = act ? (int)list0[k * 32] : 0;
+      const ChunkInfoF ci = CI[slot >> 5];
+      const int gi = GI[slot];
+      const float4 s = F[slot];
+      const bool dbl = ci.dbl != 0;
+      double sxd = 0., syd = 0., szd = 0.;
+      if (act && dbl) {
+        sxd = A.x[3 * (size_t)gi];
+        syd = A.x[3 * (size_t)gi + 1];
+        szd = A.x[3 * (size_t)gi + 2];
+      }
+      const float spx = dbl ? 0.f : s.x, spy = dbl ? 0.f : s.y, spz = dbl ? 0.f : s.z;
+      const float dx = __fsub_rn(dsubf(__dsub_rn(tx, ci.ot[0]), sxd), spx);
+      const float dy = __fsub_rn(dsubf(__dsub_rn(ty, ci.ot[1]), syd), spy);
+      const float dz = __fsub_rn(dsubf(__dsub_rn(tz, ci.ot[2]), szd), spz);
+      const float r2 = r2_exact(dx, dy, dz);
+      const float4 q2 = T.P(2)[slot];
+      const float sh = q2.y;
+      const float shg2 = hg2_exact(sh);
+      bool ok;
+      if (dbl) {
+        /* DOSELF2 :2792: doi = r2 < hig2 || r2 < hjg2 */
+        ok = (r2 < thg2 || r2 < shg2) && (gi != ti);
+      } else {
+        /* DOPAIR2: the pair constants of the item */
+        const bool tleft = (ci.sid & 256) != 0;
+        const int sid = ci.sid & 255;
+        const double rshift = ci.rshift, hi_max_g = ci.hi_max_g, hj_max_g = ci.hj_max_g,
+                     dx_max = ci.dx_max, di_max_sh = ci.di_max_sh, dj_min = ci.dj_min;
+        const float tkey = sort_key(tx, ty, tz, sid);
+        const float skey = K[slot];
+        const float shg = __fmul_rn(sh, KERNEL_GAMMA);
+        if (tleft) {
+          /* t = i in ci, s = j in cj */
+          const bool inA =
+              __dsub_rn(__dadd_rn(__dadd_rn((double)tkey, hi_max_g), dx_max), rshift) > dj_min;
+          const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(tkey, thg), dx_max), rshift);
+          const double t_di = (inA && !(di < dj_min)) ? di : -1.0e300;
+          const double t_keysh = __dsub_rn((double)tkey, rshift);
+          const bool inB = __dsub_rn(__dsub_rn((double)skey, hj_max_g), dx_max) < di_max_sh;
+          const double dj = __dsub_rn((double)__fsub_rn(skey, shg), dx_max);
+          const double s_dj = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
+          const bool c1 = ((double)skey < t_di) && (r2 < thg2);
+          const bool c2 = (t_keysh > s_dj) && (r2 < shg2) && !(r2 < thg2);
+          ok = c1 || c2;
+        } else {
+          /* t = j in cj, s = i in ci */
+          const bool inB = __dsub_rn(__dsub_rn((double)tkey, hj_max_g), dx_max) < di_max_sh;
+          const double dj = __dsub_rn((double)__fsub_rn(tkey, thg), dx_max);
+          const double t_dj = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
+          const bool inA =
+              __dsub_rn(__dadd_rn(__dadd_rn((double)skey, hi_max_g), dx_max), rshift) > dj_min;
+          const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(skey, shg), dx_max), rshift);
+          const double s_di = (inA && !(di < dj_min)) ? di : -1.0e300;
+          const double s_keysh = __dsub_rn((double)skey, rshift);
+          const bool c1 = ((double)tkey < s_di) && (r2 < shg2);
+          const bool c2 = (s_keysh > t_dj) && (r2 < thg2) && !(r2 < shg2);
+          ok = c1 || c2;
+        }
+      }
+      if (act && ok) {
+        ForceQ sq;
+        const float4 q0 = T.P(0)[slot], q1 = T.P(1)[slot];
+        sq.m = q0.x; sq.vx = q0.y; sq.vy = q0.z; sq.vz = q0.w;
+        sq.rho = q1.x; sq.P = q1.y; sq.f = q1.z; sq.cs = q1.w;
+        sq.balsara = q2.x; sq.h = q2.y; sq.u = q2.z; sq.time_bin = __float_as_int(q2.w);
+        sq.alpha_visc = sq.alpha_diff = 0.f;
+        if (SCHEME == SCH_SPHENIX) {
+          const float4 q3 = T.P(3)[slot];
+          sq.alpha_visc = q3.x;
+          sq.alpha_diff = q3.y;
+        }
+        iact_force<SCHEME>(acc, r2, dx, dy, dz, tq, sq, A.a2_Hubble);
+        nhit++;
+      }
+    }
+    nlist = 0;
+    nst = 0;
+    lp = list0;
+    __syncwarp();
+  };
+
   for (int it = 0; it < G.item_count; it++) {
     const Item I = A.items[G.item_first + it];
     const DevCell sc = A.cells[I.scell];
@@ -506,172 +721,107 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
     const int scount = sc.count;
     const bool part = tvalid && tdepth >= I.min_depth && tdepth <= I.max_depth;
     if (!__any_sync(FULL_MASK, part)) continue;
-    const float my_hg2 = part ? thg2 : -1.f;
+
+    float tpx, tpy, tpz;
+    float r2e = __fmul_rn(thg2, PREFILTER_REL);
+    double otx = 0., oty = 0., otz = 0.;
+    double fsx, fsy, fsz;
+    bool sorted = false, tleft = true;
+    double reach = 0., hi_max_g = 0., hj_max_g = 0., dx_max = 0., rshift = 0.;
+    double di_max_sh = 0., dj_min = 0.;
+    int64_t soff = 0;
+    float wadd = 0.f; /* widening of the source radius in the double mode */
 
     if (mode == MODE_SELF) {
-      /* DOSELF2 :2624-2875: doi = r2 < hig2 || r2 < hjg2 */
-      for (int base = 0; base < scount; base += 32) {
-        const int k = base + lane;
-        __syncwarp();
-        int sj = -1;
-        if (k < scount) {
-          sj = sc.first + k;
-          T.xd[lane][0] = A.x[3 * (size_t)sj];
-          T.xd[lane][1] = A.x[3 * (size_t)sj + 1];
-          T.xd[lane][2] = A.x[3 * (size_t)sj + 2];
-          const float4 q2 = A.fq2[sj];
-          T.f0[lane] = A.mv[sj];
-          T.f1[lane] = A.fq1[sj];
-          T.f2[lane] = q2;
-          if (SCHEME == SCH_SPHENIX) T.f3[lane] = A.fq3[sj];
-          T.pos[lane] = make_float4(0.f, 0.f, 0.f, hg2_exact(q2.y));
-        } else {
-          T.xd[lane][0] = T.xd[lane][1] = T.xd[lane][2] = 1.0e300;
-          T.pos[lane] = make_float4(0.f, 0.f, 0.f, -1.f);
-        }
-        T.idx[lane] = sj;
-        __syncwarp();
-        nchunks++;
-        unsigned mask = 0u;
-#pragma unroll 4
-        for (int q = 0; q < 32; q++) {
-          const float dx = dsubf(tx, T.xd[q][0]), dy = dsubf(ty, T.xd[q][1]),
-                      dz = dsubf(tz, T.xd[q][2]);
-          const float r2 = r2_exact(dx, dy, dz);
-          const float shg2 = T.pos[q].w;
-          const bool ok = part && (r2 < my_hg2 || r2 < shg2) && (T.idx[q] != ti) && (T.idx[q] >= 0);
-          mask |= (ok ? 1u : 0u) << q;
-        }
-        while (__any_sync(FULL_MASK, mask != 0u)) {
-          if (mask) {
-            const int q = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            const float dx = dsubf(tx, T.xd[q][0]), dy = dsubf(ty, T.xd[q][1]),
-                        dz = dsubf(tz, T.xd[q][2]);
-            const float r2 = r2_exact(dx, dy, dz);
-            ForceQ sq;
-            const float4 q0 = T.f0[q], q1 = T.f1[q], q2 = T.f2[q];
-            sq.m = q0.x; sq.vx = q0.y; sq.vy = q0.z; sq.vz = q0.w;
-            sq.rho = q1.x; sq.P = q1.y; sq.f = q1.z; sq.cs = q1.w;
-            sq.balsara = q2.x; sq.h = q2.y; sq.u = q2.z; sq.time_bin = __float_as_int(q2.w);
-            sq.alpha_visc = sq.alpha_diff = 0.f;
-            if (SCHEME == SCH_SPHENIX) {
-              const float4 q3 = T.f3[q];
-              sq.alpha_visc = q3.x;
-              sq.alpha_diff = q3.y;
-            }
-            iact_force<SCHEME>(acc, r2, dx, dy, dz, tq, sq, A.a2_Hubble);
-            nhit++;
-          }
-        }
+      /* DOSELF2 :2624-2875 */
+      fsx = sc.loc[0];
+      fsy = sc.loc[1];
+      fsz = sc.loc[2];
+      tpx = dsubf(tx, fsx);
+      tpy = dsubf(ty, fsy);
+      tpz = dsubf(tz, fsz);
+      wadd = 4.0e-6f * sc.width;
+      const float re = fmaf(thg, PREFILTER_REL, wadd);
+      r2e = re * re;
+    } else {
+      /* ---- DOPAIR2 ---- */
+      sorted = true;
+      const DevCell tc = A.cells[I.tcell];
+      tleft = (mode == MODE_PAIR_L);
+      const DevCell &ci = tleft ? tc : sc;
+      const DevCell &cj = tleft ? sc : tc;
+      const double shx = I.shift[0] * A.dim[0], shy = I.shift[1] * A.dim[1],
+                   shz = I.shift[2] * A.dim[2];
+      rshift = __dadd_rn(
+          __dadd_rn(__dmul_rn(shx, c_runner_shift[sid][0]), __dmul_rn(shy, c_runner_shift[sid][1])),
+          __dmul_rn(shz, c_runner_shift[sid][2]));
+      hi_max_g = __dmul_rn((double)ci.h_max, (double)KERNEL_GAMMA);
+      hj_max_g = __dmul_rn((double)cj.h_max, (double)KERNEL_GAMMA);
+      dx_max = (double)__fadd_rn(ci.dx_max_sort, cj.dx_max_sort);
+      const int64_t soff_i = sort_offset(ci, sid), soff_j = sort_offset(cj, sid);
+      const int i1 = ci.first + (int)A.sort_idx[soff_i + ci.count - 1];
+      const int j0 = cj.first + (int)A.sort_idx[soff_j];
+      const double di_max = (double)sort_key(A.x[3 * (size_t)i1], A.x[3 * (size_t)i1 + 1],
+                                             A.x[3 * (size_t)i1 + 2], sid);
+      dj_min = (double)sort_key(A.x[3 * (size_t)j0], A.x[3 * (size_t)j0 + 1],
+                                A.x[3 * (size_t)j0 + 2], sid);
+      di_max_sh = __dsub_rn(di_max, rshift);
+      const double oix = __dadd_rn(cj.loc[0], shx), oiy = __dadd_rn(cj.loc[1], shy),
+                   oiz = __dadd_rn(cj.loc[2], shz);
+      const float tkey = sort_key(tx, ty, tz, sid);
+      double t_di = -1.0e300, t_keysh = 0., t_dj = 1.0e300;
+      if (tleft) {
+        const bool inA =
+            __dsub_rn(__dadd_rn(__dadd_rn((double)tkey, hi_max_g), dx_max), rshift) > dj_min;
+        const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(tkey, thg), dx_max), rshift);
+        if (inA && !(di < dj_min)) t_di = di;
+        t_keysh = __dsub_rn((double)tkey, rshift);
+        otx = oix;
+        oty = oiy;
+        otz = oiz;
+        fsx = cj.loc[0];
+        fsy = cj.loc[1];
+        fsz = cj.loc[2];
+        /* sources j ascending; j can matter while key_j - hj_max*g - dx_max <= max(di, keysh) */
+        reach = warp_max_d(part ? fmax(t_di, t_keysh) : -1.0e300);
+        soff = soff_j;
+      } else {
+        const bool inB = __dsub_rn(__dsub_rn((double)tkey, hj_max_g), dx_max) < di_max_sh;
+        const double dj = __dsub_rn((double)__fsub_rn(tkey, thg), dx_max);
+        if (inB && !(dj > di_max_sh)) t_dj = dj;
+        otx = cj.loc[0];
+        oty = cj.loc[1];
+        otz = cj.loc[2];
+        fsx = oix;
+        fsy = oiy;
+        fsz = oiz;
+        /* sources i descending; i can matter while key_i + hi_max*g + dx_max - rshift >= min(key_t, dj) */
+        reach = warp_min_d(part ? fmin((double)tkey, t_dj) : 1.0e300);
+        soff = soff_i;
       }
-      continue;
+      tpx = dsubf(tx, otx);
+      tpy = dsubf(ty, oty);
+      tpz = dsubf(tz, otz);
     }
-
-    /* ---- DOPAIR2 ---- */
-    const DevCell tc = A.cells[I.tcell];
-    const bool tleft = (mode == MODE_PAIR_L);
-    const DevCell &ci = tleft ? tc : sc;
-    const DevCell &cj = tleft ? sc : tc;
-    const double shx = I.shift[0] * A.dim[0], shy = I.shift[1] * A.dim[1],
-                 shz = I.shift[2] * A.dim[2];
-    const double rshift = __dadd_rn(
-        __dadd_rn(__dmul_rn(shx, c_runner_shift[sid][0]), __dmul_rn(shy, c_runner_shift[sid][1])),
-        __dmul_rn(shz, c_runner_shift[sid][2]));
-    const double hi_max_g = __dmul_rn((double)ci.h_max, (double)KERNEL_GAMMA);
-    const double hj_max_g = __dmul_rn((double)cj.h_max, (double)KERNEL_GAMMA);
-    const double dx_max = (double)__fadd_rn(ci.dx_max_sort, cj.dx_max_sort);
-    const int64_t soff_i = sort_offset(ci, sid), soff_j = sort_offset(cj, sid);
-    const int i1 = ci.first + (int)A.sort_idx[soff_i + ci.count - 1];
-    const int j0 = cj.first + (int)A.sort_idx[soff_j];
-    const double di_max =
-        (double)sort_key(A.x[3 * (size_t)i1], A.x[3 * (size_t)i1 + 1], A.x[3 * (size_t)i1 + 2], sid);
-    const double dj_min =
-        (double)sort_key(A.x[3 * (size_t)j0], A.x[3 * (size_t)j0 + 1], A.x[3 * (size_t)j0 + 2], sid);
-    const double di_max_sh = __dsub_rn(di_max, rshift);
-    const double oix = __dadd_rn(cj.loc[0], shx), oiy = __dadd_rn(cj.loc[1], shy),
-                 oiz = __dadd_rn(cj.loc[2], shz);
-
-    /* Per-particle pruning values. For a particle p of ci:
-     *   okA, di(p) = (float)(key + h*gamma) + dx_max - rshift, keyA(p) = key - rshift
-     * for a particle p of cj:
-     *   okB, dj(p) = (float)(key - h*gamma) - dx_max                                  */
-    const float tkey = sort_key(tx, ty, tz, sid);
-    double t_di = -1.0e300, t_keysh = 0., t_dj = 1.0e300;
-    float tpx, tpy, tpz;
-    if (tleft) {
-      const bool inA =
-          __dsub_rn(__dadd_rn(__dadd_rn((double)tkey, hi_max_g), dx_max), rshift) > dj_min;
-      const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(tkey, thg), dx_max), rshift);
-      if (inA && !(di < dj_min)) t_di = di;
-      t_keysh = __dsub_rn((double)tkey, rshift);
-      tpx = dsubf(tx, oix);
-      tpy = dsubf(ty, oiy);
-      tpz = dsubf(tz, oiz);
-    } else {
-      const bool inB = __dsub_rn(__dsub_rn((double)tkey, hj_max_g), dx_max) < di_max_sh;
-      const double dj = __dsub_rn((double)__fsub_rn(tkey, thg), dx_max);
-      if (inB && !(dj > di_max_sh)) t_dj = dj;
-      tpx = dsubf(tx, cj.loc[0]);
-      tpy = dsubf(ty, cj.loc[1]);
-      tpz = dsubf(tz, cj.loc[2]);
-    }
-    /* Conservative reach along the axis for the sorted early exit. */
-    double reach;
-    if (tleft) {
-      /* sources j ascending; j can matter while key_j - hj_max*g - dx_max <= max(di, keysh) */
-      reach = warp_max_d(part ? fmax(t_di, t_keysh) : -1.0e300);
-    } else {
-      /* sources i descending; i can matter while key_i + hi_max*g + dx_max - rshift >= min(key_t, dj) */
-      reach = warp_min_d(part ? fmin((double)tkey, t_dj) : 1.0e300);
-    }
-    const int64_t soff = tleft ? soff_j : soff_i;
+    if (!part) tpx = 3.0e30f;
 
     for (int base = 0; base < scount; base += 32) {
       const int k = base + lane;
-      __syncwarp();
       int sj = -1;
       float skey = tleft ? 3.0e38f : -3.0e38f;
+      double sx = 0., sy = 0., sz = 0.;
       if (k < scount) {
-        const int local = (int)A.sort_idx[soff + (tleft ? k : scount - 1 - k)];
+        int local = k;
+        if (sorted) local = (int)A.sort_idx[soff + (tleft ? k : scount - 1 - k)];
         sj = sc.first + local;
-        const double sx = A.x[3 * (size_t)sj], sy = A.x[3 * (size_t)sj + 1],
-                     sz = A.x[3 * (size_t)sj + 2];
-        skey = sort_key(sx, sy, sz, sid);
-        const float4 q2 = A.fq2[sj];
-        const float sh = q2.y;
-        const float shg = __fmul_rn(sh, KERNEL_GAMMA);
-        if (tleft) {
-          /* source j in cj */
-          const bool inB = __dsub_rn(__dsub_rn((double)skey, hj_max_g), dx_max) < di_max_sh;
-          const double dj = __dsub_rn((double)__fsub_rn(skey, shg), dx_max);
-          T.dB[lane] = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
-          T.pos[lane] = make_float4(dsubf(sx, cj.loc[0]), dsubf(sy, cj.loc[1]), dsubf(sz, cj.loc[2]), skey);
-        } else {
-          /* source i in ci */
-          const bool inA =
-              __dsub_rn(__dadd_rn(__dadd_rn((double)skey, hi_max_g), dx_max), rshift) > dj_min;
-          const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(skey, shg), dx_max), rshift);
-          T.dA[lane] = (inA && !(di < dj_min)) ? di : -1.0e300;
-          T.dB[lane] = __dsub_rn((double)skey, rshift); /* keyA of the source */
-          T.pos[lane] = make_float4(dsubf(sx, oix), dsubf(sy, oiy), dsubf(sz, oiz), skey);
-        }
-        T.f0[lane] = A.mv[sj];
-        T.f1[lane] = A.fq1[sj];
-        T.f2[lane] = q2;
-        if (SCHEME == SCH_SPHENIX) T.f3[lane] = A.fq3[sj];
-      } else {
-        T.pos[lane] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, skey);
-        T.dB[lane] = tleft ? 1.0e300 : -1.0e300;
-        T.dA[lane] = -1.0e300;
-        T.f2[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sx = A.x[3 * (size_t)sj];
+        sy = A.x[3 * (size_t)sj + 1];
+        sz = A.x[3 * (size_t)sj + 2];
+        if (sorted) skey = sort_key(sx, sy, sz, sid);
       }
-      T.idx[lane] = sj;
-      __syncwarp();
-
-      /* early exit on the sorted axis (conservative, with a rounding slack) */
-      {
-        const double fk = (double)T.pos[0].w;
+      if (sorted) {
+        /* early exit on the sorted axis (conservative, with a rounding slack) */
+        const double fk = (double)__shfl_sync(FULL_MASK, skey, 0);
         const double slack = 1.0e-5 * (fabs(fk) + 1.0);
         if (tleft) {
           if (fk - hj_max_g - dx_max - slack > reach) break;
@@ -679,54 +829,52 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
           if (fk + hi_max_g + dx_max - rshift + slack < reach) break;
         }
       }
-
-      nchunks++;
-      unsigned mask = 0u;
-#pragma unroll 4
-      for (int q = 0; q < 32; q++) {
-        const float4 s = T.pos[q];
-        const float dx = __fsub_rn(tpx, s.x), dy = __fsub_rn(tpy, s.y), dz = __fsub_rn(tpz, s.z);
-        const float r2 = r2_exact(dx, dy, dz);
-        const float shg2 = hg2_exact(T.f2[q].y);
-        bool ok;
-        if (tleft) {
-          /* t = i in ci, s = j in cj */
-          const bool c1 = ((double)s.w < t_di) && (r2 < thg2);
-          const bool c2 = (t_keysh > T.dB[q]) && (r2 < shg2) && !(r2 < thg2);
-          ok = c1 || c2;
+      if (nst + 32 > SCAP2 || __any_sync(FULL_MASK, nlist > LCAP - 32)) drain();
+      const int slot = nst + lane;
+      if (k < scount) {
+        const float4 q2 = A.fq2[sj];
+        const float sh = q2.y;
+        float w;
+        if (sorted) {
+          w = __fmul_rn(hg2_exact(sh), PREFILTER_REL);
         } else {
-          /* t = j in cj, s = i in ci */
-          const bool c1 = ((double)tkey < T.dA[q]) && (r2 < shg2);
-          const bool c2 = (T.dB[q] > t_dj) && (r2 < thg2) && !(r2 < shg2);
-          ok = c1 || c2;
+          const float re = fmaf(__fmul_rn(sh, KERNEL_GAMMA), PREFILTER_REL, wadd);
+          w = re * re;
         }
-        ok = ok && part && (T.idx[q] >= 0);
-        mask |= (ok ? 1u : 0u) << q;
+        T.F()[slot] = make_float4(dsubf(sx, fsx), dsubf(sy, fsy), dsubf(sz, fsz), w);
+        T.K()[slot] = skey;
+        T.P(0)[slot] = A.mv[sj];
+        T.P(1)[slot] = A.fq1[sj];
+        T.P(2)[slot] = q2;
+        if (SCHEME == SCH_SPHENIX) T.P(3)[slot] = A.fq3[sj];
+      } else {
+        T.F()[slot] = make_float4(-3.0e30f, -3.0e30f, -3.0e30f, 0.f);
+        T.K()[slot] = skey;
+        T.P(2)[slot] = make_float4(0.f, 1.f, 0.f, 0.f);
       }
-      while (__any_sync(FULL_MASK, mask != 0u)) {
-        if (mask) {
-          const int q = __ffs(mask) - 1;
-          mask &= mask - 1u;
-          const float4 s = T.pos[q];
-          const float dx = __fsub_rn(tpx, s.x), dy = __fsub_rn(tpy, s.y), dz = __fsub_rn(tpz, s.z);
-          const float r2 = r2_exact(dx, dy, dz);
-          ForceQ sq;
-          const float4 q0 = T.f0[q], q1 = T.f1[q], q2 = T.f2[q];
-          sq.m = q0.x; sq.vx = q0.y; sq.vy = q0.z; sq.vz = q0.w;
-          sq.rho = q1.x; sq.P = q1.y; sq.f = q1.z; sq.cs = q1.w;
-          sq.balsara = q2.x; sq.h = q2.y; sq.u = q2.z; sq.time_bin = __float_as_int(q2.w);
-          sq.alpha_visc = sq.alpha_diff = 0.f;
-          if (SCHEME == SCH_SPHENIX) {
-            const float4 q3 = T.f3[q];
-            sq.alpha_visc = q3.x;
-            sq.alpha_diff = q3.y;
-          }
-          iact_force<SCHEME>(acc, r2, dx, dy, dz, tq, sq, A.a2_Hubble);
-          nhit++;
-        }
+      T.GI()[slot] = sj;
+      if (lane == 0) {
+        ChunkInfoF ci;
+        ci.ot[0] = otx;
+        ci.ot[1] = oty;
+        ci.ot[2] = otz;
+        ci.rshift = rshift;
+        ci.hi_max_g = hi_max_g;
+        ci.hj_max_g = hj_max_g;
+        ci.dx_max = dx_max;
+        ci.di_max_sh = di_max_sh;
+        ci.dj_min = dj_min;
+        ci.dbl = sorted ? 0 : 1;
+        ci.sid = sid | (tleft ? 256 : 0);
+        T.chunk()[nst >> 5] = ci;
       }
+      __syncwarp();
+      nchunks++;
+      test_chunk<3>(T.F(), nst, tpx, tpy, tpz, r2e, 0.f, lp, nlist);
+      nst += 32;
     }
   }
+  drain();
 
   if (tvalid) {
     float *po = (float *)&A.fo1[ti];

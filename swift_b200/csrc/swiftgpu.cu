@@ -956,6 +956,7 @@ static int build_lists(H *h, bool force_only) {
     d.sort_base = -1;
     d.sort_mask = 0;
     d.depth = (int8_t)s.depth;
+    d.width = (float)std::max(s.width[0], std::max(s.width[1], s.width[2]));
     d.flags = (uint8_t)((s.ti_end_min == h->step.ti_current ? 1 : 0) |
                         (s.nodeID == h->cfg.rank ? 2 : 0) | (s.split ? 4 : 0));
   }
@@ -1193,8 +1194,7 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   if (build_targets(h, h->L_density)) return 1;
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->nd, 0);
-    k_loop1<LOOP_DENSITY><<<(A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, 0,
-                            h->stream>>>(A);
+    k_loop1<LOOP_DENSITY, false><<<A.ntasks, 32, Tile1<LOOP_DENSITY, false>::kBytes, h->stream>>>(A);
     h->stats.n_launches++;
     CK(cudaGetLastError());
   }
@@ -1269,8 +1269,7 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
        * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
       CK(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long), h->stream));
       LoopArgs A = loop_args(h, D, h->nd, 4);
-      k_loop1<LOOP_DENSITY><<<(A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK,
-                              0, h->stream>>>(A);
+      k_loop1<LOOP_DENSITY, true><<<A.ntasks, 32, Tile1<LOOP_DENSITY, true>::kBytes, h->stream>>>(A);
       h->stats.n_launches++;
       CK(cudaGetLastError());
       int64_t nn = 0;
@@ -1297,8 +1296,7 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->ng, 1);
-    k_loop1<LOOP_GRADIENT><<<(A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK,
-                             0, h->stream>>>(A);
+    k_loop1<LOOP_GRADIENT, false><<<A.ntasks, 32, Tile1<LOOP_GRADIENT, false>::kBytes, h->stream>>>(A);
     h->stats.n_launches++;
     CK(cudaGetLastError());
   }
@@ -1387,11 +1385,11 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   if (build_targets(h, h->L_force)) return 1;
   if (h->L_force.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_force, h->nf, 2);
-    const unsigned grid = (A.ntasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const unsigned grid = A.ntasks;
     switch (h->cfg.scheme) {
-      case SCH_MINIMAL: k_loop2<SCH_MINIMAL><<<grid, 32 * WARPS_PER_BLOCK, 0, h->stream>>>(A); break;
-      case SCH_GADGET2: k_loop2<SCH_GADGET2><<<grid, 32 * WARPS_PER_BLOCK, 0, h->stream>>>(A); break;
-      default: k_loop2<SCH_SPHENIX><<<grid, 32 * WARPS_PER_BLOCK, 0, h->stream>>>(A); break;
+      case SCH_MINIMAL: k_loop2<SCH_MINIMAL><<<grid, 32, Tile2<SCH_MINIMAL>::kBytes, h->stream>>>(A); break;
+      case SCH_GADGET2: k_loop2<SCH_GADGET2><<<grid, 32, Tile2<SCH_GADGET2>::kBytes, h->stream>>>(A); break;
+      default: k_loop2<SCH_SPHENIX><<<grid, 32, Tile2<SCH_SPHENIX>::kBytes, h->stream>>>(A); break;
     }
     h->stats.n_launches++;
     CK(cudaGetLastError());
