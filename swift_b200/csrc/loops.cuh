@@ -138,13 +138,15 @@ __device__ __forceinline__ void atomic_max_pos(float *addr, float v) {
 /* Relative inflation of the prefilter radius^2: covers the difference between
  * the fused r2 of the prefilter and the reference's un-fused r2 (~2^-22). */
 #define PREFILTER_REL 1.00001f
-#define LCAP 96 /* hit-list capacity per lane */
+#define LCAP 64 /* hit-list capacity per target */
+#define TPL 2   /* targets per lane: every staged source is tested against 2 targets */
+#define TASK_TARGETS (32 * TPL)
 
 /* What the drain needs to know about a staged chunk of 32 slots. */
 struct __align__(16) ChunkInfo {
   double ot[3]; /* subtracted from the target's double position */
   int32_t dbl;  /* 1: dx from doubles (MODE_SELF, MODE_SUB_PAIR*) */
-  int32_t item; /* index into the item array (force: pair constants) */
+  int32_t item;
 };
 
 /* Type-2 (force) chunks also carry the constants of their pair item
@@ -165,7 +167,7 @@ struct Tile {
   static constexpr int kK = kGI + SCAP * 4;
   static constexpr int kD = kK + (KEYS ? SCAP * 4 : 0);
   static constexpr int kList = kD + (STAGE_D ? SCAP * 24 : 0);
-  static constexpr int kChunk = kList + LCAP * 32 * 2;
+  static constexpr int kChunk = kList + LCAP * TASK_TARGETS * 2;
   static constexpr int kBytes = kChunk + (SCAP / 32) * (int)sizeof(CIT);
   char *base;
   __device__ __forceinline__ float4 *F() const { return (float4 *)(base + kF); }
@@ -177,40 +179,45 @@ struct Tile {
   __device__ __forceinline__ CIT *chunk() const { return (CIT *)(base + kChunk); }
 };
 
-/* The prefilter over one freshly staged chunk: lane-private target against 32
- * broadcast sources. KC: 0 no key condition, 1 key < thr, 2 key > thr,
- * 3 type-2 (radius^2 = max(target, source)). */
+/* The prefilter over one freshly staged chunk: TPL lane-private targets
+ * against 32 broadcast sources. KC: 0 no key condition, 1 key < thr,
+ * 2 key > thr, 3 type-2 (radius^2 = max(target, source)). */
 template <int KC>
-__device__ __forceinline__ void test_chunk(const float4 *__restrict__ F, int nst, float tpx,
-                                           float tpy, float tpz, float r2e, float thr,
-                                           uint16_t *&lp, int &nlist) {
-  unsigned mask = 0u;
+__device__ __forceinline__ void test_chunk(const float4 *__restrict__ F, int nst,
+                                           const float (&tp)[TPL][3], const float (&r2e)[TPL],
+                                           const float (&thr)[TPL], uint16_t *(&lp)[TPL],
+                                           int (&nlist)[TPL]) {
+  unsigned mask[TPL];
 #pragma unroll
-  for (int qq = 0; qq < 32; qq += 8) {
-    float4 s[8];
+  for (int u = 0; u < TPL; u++) mask[u] = 0u;
+#pragma unroll 16
+  for (int q = 0; q < 32; q++) {
+    const float4 s = F[nst + q];
 #pragma unroll
-    for (int j = 0; j < 8; j++) s[j] = F[nst + qq + j];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const float dx = tpx - s[j].x, dy = tpy - s[j].y, dz = tpz - s[j].z;
+    for (int u = 0; u < TPL; u++) {
+      const float dx = tp[u][0] - s.x, dy = tp[u][1] - s.y, dz = tp[u][2] - s.z;
       const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
       bool ok;
       if (KC == 3)
-        ok = r2 < fmaxf(r2e, s[j].w);
+        ok = r2 < fmaxf(r2e[u], s.w);
       else
-        ok = r2 < r2e;
-      if (KC == 1) ok = ok && (s[j].w < thr);
-      if (KC == 2) ok = ok && (s[j].w > thr);
-      if (ok) mask |= 1u << (qq + j);
+        ok = r2 < r2e[u];
+      if (KC == 1) ok = ok && (s.w < thr[u]);
+      if (KC == 2) ok = ok && (s.w > thr[u]);
+      if (ok) mask[u] |= 1u << q;
     }
   }
-  /* decode the (sparse) mask into the lane's hit list */
-  while (mask) {
-    const int q = __ffs(mask) - 1;
-    mask &= mask - 1u;
-    *lp = (uint16_t)(nst + q);
-    lp += 32;
-    nlist++;
+  /* decode the (sparse) masks into the hit lists */
+#pragma unroll
+  for (int u = 0; u < TPL; u++) {
+    unsigned m = mask[u];
+    while (m) {
+      const int q = __ffs(m) - 1;
+      m &= m - 1u;
+      *lp[u] = (uint16_t)(nst + q);
+      lp[u] += TASK_TARGETS;
+      nlist[u]++;
+    }
   }
 }
 
@@ -218,7 +225,7 @@ __device__ __forceinline__ void test_chunk(const float4 *__restrict__ F, int nst
 /* Type-1 loops: density (all schemes), gradient (SPHENIX), and (SUBSET) the  */
 /* density re-runs of the ghost. Hit criterion r2 < h_t^2 gamma^2.            */
 /* ------------------------------------------------------------------------ */
-#define SCAP1 384
+#define SCAP1 256
 template <int LOOP, bool SUBSET>
 struct Tile1 : Tile<SCAP1, (LOOP == LOOP_GRADIENT ? 2 : 1), SUBSET, false, ChunkInfo> {};
 
@@ -234,98 +241,121 @@ __global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
   const int g = A.task_group[task];
   const int chunk = A.task_chunk[task];
   const int nt = A.tgt_count[g];
-  if (chunk * 32 >= nt) return;
+  if (chunk * TASK_TARGETS >= nt) return;
   const Group G = A.groups[g];
-  const int slot_t = chunk * 32 + lane;
-  const bool tvalid = slot_t < nt;
-  const int ti = tvalid ? A.tgt_list[A.tgt_first[g] + slot_t] : -1;
 
   /* target state */
-  double tx = 0., ty = 0., tz = 0.;
-  float th = 1.f, tvx = 0.f, tvy = 0.f, tvz = 0.f;
-  float tu = 0.f, tcs = 0.f;
-  int tdepth = 0;
-  if (tvalid) {
-    tx = A.x[3 * (size_t)ti];
-    ty = A.x[3 * (size_t)ti + 1];
-    tz = A.x[3 * (size_t)ti + 2];
-    th = A.h[ti];
-    const float4 q = A.mv[ti];
-    tvx = q.y;
-    tvy = q.z;
-    tvz = q.w;
-    tdepth = A.depth_h[ti];
-    if (LOOP == LOOP_GRADIENT) {
-      tu = A.fq2[ti].z;
-      tcs = A.fq1[ti].w;
+  bool tvalid[TPL];
+  int ti[TPL], tdepth[TPL];
+  double tx[TPL], ty[TPL], tz[TPL];
+  float th[TPL], tvx[TPL], tvy[TPL], tvz[TPL], tu[TPL], tcs[TPL], thg2[TPL], th_inv[TPL], thg[TPL];
+  DensityAcc dacc[TPL];
+  GradientAcc gacc[TPL];
+  int nhit[TPL];
+#pragma unroll
+  for (int u = 0; u < TPL; u++) {
+    const int slot_t = chunk * TASK_TARGETS + u * 32 + lane;
+    tvalid[u] = slot_t < nt;
+    ti[u] = tvalid[u] ? A.tgt_list[A.tgt_first[g] + slot_t] : -1;
+    tx[u] = ty[u] = tz[u] = 0.;
+    th[u] = 1.f;
+    tvx[u] = tvy[u] = tvz[u] = tu[u] = tcs[u] = 0.f;
+    tdepth[u] = 0;
+    if (tvalid[u]) {
+      const size_t p = (size_t)ti[u];
+      tx[u] = A.x[3 * p];
+      ty[u] = A.x[3 * p + 1];
+      tz[u] = A.x[3 * p + 2];
+      th[u] = A.h[p];
+      const float4 q = A.mv[p];
+      tvx[u] = q.y;
+      tvy[u] = q.z;
+      tvz[u] = q.w;
+      tdepth[u] = A.depth_h[p];
+      if (LOOP == LOOP_GRADIENT) {
+        tu[u] = A.fq2[p].z;
+        tcs[u] = A.fq1[p].w;
+      }
     }
+    thg2[u] = hg2_exact(th[u]);
+    th_inv[u] = 1.f / th[u];
+    thg[u] = __fmul_rn(th[u], KERNEL_GAMMA); /* hi * kernel_gamma (float) */
+    dacc[u].zero();
+    gacc[u].v_sig = 0.f;
+    gacc[u].laplace_u = 0.f;
+    gacc[u].alpha_max = 0.f;
+    nhit[u] = 0;
   }
-  const float thg2 = hg2_exact(th);
-  const float th_inv = 1.f / th;
-  const float thg = __fmul_rn(th, KERNEL_GAMMA); /* hi * kernel_gamma (float) */
-
-  DensityAcc dacc;
-  dacc.zero();
-  GradientAcc gacc;
-  gacc.v_sig = 0.f;
-  gacc.laplace_u = 0.f;
-  gacc.alpha_max = 0.f;
-  int nhit = 0;
   int nchunks = 0;
 
   /* tile state */
-  int nst = 0;   /* staged slots */
-  int nlist = 0; /* lane-private number of queued candidates */
-  uint16_t *const list0 = T.list() + lane;
-  uint16_t *lp = list0;
+  int nst = 0; /* staged slots */
+  int nlist[TPL];
+  uint16_t *lp[TPL];
+#pragma unroll
+  for (int u = 0; u < TPL; u++) {
+    nlist[u] = 0;
+    lp[u] = T.list() + u * 32 + lane;
+  }
 
   /* ---- INTERACT: drain the hit lists ---- */
   auto drain = [&]() {
     __syncwarp();
-    const int maxn = __reduce_max_sync(FULL_MASK, nlist);
+    int mx = nlist[0];
+#pragma unroll
+    for (int u = 1; u < TPL; u++) mx = max(mx, nlist[u]);
+    const int maxn = __reduce_max_sync(FULL_MASK, mx);
     const float4 *F = T.F();
     const int32_t *GI = T.GI();
     const ChunkInfo *CI = T.chunk();
+    const uint16_t *l0 = T.list() + lane;
     for (int k = 0; k < maxn; k++) {
-      const bool act = k < nlist;
-      const int slot = act ? (int)list0[k * 32] : 0;
-      const ChunkInfo ci = CI[slot >> 5];
-      const int gi = GI[slot];
-      const float4 s = F[slot];
-      const bool dbl = ci.dbl != 0;
-      double sxd = 0., syd = 0., szd = 0.;
-      if (act && dbl) {
-        if (SUBSET) {
-          const double *D = T.D();
-          sxd = D[slot];
-          syd = D[SCAP1 + slot];
-          szd = D[2 * SCAP1 + slot];
-        } else {
-          sxd = A.x[3 * (size_t)gi];
-          syd = A.x[3 * (size_t)gi + 1];
-          szd = A.x[3 * (size_t)gi + 2];
+#pragma unroll
+      for (int u = 0; u < TPL; u++) {
+        const bool act = k < nlist[u];
+        const int slot = act ? (int)l0[k * TASK_TARGETS + u * 32] : 0;
+        const ChunkInfo ci = CI[slot >> 5];
+        const int gi = GI[slot];
+        const float4 s = F[slot];
+        const bool dbl = ci.dbl != 0;
+        double sxd = 0., syd = 0., szd = 0.;
+        if (act && dbl) {
+          if (SUBSET) {
+            const double *D = T.D();
+            sxd = D[slot];
+            syd = D[SCAP1 + slot];
+            szd = D[2 * SCAP1 + slot];
+          } else {
+            sxd = A.x[3 * (size_t)gi];
+            syd = A.x[3 * (size_t)gi + 1];
+            szd = A.x[3 * (size_t)gi + 2];
+          }
         }
-      }
-      const float spx = dbl ? 0.f : s.x, spy = dbl ? 0.f : s.y, spz = dbl ? 0.f : s.z;
-      const float dx = __fsub_rn(dsubf(__dsub_rn(tx, ci.ot[0]), sxd), spx);
-      const float dy = __fsub_rn(dsubf(__dsub_rn(ty, ci.ot[1]), syd), spy);
-      const float dz = __fsub_rn(dsubf(__dsub_rn(tz, ci.ot[2]), szd), spz);
-      const float r2 = r2_exact(dx, dy, dz);
-      if (act && (r2 < thg2) && (gi != ti)) {
-        const float4 f0 = T.P(0)[slot];
-        if (LOOP == LOOP_DENSITY) {
-          iact_density(dacc, r2, dx, dy, dz, th_inv, tvx, tvy, tvz, f0.x, f0.y, f0.z, f0.w);
-        } else {
-          const float4 f1 = T.P(1)[slot];
-          iact_gradient(gacc, r2, dx, dy, dz, th, tvx, tvy, tvz, tu, tcs, f0.x, f0.y, f0.z, f0.w,
-                        f1.x, f1.y, f1.z, f1.w, A.a2_Hubble);
+        const float spx = dbl ? 0.f : s.x, spy = dbl ? 0.f : s.y, spz = dbl ? 0.f : s.z;
+        const float dx = __fsub_rn(dsubf(__dsub_rn(tx[u], ci.ot[0]), sxd), spx);
+        const float dy = __fsub_rn(dsubf(__dsub_rn(ty[u], ci.ot[1]), syd), spy);
+        const float dz = __fsub_rn(dsubf(__dsub_rn(tz[u], ci.ot[2]), szd), spz);
+        const float r2 = r2_exact(dx, dy, dz);
+        if (act && (r2 < thg2[u]) && (gi != ti[u])) {
+          const float4 f0 = T.P(0)[slot];
+          if (LOOP == LOOP_DENSITY) {
+            iact_density(dacc[u], r2, dx, dy, dz, th_inv[u], tvx[u], tvy[u], tvz[u], f0.x, f0.y, f0.z,
+                         f0.w);
+          } else {
+            const float4 f1 = T.P(1)[slot];
+            iact_gradient(gacc[u], r2, dx, dy, dz, th[u], tvx[u], tvy[u], tvz[u], tu[u], tcs[u], f0.x,
+                          f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, A.a2_Hubble);
+          }
+          nhit[u]++;
         }
-        nhit++;
       }
     }
-    nlist = 0;
     nst = 0;
-    lp = list0;
+#pragma unroll
+    for (int u = 0; u < TPL; u++) {
+      nlist[u] = 0;
+      lp[u] = T.list() + u * 32 + lane;
+    }
     __syncwarp();
   };
 
@@ -336,48 +366,41 @@ __global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
     const int sid = I.sid;
     const int scount = sc.count;
 
-    /* per-lane participation and frame */
-    bool part = tvalid && tdepth >= I.min_depth && tdepth <= I.max_depth;
-    float tpx = 0.f, tpy = 0.f, tpz = 0.f; /* prefilter position of the target */
-    float thr = 0.f;                       /* pruning threshold on the source key */
+    /* item-level (warp-uniform) frame */
     bool ascending = true;
     double fsx = 0., fsy = 0., fsz = 0.; /* frame origin of the staged source floats */
     double otx = 0., oty = 0., otz = 0.; /* subtracted from the target double in the drain */
     const bool dbl_mode = (mode == MODE_SELF || mode == MODE_SUB_PAIR || mode == MODE_SUB_PAIR_F);
     const bool sorted = (mode == MODE_PAIR_L || mode == MODE_PAIR_R || mode == MODE_SUB_PAIR ||
                          mode == MODE_SUB_PAIR_F);
+    const bool is_pair = (mode == MODE_PAIR_L || mode == MODE_PAIR_R);
     const double shx = I.shift[0] * A.dim[0], shy = I.shift[1] * A.dim[1],
                  shz = I.shift[2] * A.dim[2];
     int64_t soff = 0;
     if (sorted) soff = sort_offset(sc, sid);
-    float r2e = __fmul_rn(thg2, PREFILTER_REL);
+    double rshift = 0., lim_a = 0., lim_b = 0.; /* pair: hi_max / dj_min or hj_max / di_max */
+    float dx_max = 0.f;
 
-    if (mode == MODE_PAIR_L || mode == MODE_PAIR_R) {
+    if (is_pair) {
       /* oriented pair: ci = left cell, cj = right cell */
       const DevCell tc = A.cells[I.tcell];
       const DevCell &ci = (mode == MODE_PAIR_L) ? tc : sc;
       const DevCell &cj = (mode == MODE_PAIR_L) ? sc : tc;
-      const double rshift = __dadd_rn(
+      rshift = __dadd_rn(
           __dadd_rn(__dmul_rn(shx, c_runner_shift[sid][0]), __dmul_rn(shy, c_runner_shift[sid][1])),
           __dmul_rn(shz, c_runner_shift[sid][2]));
       const float h_max_lim = (I.flags & 1) ? ci.h_max_allowed : 3.402823466e+38f;
-      const float dx_max = __fadd_rn(ci.dx_max_sort, cj.dx_max_sort);
+      dx_max = __fadd_rn(ci.dx_max_sort, cj.dx_max_sort);
       /* frame origins: ci particles are shifted by cj->loc + shift, cj by cj->loc */
       const double oix = __dadd_rn(cj.loc[0], shx), oiy = __dadd_rn(cj.loc[1], shy),
                    oiz = __dadd_rn(cj.loc[2], shz);
-      const float tkey = sort_key(tx, ty, tz, sid);
       if (mode == MODE_PAIR_L) {
         /* targets in ci: functions_hydro.h:1296-1332 */
-        const double hi_max =
-            __dsub_rn((double)__fmul_rn(fminf(h_max_lim, ci.h_max_active), KERNEL_GAMMA), rshift);
+        lim_a = __dsub_rn((double)__fmul_rn(fminf(h_max_lim, ci.h_max_active), KERNEL_GAMMA), rshift);
         /* dj_min = sort_j[0].d */
         const int j0 = cj.first + (int)A.sort_idx[sort_offset(cj, sid)];
-        const double dj_min =
-            (double)sort_key(A.x[3 * (size_t)j0], A.x[3 * (size_t)j0 + 1], A.x[3 * (size_t)j0 + 2], sid);
-        const bool in_loop = __dadd_rn(__dadd_rn((double)tkey, hi_max), (double)dx_max) > dj_min;
-        const double di = __dsub_rn((double)__fadd_rn(__fadd_rn(tkey, thg), dx_max), rshift);
-        part = part && in_loop && !(di < dj_min);
-        thr = __double2float_ru(di); /* key < di  <=>  key < ru(di) for float keys */
+        lim_b = (double)sort_key(A.x[3 * (size_t)j0], A.x[3 * (size_t)j0 + 1], A.x[3 * (size_t)j0 + 2],
+                                 sid);
         otx = oix;
         oty = oiy;
         otz = oiz;
@@ -387,15 +410,11 @@ __global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
         ascending = true;
       } else {
         /* targets in cj: functions_hydro.h:1420-1448 */
-        const double hj_max = (double)__fmul_rn(fminf(h_max_lim, cj.h_max_active), KERNEL_GAMMA);
+        lim_a = (double)__fmul_rn(fminf(h_max_lim, cj.h_max_active), KERNEL_GAMMA);
         const int i1 = ci.first + (int)A.sort_idx[sort_offset(ci, sid) + ci.count - 1];
-        const double di_max = __dsub_rn(
-            (double)sort_key(A.x[3 * (size_t)i1], A.x[3 * (size_t)i1 + 1], A.x[3 * (size_t)i1 + 2], sid),
-            rshift);
-        const bool in_loop = __dsub_rn(__dsub_rn((double)tkey, hj_max), (double)dx_max) < di_max;
-        const double dj = __dadd_rn((double)__fsub_rn(__fsub_rn(tkey, thg), dx_max), rshift);
-        part = part && in_loop && !(__dsub_rn(dj, rshift) > di_max);
-        thr = __double2float_rd(dj); /* key > dj  <=>  key > rd(dj) */
+        lim_b = __dsub_rn((double)sort_key(A.x[3 * (size_t)i1], A.x[3 * (size_t)i1 + 1],
+                                           A.x[3 * (size_t)i1 + 2], sid),
+                          rshift);
         otx = cj.loc[0];
         oty = cj.loc[1];
         otz = cj.loc[2];
@@ -404,17 +423,11 @@ __global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
         fsz = oiz;
         ascending = false;
       }
-      tpx = dsubf(tx, otx);
-      tpy = dsubf(ty, oty);
-      tpz = dsubf(tz, otz);
     } else if (mode == MODE_SUB_SELF) {
       /* DOSELF_SUBSET :1127-1129: floats relative to c->loc (c = scell) */
       otx = fsx = sc.loc[0];
       oty = fsy = sc.loc[1];
       otz = fsz = sc.loc[2];
-      tpx = dsubf(tx, otx);
-      tpy = dsubf(ty, oty);
-      tpz = dsubf(tz, otz);
     } else {
       /* Double modes. MODE_SELF: dx = (float)(x_t - x_s). MODE_SUB_PAIR*:
        * (float)((x_t - shift) - x_s), DOPAIR_SUBSET :885-897 / :955-967. The
@@ -424,39 +437,72 @@ __global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
         otx = shx;
         oty = shy;
         otz = shz;
+        ascending = (mode == MODE_SUB_PAIR);
       }
-      const double tdx = __dsub_rn(tx, otx), tdy = __dsub_rn(ty, oty), tdz = __dsub_rn(tz, otz);
       fsx = sc.loc[0];
       fsy = sc.loc[1];
       fsz = sc.loc[2];
-      tpx = dsubf(tdx, fsx);
-      tpy = dsubf(tdy, fsy);
-      tpz = dsubf(tdz, fsz);
-      const float re = fmaf(thg, PREFILTER_REL, 4.0e-6f * sc.width);
-      r2e = re * re;
-      if (mode != MODE_SELF) {
-        /* di = hi*kernel_gamma + dxj + pix*rs0 + piy*rs1 + piz*rs2, left to right */
-        const float dxj = sc.dx_max_sort;
-        const float f0 = (mode == MODE_SUB_PAIR) ? __fadd_rn(thg, dxj) : __fsub_rn(-thg, dxj);
-        const double di =
-            __dadd_rn(__dadd_rn(__dadd_rn((double)f0, __dmul_rn(tdx, c_runner_shift[sid][0])),
-                                __dmul_rn(tdy, c_runner_shift[sid][1])),
-                      __dmul_rn(tdz, c_runner_shift[sid][2]));
-        if (mode == MODE_SUB_PAIR) {
-          thr = __double2float_ru(di);
-          ascending = true;
-        } else {
-          thr = __double2float_rd(di);
-          ascending = false;
-        }
-      }
     }
 
-    if (!__any_sync(FULL_MASK, part)) continue;
-    if (!part) tpx = 3.0e30f; /* never passes the prefilter */
+    /* per-target participation, prefilter position and key threshold */
+    float tp[TPL][3], r2e[TPL], thr[TPL];
+    bool anypart = false;
+    float reach_l = ascending ? -3.0e38f : 3.0e38f;
+#pragma unroll
+    for (int u = 0; u < TPL; u++) {
+      bool part = tvalid[u] && tdepth[u] >= I.min_depth && tdepth[u] <= I.max_depth;
+      thr[u] = 0.f;
+      r2e[u] = __fmul_rn(thg2[u], PREFILTER_REL);
+      if (is_pair) {
+        const float tkey = sort_key(tx[u], ty[u], tz[u], sid);
+        if (mode == MODE_PAIR_L) {
+          const bool in_loop = __dadd_rn(__dadd_rn((double)tkey, lim_a), (double)dx_max) > lim_b;
+          const double di = __dsub_rn((double)__fadd_rn(__fadd_rn(tkey, thg[u]), dx_max), rshift);
+          part = part && in_loop && !(di < lim_b);
+          thr[u] = __double2float_ru(di); /* key < di  <=>  key < ru(di) for float keys */
+        } else {
+          const bool in_loop = __dsub_rn(__dsub_rn((double)tkey, lim_a), (double)dx_max) < lim_b;
+          const double dj = __dadd_rn((double)__fsub_rn(__fsub_rn(tkey, thg[u]), dx_max), rshift);
+          part = part && in_loop && !(__dsub_rn(dj, rshift) > lim_b);
+          thr[u] = __double2float_rd(dj); /* key > dj  <=>  key > rd(dj) */
+        }
+        tp[u][0] = dsubf(tx[u], otx);
+        tp[u][1] = dsubf(ty[u], oty);
+        tp[u][2] = dsubf(tz[u], otz);
+      } else if (mode == MODE_SUB_SELF) {
+        tp[u][0] = dsubf(tx[u], otx);
+        tp[u][1] = dsubf(ty[u], oty);
+        tp[u][2] = dsubf(tz[u], otz);
+      } else {
+        const double tdx = __dsub_rn(tx[u], otx), tdy = __dsub_rn(ty[u], oty),
+                     tdz = __dsub_rn(tz[u], otz);
+        tp[u][0] = dsubf(tdx, fsx);
+        tp[u][1] = dsubf(tdy, fsy);
+        tp[u][2] = dsubf(tdz, fsz);
+        const float re = fmaf(thg[u], PREFILTER_REL, 4.0e-6f * sc.width);
+        r2e[u] = re * re;
+        if (mode != MODE_SELF) {
+          /* di = hi*kernel_gamma + dxj + pix*rs0 + piy*rs1 + piz*rs2, left to right */
+          const float dxj = sc.dx_max_sort;
+          const float f0 = (mode == MODE_SUB_PAIR) ? __fadd_rn(thg[u], dxj) : __fsub_rn(-thg[u], dxj);
+          const double di =
+              __dadd_rn(__dadd_rn(__dadd_rn((double)f0, __dmul_rn(tdx, c_runner_shift[sid][0])),
+                                  __dmul_rn(tdy, c_runner_shift[sid][1])),
+                        __dmul_rn(tdz, c_runner_shift[sid][2]));
+          thr[u] = (mode == MODE_SUB_PAIR) ? __double2float_ru(di) : __double2float_rd(di);
+        }
+      }
+      if (part) {
+        anypart = true;
+        reach_l = ascending ? fmaxf(reach_l, thr[u]) : fminf(reach_l, thr[u]);
+      } else {
+        tp[u][0] = 3.0e30f; /* never passes the prefilter */
+      }
+    }
+    if (!__any_sync(FULL_MASK, anypart)) continue;
     /* reach of the warp along the axis, for the sorted early exit */
     float reach = 0.f;
-    if (sorted) reach = ascending ? warp_max(part ? thr : -3.0e38f) : warp_min(part ? thr : 3.0e38f);
+    if (sorted) reach = ascending ? warp_max(reach_l) : warp_min(reach_l);
 
     for (int base = 0; base < scount; base += 32) {
       /* ---- stage 32 sources ---- */
@@ -478,7 +524,12 @@ __global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
         const float first_key = __shfl_sync(FULL_MASK, skey, 0);
         if (ascending ? !(first_key < reach) : !(first_key > reach)) break;
       }
-      if (nst + 32 > SCAP1 || __any_sync(FULL_MASK, nlist > LCAP - 32)) drain();
+      {
+        bool full = nst + 32 > SCAP1;
+#pragma unroll
+        for (int u = 0; u < TPL; u++) full = full || (nlist[u] > LCAP - 32);
+        if (__any_sync(FULL_MASK, full)) drain();
+      }
       const int slot = nst + lane;
       if (k < scount) {
         T.F()[slot] = make_float4(dsubf(sx, fsx), dsubf(sy, fsy), dsubf(sz, fsz), skey);
@@ -513,42 +564,48 @@ __global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
       /* ---- test ---- */
       nchunks++;
       if (!sorted)
-        test_chunk<0>(T.F(), nst, tpx, tpy, tpz, r2e, thr, lp, nlist);
+        test_chunk<0>(T.F(), nst, tp, r2e, thr, lp, nlist);
       else if (ascending)
-        test_chunk<1>(T.F(), nst, tpx, tpy, tpz, r2e, thr, lp, nlist);
+        test_chunk<1>(T.F(), nst, tp, r2e, thr, lp, nlist);
       else
-        test_chunk<2>(T.F(), nst, tpx, tpy, tpz, r2e, thr, lp, nlist);
+        test_chunk<2>(T.F(), nst, tp, r2e, thr, lp, nlist);
       nst += 32;
     }
   }
   drain();
 
   /* ---- flush (once per task) ---- */
-  if (tvalid) {
-    if (LOOP == LOOP_DENSITY) {
-      float *pa = (float *)&A.dA[ti];
-      float *pb = (float *)&A.dB[ti];
-      atomicAdd(pa + 0, dacc.rho);
-      atomicAdd(pa + 1, dacc.rho_dh);
-      atomicAdd(pa + 2, dacc.wcount);
-      atomicAdd(pa + 3, dacc.wcount_dh);
-      atomicAdd(pb + 0, dacc.div_v);
-      atomicAdd(pb + 1, dacc.rot[0]);
-      atomicAdd(pb + 2, dacc.rot[1]);
-      atomicAdd(pb + 3, dacc.rot[2]);
-    } else {
-      atomic_max_pos(&A.g_vsig[ti], gacc.v_sig);
-      atomicAdd(&A.g_lap[ti], gacc.laplace_u);
-      atomic_max_pos(&A.g_amax[ti], gacc.alpha_max);
+  int tot = 0;
+#pragma unroll
+  for (int u = 0; u < TPL; u++) {
+    if (tvalid[u]) {
+      const int p = ti[u];
+      if (LOOP == LOOP_DENSITY) {
+        float *pa = (float *)&A.dA[p];
+        float *pb = (float *)&A.dB[p];
+        atomicAdd(pa + 0, dacc[u].rho);
+        atomicAdd(pa + 1, dacc[u].rho_dh);
+        atomicAdd(pa + 2, dacc[u].wcount);
+        atomicAdd(pa + 3, dacc[u].wcount_dh);
+        atomicAdd(pb + 0, dacc[u].div_v);
+        atomicAdd(pb + 1, dacc[u].rot[0]);
+        atomicAdd(pb + 2, dacc[u].rot[1]);
+        atomicAdd(pb + 3, dacc[u].rot[2]);
+      } else {
+        atomic_max_pos(&A.g_vsig[p], gacc[u].v_sig);
+        atomicAdd(&A.g_lap[p], gacc[u].laplace_u);
+        atomic_max_pos(&A.g_amax[p], gacc[u].alpha_max);
+      }
+      if (nhit[u]) atomicAdd(&A.count[p], nhit[u]);
     }
-    if (nhit) atomicAdd(&A.count[ti], nhit);
+    tot += nhit[u];
   }
   /* global interaction counter */
-  int tot = nhit;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL_MASK, tot, o);
   if (lane == 0 && tot) atomicAdd(A.total, (unsigned long long)tot);
-  if (lane == 0 && nchunks) atomicAdd(A.tests, (unsigned long long)nchunks * 1024ull);
+  if (lane == 0 && nchunks)
+    atomicAdd(A.tests, (unsigned long long)nchunks * (unsigned long long)(1024 * TPL));
 }
 
 /* ------------------------------------------------------------------------ */
@@ -559,7 +616,7 @@ __global__ void __launch_bounds__(32) k_loop1(const LoopArgs A) {
  * The prefilter only applies the radius; the pass conditions (doubles) are
  * evaluated per candidate in the drain.                                      */
 /* ------------------------------------------------------------------------ */
-#define SCAP2 256
+#define SCAP2 192
 template <int SCHEME>
 struct Tile2 : Tile<SCAP2, (SCHEME == SCH_SPHENIX ? 4 : 3), false, true, ChunkInfoF> {};
 
@@ -575,141 +632,161 @@ __global__ void __launch_bounds__(32) k_loop2(const LoopArgs A) {
   const int g = A.task_group[task];
   const int chunk = A.task_chunk[task];
   const int nt = A.tgt_count[g];
-  if (chunk * 32 >= nt) return;
+  if (chunk * TASK_TARGETS >= nt) return;
   const Group G = A.groups[g];
-  const int slot_t = chunk * 32 + lane;
-  const bool tvalid = slot_t < nt;
-  const int ti = tvalid ? A.tgt_list[A.tgt_first[g] + slot_t] : -1;
 
-  double tx = 0., ty = 0., tz = 0.;
-  ForceQ tq;
-  tq.m = tq.vx = tq.vy = tq.vz = 0.f;
-  tq.rho = 1.f;
-  tq.P = tq.f = tq.cs = tq.balsara = 0.f;
-  tq.h = 1.f;
-  tq.u = tq.alpha_visc = tq.alpha_diff = 0.f;
-  tq.time_bin = 0;
-  int tdepth = 0;
-  if (tvalid) {
-    tx = A.x[3 * (size_t)ti];
-    ty = A.x[3 * (size_t)ti + 1];
-    tz = A.x[3 * (size_t)ti + 2];
-    const float4 q0 = A.mv[ti], q1 = A.fq1[ti], q2 = A.fq2[ti];
-    tq.m = q0.x; tq.vx = q0.y; tq.vy = q0.z; tq.vz = q0.w;
-    tq.rho = q1.x; tq.P = q1.y; tq.f = q1.z; tq.cs = q1.w;
-    tq.balsara = q2.x; tq.h = q2.y; tq.u = q2.z; tq.time_bin = __float_as_int(q2.w);
-    if (SCHEME == SCH_SPHENIX) {
-      const float4 q3 = A.fq3[ti];
-      tq.alpha_visc = q3.x;
-      tq.alpha_diff = q3.y;
+  bool tvalid[TPL];
+  int ti[TPL], tdepth[TPL], nhit[TPL];
+  double tx[TPL], ty[TPL], tz[TPL];
+  ForceQ tq[TPL];
+  float thg2[TPL], thg[TPL];
+  ForceAcc acc[TPL];
+#pragma unroll
+  for (int u = 0; u < TPL; u++) {
+    const int slot_t = chunk * TASK_TARGETS + u * 32 + lane;
+    tvalid[u] = slot_t < nt;
+    ti[u] = tvalid[u] ? A.tgt_list[A.tgt_first[g] + slot_t] : -1;
+    tx[u] = ty[u] = tz[u] = 0.;
+    tq[u].m = tq[u].vx = tq[u].vy = tq[u].vz = 0.f;
+    tq[u].rho = 1.f;
+    tq[u].P = tq[u].f = tq[u].cs = tq[u].balsara = 0.f;
+    tq[u].h = 1.f;
+    tq[u].u = tq[u].alpha_visc = tq[u].alpha_diff = 0.f;
+    tq[u].time_bin = 0;
+    tdepth[u] = 0;
+    if (tvalid[u]) {
+      const size_t p = (size_t)ti[u];
+      tx[u] = A.x[3 * p];
+      ty[u] = A.x[3 * p + 1];
+      tz[u] = A.x[3 * p + 2];
+      const float4 q0 = A.mv[p], q1 = A.fq1[p], q2 = A.fq2[p];
+      tq[u].m = q0.x; tq[u].vx = q0.y; tq[u].vy = q0.z; tq[u].vz = q0.w;
+      tq[u].rho = q1.x; tq[u].P = q1.y; tq[u].f = q1.z; tq[u].cs = q1.w;
+      tq[u].balsara = q2.x; tq[u].h = q2.y; tq[u].u = q2.z; tq[u].time_bin = __float_as_int(q2.w);
+      if (SCHEME == SCH_SPHENIX) {
+        const float4 q3 = A.fq3[p];
+        tq[u].alpha_visc = q3.x;
+        tq[u].alpha_diff = q3.y;
+      }
+      tdepth[u] = A.depth_h[p];
     }
-    tdepth = A.depth_h[ti];
+    thg2[u] = hg2_exact(tq[u].h);
+    thg[u] = __fmul_rn(tq[u].h, KERNEL_GAMMA);
+    acc[u].ax = acc[u].ay = acc[u].az = acc[u].u_dt = acc[u].h_dt = 0.f;
+    acc[u].v_sig = 0.f;
+    acc[u].min_ngb = NUM_TIME_BINS + 1;
+    nhit[u] = 0;
   }
-  const float th = tq.h;
-  const float thg2 = hg2_exact(th);
-  const float thg = __fmul_rn(th, KERNEL_GAMMA);
-
-  ForceAcc acc;
-  acc.ax = acc.ay = acc.az = acc.u_dt = acc.h_dt = 0.f;
-  acc.v_sig = 0.f;
-  acc.min_ngb = NUM_TIME_BINS + 1;
-  int nhit = 0;
   int nchunks = 0;
 
   int nst = 0;
-  int nlist = 0;
-  uint16_t *const list0 = T.list() + lane;
-  uint16_t *lp = list0;
+  int nlist[TPL];
+  uint16_t *lp[TPL];
+#pragma unroll
+  for (int u = 0; u < TPL; u++) {
+    nlist[u] = 0;
+    lp[u] = T.list() + u * 32 + lane;
+  }
 
   /* ---- INTERACT ---- */
   auto drain = [&]() {
     __syncwarp();
-    const int maxn = __reduce_max_sync(FULL_MASK, nlist);
+    int mx = nlist[0];
+#pragma unroll
+    for (int u = 1; u < TPL; u++) mx = max(mx, nlist[u]);
+    const int maxn = __reduce_max_sync(FULL_MASK, mx);
     const float4 *F = T.F();
     const int32_t *GI = T.GI();
     const float *K = T.K();
     const ChunkInfoF *CI = T.chunk();
+    const uint16_t *l0 = T.list() + lane;
     for (int k = 0; k < maxn; k++) {
-      const bool act = k < nlist;
-      const int slot = act ? (int)list0[k * 32] : 0;
-      const ChunkInfoF ci = CI[slot >> 5];
-      const int gi = GI[slot];
-      const float4 s = F[slot];
-      const bool dbl = ci.dbl != 0;
-      double sxd = 0., syd = 0., szd = 0.;
-      if (act && dbl) {
-        sxd = A.x[3 * (size_t)gi];
-        syd = A.x[3 * (size_t)gi + 1];
-        szd = A.x[3 * (size_t)gi + 2];
-      }
-      const float spx = dbl ? 0.f : s.x, spy = dbl ? 0.f : s.y, spz = dbl ? 0.f : s.z;
-      const float dx = __fsub_rn(dsubf(__dsub_rn(tx, ci.ot[0]), sxd), spx);
-      const float dy = __fsub_rn(dsubf(__dsub_rn(ty, ci.ot[1]), syd), spy);
-      const float dz = __fsub_rn(dsubf(__dsub_rn(tz, ci.ot[2]), szd), spz);
-      const float r2 = r2_exact(dx, dy, dz);
-      const float4 q2 = T.P(2)[slot];
-      const float sh = q2.y;
-      const float shg2 = hg2_exact(sh);
-      bool ok;
-      if (dbl) {
-        /* DOSELF2 :2792: doi = r2 < hig2 || r2 < hjg2 */
-        ok = (r2 < thg2 || r2 < shg2) && (gi != ti);
-      } else {
-        /* DOPAIR2: the pair constants of the item */
-        const bool tleft = (ci.sid & 256) != 0;
-        const int sid = ci.sid & 255;
-        const double rshift = ci.rshift, hi_max_g = ci.hi_max_g, hj_max_g = ci.hj_max_g,
-                     dx_max = ci.dx_max, di_max_sh = ci.di_max_sh, dj_min = ci.dj_min;
-        const float tkey = sort_key(tx, ty, tz, sid);
-        const float skey = K[slot];
-        const float shg = __fmul_rn(sh, KERNEL_GAMMA);
-        if (tleft) {
-          /* t = i in ci, s = j in cj */
-          const bool inA =
-              __dsub_rn(__dadd_rn(__dadd_rn((double)tkey, hi_max_g), dx_max), rshift) > dj_min;
-          const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(tkey, thg), dx_max), rshift);
-          const double t_di = (inA && !(di < dj_min)) ? di : -1.0e300;
-          const double t_keysh = __dsub_rn((double)tkey, rshift);
-          const bool inB = __dsub_rn(__dsub_rn((double)skey, hj_max_g), dx_max) < di_max_sh;
-          const double dj = __dsub_rn((double)__fsub_rn(skey, shg), dx_max);
-          const double s_dj = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
-          const bool c1 = ((double)skey < t_di) && (r2 < thg2);
-          const bool c2 = (t_keysh > s_dj) && (r2 < shg2) && !(r2 < thg2);
-          ok = c1 || c2;
+#pragma unroll
+      for (int u = 0; u < TPL; u++) {
+        const bool act = k < nlist[u];
+        const int slot = act ? (int)l0[k * TASK_TARGETS + u * 32] : 0;
+        const ChunkInfoF &ci = CI[slot >> 5];
+        const int gi = GI[slot];
+        const float4 s = F[slot];
+        const bool dbl = ci.dbl != 0;
+        double sxd = 0., syd = 0., szd = 0.;
+        if (act && dbl) {
+          sxd = A.x[3 * (size_t)gi];
+          syd = A.x[3 * (size_t)gi + 1];
+          szd = A.x[3 * (size_t)gi + 2];
+        }
+        const float spx = dbl ? 0.f : s.x, spy = dbl ? 0.f : s.y, spz = dbl ? 0.f : s.z;
+        const float dx = __fsub_rn(dsubf(__dsub_rn(tx[u], ci.ot[0]), sxd), spx);
+        const float dy = __fsub_rn(dsubf(__dsub_rn(ty[u], ci.ot[1]), syd), spy);
+        const float dz = __fsub_rn(dsubf(__dsub_rn(tz[u], ci.ot[2]), szd), spz);
+        const float r2 = r2_exact(dx, dy, dz);
+        const float4 q2 = T.P(2)[slot];
+        const float sh = q2.y;
+        const float shg2 = hg2_exact(sh);
+        bool ok;
+        if (dbl) {
+          /* DOSELF2 :2792: doi = r2 < hig2 || r2 < hjg2 */
+          ok = (r2 < thg2[u] || r2 < shg2) && (gi != ti[u]);
         } else {
-          /* t = j in cj, s = i in ci */
-          const bool inB = __dsub_rn(__dsub_rn((double)tkey, hj_max_g), dx_max) < di_max_sh;
-          const double dj = __dsub_rn((double)__fsub_rn(tkey, thg), dx_max);
-          const double t_dj = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
-          const bool inA =
-              __dsub_rn(__dadd_rn(__dadd_rn((double)skey, hi_max_g), dx_max), rshift) > dj_min;
-          const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(skey, shg), dx_max), rshift);
-          const double s_di = (inA && !(di < dj_min)) ? di : -1.0e300;
-          const double s_keysh = __dsub_rn((double)skey, rshift);
-          const bool c1 = ((double)tkey < s_di) && (r2 < shg2);
-          const bool c2 = (s_keysh > t_dj) && (r2 < thg2) && !(r2 < shg2);
-          ok = c1 || c2;
+          /* DOPAIR2: the pair constants of the item */
+          const bool tleft = (ci.sid & 256) != 0;
+          const int sid = ci.sid & 255;
+          const double rshift = ci.rshift, hi_max_g = ci.hi_max_g, hj_max_g = ci.hj_max_g,
+                       dx_max = ci.dx_max, di_max_sh = ci.di_max_sh, dj_min = ci.dj_min;
+          const float tkey = sort_key(tx[u], ty[u], tz[u], sid);
+          const float skey = K[slot];
+          const float shg = __fmul_rn(sh, KERNEL_GAMMA);
+          if (tleft) {
+            /* t = i in ci, s = j in cj */
+            const bool inA =
+                __dsub_rn(__dadd_rn(__dadd_rn((double)tkey, hi_max_g), dx_max), rshift) > dj_min;
+            const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(tkey, thg[u]), dx_max), rshift);
+            const double t_di = (inA && !(di < dj_min)) ? di : -1.0e300;
+            const double t_keysh = __dsub_rn((double)tkey, rshift);
+            const bool inB = __dsub_rn(__dsub_rn((double)skey, hj_max_g), dx_max) < di_max_sh;
+            const double dj = __dsub_rn((double)__fsub_rn(skey, shg), dx_max);
+            const double s_dj = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
+            const bool c1 = ((double)skey < t_di) && (r2 < thg2[u]);
+            const bool c2 = (t_keysh > s_dj) && (r2 < shg2) && !(r2 < thg2[u]);
+            ok = c1 || c2;
+          } else {
+            /* t = j in cj, s = i in ci */
+            const bool inB = __dsub_rn(__dsub_rn((double)tkey, hj_max_g), dx_max) < di_max_sh;
+            const double dj = __dsub_rn((double)__fsub_rn(tkey, thg[u]), dx_max);
+            const double t_dj = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
+            const bool inA =
+                __dsub_rn(__dadd_rn(__dadd_rn((double)skey, hi_max_g), dx_max), rshift) > dj_min;
+            const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(skey, shg), dx_max), rshift);
+            const double s_di = (inA && !(di < dj_min)) ? di : -1.0e300;
+            const double s_keysh = __dsub_rn((double)skey, rshift);
+            const bool c1 = ((double)tkey < s_di) && (r2 < shg2);
+            const bool c2 = (s_keysh > t_dj) && (r2 < thg2[u]) && !(r2 < shg2);
+            ok = c1 || c2;
+          }
         }
-      }
-      if (act && ok) {
-        ForceQ sq;
-        const float4 q0 = T.P(0)[slot], q1 = T.P(1)[slot];
-        sq.m = q0.x; sq.vx = q0.y; sq.vy = q0.z; sq.vz = q0.w;
-        sq.rho = q1.x; sq.P = q1.y; sq.f = q1.z; sq.cs = q1.w;
-        sq.balsara = q2.x; sq.h = q2.y; sq.u = q2.z; sq.time_bin = __float_as_int(q2.w);
-        sq.alpha_visc = sq.alpha_diff = 0.f;
-        if (SCHEME == SCH_SPHENIX) {
-          const float4 q3 = T.P(3)[slot];
-          sq.alpha_visc = q3.x;
-          sq.alpha_diff = q3.y;
+        if (act && ok) {
+          ForceQ sq;
+          const float4 q0 = T.P(0)[slot], q1 = T.P(1)[slot];
+          sq.m = q0.x; sq.vx = q0.y; sq.vy = q0.z; sq.vz = q0.w;
+          sq.rho = q1.x; sq.P = q1.y; sq.f = q1.z; sq.cs = q1.w;
+          sq.balsara = q2.x; sq.h = q2.y; sq.u = q2.z; sq.time_bin = __float_as_int(q2.w);
+          sq.alpha_visc = sq.alpha_diff = 0.f;
+          if (SCHEME == SCH_SPHENIX) {
+            const float4 q3 = T.P(3)[slot];
+            sq.alpha_visc = q3.x;
+            sq.alpha_diff = q3.y;
+          }
+          iact_force<SCHEME>(acc[u], r2, dx, dy, dz, tq[u], sq, A.a2_Hubble);
+          nhit[u]++;
         }
-        iact_force<SCHEME>(acc, r2, dx, dy, dz, tq, sq, A.a2_Hubble);
-        nhit++;
       }
     }
-    nlist = 0;
     nst = 0;
-    lp = list0;
+#pragma unroll
+    for (int u = 0; u < TPL; u++) {
+      nlist[u] = 0;
+      lp[u] = T.list() + u * 32 + lane;
+    }
     __syncwarp();
   };
 
@@ -719,30 +796,24 @@ __global__ void __launch_bounds__(32) k_loop2(const LoopArgs A) {
     const int mode = I.mode;
     const int sid = I.sid;
     const int scount = sc.count;
-    const bool part = tvalid && tdepth >= I.min_depth && tdepth <= I.max_depth;
-    if (!__any_sync(FULL_MASK, part)) continue;
 
-    float tpx, tpy, tpz;
-    float r2e = __fmul_rn(thg2, PREFILTER_REL);
     double otx = 0., oty = 0., otz = 0.;
     double fsx, fsy, fsz;
     bool sorted = false, tleft = true;
-    double reach = 0., hi_max_g = 0., hj_max_g = 0., dx_max = 0., rshift = 0.;
+    double hi_max_g = 0., hj_max_g = 0., dx_max = 0., rshift = 0.;
     double di_max_sh = 0., dj_min = 0.;
     int64_t soff = 0;
-    float wadd = 0.f; /* widening of the source radius in the double mode */
+    float wadd = 0.f; /* widening of the radii in the double mode */
 
     if (mode == MODE_SELF) {
       /* DOSELF2 :2624-2875 */
       fsx = sc.loc[0];
       fsy = sc.loc[1];
       fsz = sc.loc[2];
-      tpx = dsubf(tx, fsx);
-      tpy = dsubf(ty, fsy);
-      tpz = dsubf(tz, fsz);
+      otx = fsx; /* prefilter frame only; the drain uses ot = 0 */
+      oty = fsy;
+      otz = fsz;
       wadd = 4.0e-6f * sc.width;
-      const float re = fmaf(thg, PREFILTER_REL, wadd);
-      r2e = re * re;
     } else {
       /* ---- DOPAIR2 ---- */
       sorted = true;
@@ -768,42 +839,69 @@ __global__ void __launch_bounds__(32) k_loop2(const LoopArgs A) {
       di_max_sh = __dsub_rn(di_max, rshift);
       const double oix = __dadd_rn(cj.loc[0], shx), oiy = __dadd_rn(cj.loc[1], shy),
                    oiz = __dadd_rn(cj.loc[2], shz);
-      const float tkey = sort_key(tx, ty, tz, sid);
-      double t_di = -1.0e300, t_keysh = 0., t_dj = 1.0e300;
       if (tleft) {
-        const bool inA =
-            __dsub_rn(__dadd_rn(__dadd_rn((double)tkey, hi_max_g), dx_max), rshift) > dj_min;
-        const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(tkey, thg), dx_max), rshift);
-        if (inA && !(di < dj_min)) t_di = di;
-        t_keysh = __dsub_rn((double)tkey, rshift);
         otx = oix;
         oty = oiy;
         otz = oiz;
         fsx = cj.loc[0];
         fsy = cj.loc[1];
         fsz = cj.loc[2];
-        /* sources j ascending; j can matter while key_j - hj_max*g - dx_max <= max(di, keysh) */
-        reach = warp_max_d(part ? fmax(t_di, t_keysh) : -1.0e300);
         soff = soff_j;
       } else {
-        const bool inB = __dsub_rn(__dsub_rn((double)tkey, hj_max_g), dx_max) < di_max_sh;
-        const double dj = __dsub_rn((double)__fsub_rn(tkey, thg), dx_max);
-        if (inB && !(dj > di_max_sh)) t_dj = dj;
         otx = cj.loc[0];
         oty = cj.loc[1];
         otz = cj.loc[2];
         fsx = oix;
         fsy = oiy;
         fsz = oiz;
-        /* sources i descending; i can matter while key_i + hi_max*g + dx_max - rshift >= min(key_t, dj) */
-        reach = warp_min_d(part ? fmin((double)tkey, t_dj) : 1.0e300);
         soff = soff_i;
       }
-      tpx = dsubf(tx, otx);
-      tpy = dsubf(ty, oty);
-      tpz = dsubf(tz, otz);
     }
-    if (!part) tpx = 3.0e30f;
+
+    float tp[TPL][3], r2e[TPL], thr_unused[TPL];
+    bool anypart = false;
+    double reach_l = tleft ? -1.0e300 : 1.0e300;
+#pragma unroll
+    for (int u = 0; u < TPL; u++) {
+      const bool part = tvalid[u] && tdepth[u] >= I.min_depth && tdepth[u] <= I.max_depth;
+      thr_unused[u] = 0.f;
+      tp[u][0] = dsubf(tx[u], otx);
+      tp[u][1] = dsubf(ty[u], oty);
+      tp[u][2] = dsubf(tz[u], otz);
+      if (!sorted) {
+        const float re = fmaf(thg[u], PREFILTER_REL, wadd);
+        r2e[u] = re * re;
+      } else {
+        r2e[u] = __fmul_rn(thg2[u], PREFILTER_REL);
+        /* Conservative reach along the axis for the sorted early exit. */
+        const float tkey = sort_key(tx[u], ty[u], tz[u], sid);
+        if (tleft) {
+          double t_di = -1.0e300;
+          const bool inA =
+              __dsub_rn(__dadd_rn(__dadd_rn((double)tkey, hi_max_g), dx_max), rshift) > dj_min;
+          const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(tkey, thg[u]), dx_max), rshift);
+          if (inA && !(di < dj_min)) t_di = di;
+          const double t_keysh = __dsub_rn((double)tkey, rshift);
+          /* sources j ascending; j can matter while key_j - hj_max*g - dx_max <= max(di, keysh) */
+          if (part) reach_l = fmax(reach_l, fmax(t_di, t_keysh));
+        } else {
+          double t_dj = 1.0e300;
+          const bool inB = __dsub_rn(__dsub_rn((double)tkey, hj_max_g), dx_max) < di_max_sh;
+          const double dj = __dsub_rn((double)__fsub_rn(tkey, thg[u]), dx_max);
+          if (inB && !(dj > di_max_sh)) t_dj = dj;
+          /* sources i descending; i can matter while key_i + hi_max*g + dx_max - rshift >= min(key_t, dj) */
+          if (part) reach_l = fmin(reach_l, fmin((double)tkey, t_dj));
+        }
+      }
+      if (part)
+        anypart = true;
+      else
+        tp[u][0] = 3.0e30f;
+    }
+    if (!__any_sync(FULL_MASK, anypart)) continue;
+    double reach = 0.;
+    if (sorted) reach = tleft ? warp_max_d(reach_l) : warp_min_d(reach_l);
+    if (!sorted) otx = oty = otz = 0.; /* MODE_SELF: the drain subtracts the doubles directly */
 
     for (int base = 0; base < scount; base += 32) {
       const int k = base + lane;
@@ -829,7 +927,12 @@ __global__ void __launch_bounds__(32) k_loop2(const LoopArgs A) {
           if (fk + hi_max_g + dx_max - rshift + slack < reach) break;
         }
       }
-      if (nst + 32 > SCAP2 || __any_sync(FULL_MASK, nlist > LCAP - 32)) drain();
+      {
+        bool full = nst + 32 > SCAP2;
+#pragma unroll
+        for (int u = 0; u < TPL; u++) full = full || (nlist[u] > LCAP - 32);
+        if (__any_sync(FULL_MASK, full)) drain();
+      }
       const int slot = nst + lane;
       if (k < scount) {
         const float4 q2 = A.fq2[sj];
@@ -870,28 +973,34 @@ __global__ void __launch_bounds__(32) k_loop2(const LoopArgs A) {
       }
       __syncwarp();
       nchunks++;
-      test_chunk<3>(T.F(), nst, tpx, tpy, tpz, r2e, 0.f, lp, nlist);
+      test_chunk<3>(T.F(), nst, tp, r2e, thr_unused, lp, nlist);
       nst += 32;
     }
   }
   drain();
 
-  if (tvalid) {
-    float *po = (float *)&A.fo1[ti];
-    atomicAdd(po + 0, acc.ax);
-    atomicAdd(po + 1, acc.ay);
-    atomicAdd(po + 2, acc.az);
-    atomicAdd(po + 3, acc.u_dt);
-    atomicAdd(&A.f_hdt[ti], acc.h_dt);
-    if (SCHEME != SCH_SPHENIX) atomic_max_pos(&A.f_vsig[ti], acc.v_sig);
-    atomicMin(&A.f_minngb[ti], acc.min_ngb);
-    if (nhit) atomicAdd(&A.count[ti], nhit);
+  int tot = 0;
+#pragma unroll
+  for (int u = 0; u < TPL; u++) {
+    if (tvalid[u]) {
+      const int p = ti[u];
+      float *po = (float *)&A.fo1[p];
+      atomicAdd(po + 0, acc[u].ax);
+      atomicAdd(po + 1, acc[u].ay);
+      atomicAdd(po + 2, acc[u].az);
+      atomicAdd(po + 3, acc[u].u_dt);
+      atomicAdd(&A.f_hdt[p], acc[u].h_dt);
+      if (SCHEME != SCH_SPHENIX) atomic_max_pos(&A.f_vsig[p], acc[u].v_sig);
+      atomicMin(&A.f_minngb[p], acc[u].min_ngb);
+      if (nhit[u]) atomicAdd(&A.count[p], nhit[u]);
+    }
+    tot += nhit[u];
   }
-  int tot = nhit;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL_MASK, tot, o);
   if (lane == 0 && tot) atomicAdd(A.total, (unsigned long long)tot);
-  if (lane == 0 && nchunks) atomicAdd(A.tests, (unsigned long long)nchunks * 1024ull);
+  if (lane == 0 && nchunks)
+    atomicAdd(A.tests, (unsigned long long)nchunks * (unsigned long long)(1024 * TPL));
 }
 
 }  // namespace swiftgpu

@@ -890,7 +890,7 @@ static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
   }
   for (int32_t g : order) {
     const swiftgpu_cell &c = h->cells[W.groups[g].tcell];
-    const int nch = (c.count + 31) / 32;
+    const int nch = (c.count + TASK_TARGETS - 1) / TASK_TARGETS;
     for (int k = 0; k < nch; k++) {
       tg.push_back(g);
       tc.push_back(k);
