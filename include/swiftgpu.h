@@ -263,11 +263,42 @@ int swiftgpu_worklist_stats(const swiftgpu_config *cfg, const swiftgpu_step *ste
                             const int32_t *top, int32_t ntop, int loop,
                             int64_t out[6]);
 
-/* Multi-GPU halo exchange (replaces send/recv xv, rho, gradient tasks,
- * scheduler.c:977-988,1088-1112). `nccl_comm` is an ncclComm_t created by the
- * caller (one rank per GPU); phase: 0 = xv, 1 = rho, 2 = gradient. */
-int swiftgpu_halo_setup(swiftgpu_t *h, void *nccl_comm);
+/*
+ * Multi-GPU: one rank (process) per GPU, top-level cells assigned to ranks by
+ * the reference's partition (cell.nodeID, src/partition.c:104-121). A rank
+ * uploads its own cells plus a read-only copy of every foreign top-level cell
+ * adjacent to one of them (the reference's proxies, src/engine_proxy.c). The
+ * halo exchange replaces the send/recv tasks of the reference
+ * (scheduler.c:977-988,1088-1112; dependencies engine_maketasks.c:208-330):
+ *   phase 0 "xv"        before density:  x, v, m, h, u, time_bin, depth_h and
+ *                                        the force-union members of inactive parts
+ *   phase 1 "rho"       after the ghost: h, rho, depth_h, P|P/rho^2, c_s, f,
+ *                                        balsara, (alpha); then h_max/h_max_active
+ *                                        of the foreign cells are recomputed like
+ *                                        runner_do_recv_part (runner_recv.c:95-137)
+ *   phase 2 "gradient"  after the extra ghost (SPHENIX): alpha_visc, alpha_diff
+ * Transport is NCCL point-to-point (grouped ncclSend/ncclRecv of device-packed
+ * SoA slabs) over NVLink; libnccl.so.2 is resolved at run time.
+ *
+ * swiftgpu_nccl_unique_id: rank 0 obtains the 128-byte NCCL id and distributes
+ * it by any means (MPI_Bcast in SWIFT, torch.distributed in the benchmark);
+ * swiftgpu_halo_setup creates the communicator (cfg.rank / cfg.nranks) and the
+ * send/receive lists from the uploaded cells. swiftgpu_run_step() performs the
+ * three exchanges itself once the halo is set up.
+ */
+int swiftgpu_nccl_unique_id(void *id128);
+int swiftgpu_halo_setup(swiftgpu_t *h, const void *id128);
 int swiftgpu_halo_exchange(swiftgpu_t *h, int phase);
+
+/* Host-only: the halo plan of this rank for `peer`, from the cells alone.
+ * Fills send_cells / recv_cells (capacity ntop each) with indices into
+ * `cells` of the top-level cells sent to / received from that peer, both
+ * ordered by cell location so that the two sides agree without negotiation,
+ * and the particle totals. */
+int swiftgpu_halo_plan(const swiftgpu_config *cfg, const swiftgpu_cell *cells, int32_t ncells,
+                       const int32_t *top, int32_t ntop, int32_t peer, int32_t *send_cells,
+                       int32_t *nsend_cells, int32_t *recv_cells, int32_t *nrecv_cells,
+                       int64_t *nsend_parts, int64_t *nrecv_parts);
 
 #ifdef __cplusplus
 }

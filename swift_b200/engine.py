@@ -12,6 +12,16 @@ import numpy as np
 from . import abi
 
 
+def nccl_unique_id():
+    """128-byte NCCL id (call on rank 0, broadcast to the other ranks)."""
+    lib = abi.load()
+    buf = (C.c_char * 128)()
+    if lib.swiftgpu_nccl_unique_id(C.addressof(buf)) != 0:
+        msg = lib.swiftgpu_last_error(None)
+        raise RuntimeError(f"swiftgpu_nccl_unique_id failed: {msg.decode() if msg else ''}")
+    return bytes(buf)
+
+
 class SwiftGPU:
     def __init__(self, cfg):
         self.lib = abi.load()
@@ -55,6 +65,14 @@ class SwiftGPU:
     def set_stream(self, cuda_stream):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
         self._ck(self.lib.swiftgpu_set_stream(self.h, cuda_stream), "set_stream")
+
+    def halo_setup(self, unique_id):
+        """unique_id: the 128 bytes of swiftgpu_nccl_unique_id() obtained on rank 0."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.swiftgpu_halo_setup(self.h, C.addressof(buf)), "halo_setup")
+
+    def halo_exchange(self, phase):
+        self._ck(self.lib.swiftgpu_halo_exchange(self.h, phase), "halo_exchange")
 
     def run_sort(self):
         self._ck(self.lib.swiftgpu_run_sort(self.h), "run_sort")

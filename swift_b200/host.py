@@ -228,3 +228,65 @@ def step_scalars(max_active_bin=56):
     if max_active_bin >= 56:
         return dict(ti_current=8, max_active_bin=56, time_base=1e-6)
     return dict(ti_current=3 * (1 << (max_active_bin + 1)), max_active_bin=max_active_bin, time_base=1e-6)
+
+
+# ---------------------------------------------------------------------------
+# Multi-GPU: what one rank holds. The reference keeps, on every rank, its own
+# top-level cells plus a proxy copy of every foreign top-level cell that
+# touches one of them (src/engine_proxy.c; a pair task exists iff at least one
+# side is local, engine_maketasks.c:3562-3569).
+# ---------------------------------------------------------------------------
+def extract_rank(tree, parts_u8, layout, rank, periodic=True):
+    """Sub-tree + particles of `rank`: local top-level cells and their foreign
+    neighbours. Returns (Tree, parts_u8, sel, is_local) where sel[k] is the
+    index in the global (cell-ordered) particle array of local particle k."""
+    cells, top = tree.cells, np.asarray(tree.top)
+    ntop = top.shape[0]
+    tc = cells[top]
+    cdim = np.maximum(np.floor(1.0 / 1.0 + 0.5), 1)  # placeholder, replaced below
+    width = tc["width"][0]
+    idx3 = np.floor(tc["loc"] / tc["width"] + 0.5).astype(np.int64)
+    cdim = idx3.max(axis=0) + 1
+    grid = -np.ones(tuple(cdim), dtype=np.int64)
+    grid[idx3[:, 0], idx3[:, 1], idx3[:, 2]] = np.arange(ntop)
+    local = tc["nodeID"] == rank
+    keep = local.copy()
+    li = idx3[local]
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                j = li + np.array([dx, dy, dz])
+                if periodic:
+                    j = np.mod(j, cdim)
+                    ok = np.ones(len(j), bool)
+                else:
+                    ok = ((j >= 0) & (j < cdim)).all(axis=1)
+                    j = np.clip(j, 0, cdim - 1)
+                g = grid[j[:, 0], j[:, 1], j[:, 2]]
+                keep[g[ok & (g >= 0)]] = True
+    pos = -np.ones(cells.shape[0], dtype=np.int64)
+    pos[top] = np.arange(ntop)
+    cell_keep = keep[pos[cells["top"]]]
+    new_index = np.cumsum(cell_keep) - 1
+    new_index[~cell_keep] = -1
+    sub = cells[cell_keep].copy()
+    # particle ranges of the kept top-level cells, in `top` order
+    kept_top = top[keep]
+    counts = cells["count"][kept_top].astype(np.int64)
+    offs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    top_off = np.zeros(ntop, dtype=np.int64)
+    top_off[keep] = offs
+    top_first = cells["first_part"][top]
+    tpos = pos[sub["top"]]
+    sub["first_part"] = top_off[tpos] + (sub["first_part"] - top_first[tpos])
+    for name in ("parent", "top"):
+        v = sub[name]
+        sub[name] = np.where(v >= 0, new_index[np.maximum(v, 0)], -1)
+    pr = sub["progeny"]
+    sub["progeny"] = np.where(pr >= 0, new_index[np.maximum(pr, 0)], -1)
+    sel = np.concatenate([np.arange(f, f + c) for f, c in zip(top_first[keep], counts)]) if len(counts) else np.zeros(0, np.int64)
+    size = layout.size
+    sub_parts = np.ascontiguousarray(parts_u8.reshape(-1, size)[sel]).reshape(-1)
+    new_top = new_index[kept_top].astype(np.int32)
+    is_local = np.repeat(cells["nodeID"][kept_top] == rank, counts)
+    return Tree(sub, new_top, tree.perm[sel], tree.depth_h[sel]), sub_parts, sel, is_local

@@ -112,7 +112,9 @@ def compare_fields(got_u8, ref_u8, layout, names, rtol, report=None, floors=None
 #    is the size of the un-cancelled pair sum, 48 m (P/rho^2) 2 / h^4 -- the
 #    "ignore-below" column of the reference's tests/difffloat.py.
 # ---------------------------------------------------------------------------
-def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4):
+def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None):
+    """only: boolean mask of the particles whose fields are compared (flips are
+    detected on all of them: a flipped foreign neighbour dirties local ones)."""
     from scipy.spatial import cKDTree
     f = lambda a, n: host.field(a, layout, n).astype(np.float64)  # noqa: E731
     hg, hr = f(got, "h"), f(ref, "h")
@@ -128,6 +130,8 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4):
         for i in np.nonzero(flip)[0]:
             dirty[tree.query_ball_point(np.mod(x[i], 1.0) if box.max() <= 1.0 else x[i], reach)] = True
     clean = ~dirty
+    if only is not None:
+        clean = clean & np.asarray(only, bool)
     rep = {"n": n, "flips": int(flip.sum()), "flip_max": float(herr.max()), "dirty": int(dirty.sum())}
     rho = f(ref, "rho")
     m = f(ref, "mass")
