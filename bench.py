@@ -59,20 +59,41 @@ WORKLOADS = {
 }
 
 
-def make_workload(name):
+GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}  # partition.c:112-120 bricks
+
+
+def make_workload(name, world=1, rank=0):
+    """Builds the case of `rank`. world > 1: WEAK scaling - the box is made of
+    one L^3 brick per GPU (brick grid GRIDS[world]); the rank keeps its brick
+    and a proxy copy of the foreign top-level cells that touch it."""
     import util
     from swift_b200 import abi, host
     scheme, L, gen = WORKLOADS[name]
     sid = abi.SCHEMES[scheme]
+    bricks = GRIDS[world]
+    if world > 1 and gen in ("uniform", "clustered"):
+        raise SystemExit(f"workload {name} has no multi-GPU generator")
     if gen == "uniform":
         ic = host.uniform_box(L, sid)
     elif gen == "sedov":
-        ic = host.sedov_box(L, sid)
+        ic = host.sedov_box(L, sid, bricks=bricks)
     elif gen == "clustered":
         ic = host.clustered_box(L, sid)
     else:
-        ic = host.jittered_box(L, sid, jitter=0.2, seed=42)
-    c = util.make_case(scheme, ic, host.default_top_grid(L))
+        ic = host.jittered_box(L, sid, jitter=0.2, seed=42, bricks=bricks)
+    tg = host.default_top_grid(L)
+    cdim = tuple(t * b for t, b in zip(tg, bricks))
+    dim = tuple(float(b) for b in bricks)
+    c = util.make_case(scheme, ic, cdim, rank_grid=bricks, rank=rank, dim=dim, pack=(world == 1))
+    c.sub_tree = c.tree
+    if world > 1:
+        sub, _, sel, is_local = host.extract_rank(c.tree, None, c.layout, rank)
+        c.sub_tree = sub
+        c.parts = host.pack_parts(c.layout, c.scheme, sub, ic)
+        c.n_local = int(is_local.sum())
+        c.n = int(sel.shape[0])
+    else:
+        c.n_local = c.n
     return c
 
 
@@ -92,7 +113,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.samples.append(line.strip())
@@ -208,7 +229,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="swiftgpu")
     ap.add_argument("--workload", default=None)
@@ -236,7 +257,9 @@ def main():
 
     args.warmup = max(args.warmup, 3)
     scheme = WORKLOADS[args.workload][0]
-    c = make_workload(args.workload)
+    if world not in GRIDS:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    c = make_workload(args.workload, world, rank)
     c.cfg.device = local_rank
     n = c.n
     psize = c.layout.size
@@ -244,8 +267,15 @@ def main():
     g = SwiftGPU(c.cfg)
     stream = torch.cuda.Stream()
     g.set_stream(stream.cuda_stream)
-    g.upload_cells(c.tree.cells, c.tree.top)
+    g.upload_cells(c.sub_tree.cells, c.sub_tree.top)
     g.set_step(c.step)
+    if world > 1:
+        from swift_b200.engine import nccl_unique_id
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        g.halo_setup(idt.cpu().numpy().tobytes())
 
     host_in = torch.from_numpy(c.parts).pin_memory()
     host_out = torch.empty_like(host_in).pin_memory()
@@ -325,12 +355,11 @@ def main():
     ms_force = phase_ms["force"] / args.steps
     ms_density = phase_ms["density"] / args.steps
     fl_force = FLOPS["force_" + scheme]
-    n_active = int((nf >= 0).sum()) if True else n
     cand = {"density": st.t_density, "gradient": st.t_gradient, "force": st.t_force}
+    # (CUDA-event ms of the phase = one launch of the loop kernel, algorithmic flops, algorithmic bytes)
     kernels = {
-        "force": (ms_force, float(nf.sum()) * fl_force, n * BYTES["force"]),
-        "density": (ms_density, float(st.n_density - 0) * FLOPS["density"] if False else float(nd.sum()) * FLOPS["density"],
-                    n * BYTES["density"]),
+        "force": (ms_force, float(nf.sum()) * fl_force, c.n_local * BYTES["force"]),
+        "density": (ms_density, float(nd.sum()) * FLOPS["density"], c.n_local * BYTES["density"]),
     }
     dom = max(kernels, key=lambda k: kernels[k][0])
     kms, kflops, kbytes = kernels[dom]
@@ -341,7 +370,7 @@ def main():
                 "traffic": None,
                 "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peak_src})",
                 "ms_per_launch": kms, "flops_per_interaction": fl_force if dom == "force" else FLOPS["density"],
-                "candidates_per_hit": (cand[dom] / max(1.0, float(nf.sum() if dom == "force" else st.n_density)))}
+                "candidates_per_hit": (cand[dom] / max(1.0, float(nf.sum() if dom == "force" else nd.sum())))}
     roofline_hbm = {"bound": "hbm", "kernel": roofline["kernel"], "achieved": achieved_gbs, "peak": hbm_peak,
                     "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": None,
                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})"}
@@ -349,9 +378,11 @@ def main():
     line = {
         "metric": "SPH pair interactions/s (density+gradient+force)", "value": value, "unit": "interactions/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak" if world > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "scheme": scheme, "particles": n * world, "active_fraction": 1.0,
+        "config": {"workload": args.workload + ("" if world == 1 else " x%d bricks %s (weak scaling: one brick per GPU)" % (world, "x".join(map(str, GRIDS[world])))),
+                   "scheme": scheme, "particles": int(c.n_local) * world, "particles_per_gpu_incl_halo": int(n),
+                   "active_fraction": 1.0,
                    "l2": "inputs larger than L2 (%.0f MB AoS + SoA state per step)" % (n * psize / 1e6),
                    "top_grid": list(host.default_top_grid(WORKLOADS[args.workload][1])),
                    "ghost_iterations": int(st.ghost_iterations)},

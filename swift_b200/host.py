@@ -72,7 +72,7 @@ def build_tree(x, h, time_bin, dim, cdim, max_active_bin, ti_current,
 def pack_parts(layout, scheme, tree, ic):
     """AoS struct part[] in cell order (what space->parts holds)."""
     host = abi.load_host()
-    n = ic["x"].shape[0]
+    n = int(tree.perm.shape[0])  # a rank's sub-tree packs only its own particles
     out = np.zeros(n * layout.size, dtype=np.uint8)
 
     def p(a, dt):
@@ -129,16 +129,18 @@ def uniform_box(L=32, scheme=abi.SCHEME_MINIMAL, rho=2.0, P=1.0, eta=1.2349, box
 
 
 def jittered_box(L, scheme, jitter=0.2, seed=42, eta=1.2348, box=1.0, rho=1.0,
-                 u0=1.0, vamp=0.05, h_scatter=0.0, active_fraction=1.0):
+                 u0=1.0, vamp=0.05, h_scatter=0.0, active_fraction=1.0, bricks=(1, 1, 1)):
     """Lattice + uniform jitter (+-jitter spacing); smooth solenoidal-ish
     velocity field; optionally scattered h (to exercise the ghost) and a
-    multi-time-step active subset clustered in space."""
+    multi-time-step active subset clustered in space. bricks=(bx,by,bz) makes
+    a box of bx*by*bz unit bricks of L^3 particles each (weak scaling)."""
     rng = np.random.default_rng(seed)
-    n = L ** 3
-    g = (np.arange(L) + 0.5) / L
-    x = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(n, 3)
+    Ls = [L * b for b in bricks]
+    n = Ls[0] * Ls[1] * Ls[2]
+    gs = [(np.arange(m) + 0.5) / L for m in Ls]
+    x = np.stack(np.meshgrid(*gs, indexing="ij"), axis=-1).reshape(n, 3)
     x = x + rng.uniform(-jitter, jitter, size=(n, 3)) / L
-    x = np.mod(x, 1.0) * box
+    x = np.mod(x, np.array(bricks, dtype=np.float64)) * box
     k = 2 * np.pi / box
     v = np.stack([np.sin(k * x[:, 1]) + 0.5 * np.cos(2 * k * x[:, 2]),
                   np.sin(k * x[:, 2]) + 0.5 * np.cos(2 * k * x[:, 0]),
@@ -147,7 +149,7 @@ def jittered_box(L, scheme, jitter=0.2, seed=42, eta=1.2348, box=1.0, rho=1.0,
     if h_scatter > 0:
         h = h * np.exp(rng.uniform(-h_scatter, h_scatter, size=n))
     u = u0 * (1.0 + 0.1 * np.sin(k * x[:, 0]) * np.cos(k * x[:, 1]))
-    ic = {"x": x, "v": v.astype(np.float32), "mass": np.full(n, rho * box ** 3 / n, np.float32),
+    ic = {"x": x, "v": v.astype(np.float32), "mass": np.full(n, rho * box ** 3 / L ** 3, np.float32),
           "h": h.astype(np.float32), "u": u.astype(np.float32), "_rho0": rho}
     tb = None
     if active_fraction < 1.0:
@@ -158,13 +160,15 @@ def jittered_box(L, scheme, jitter=0.2, seed=42, eta=1.2348, box=1.0, rho=1.0,
     return _finish(ic, scheme, n, tb)
 
 
-def sedov_box(L=128, scheme=abi.SCHEME_GADGET2, seed=1234, eta=1.2348, E0=1.0, P0=1e-6, rho0=1.0):
+def sedov_box(L=128, scheme=abi.SCHEME_GADGET2, seed=1234, eta=1.2348, E0=1.0, P0=1e-6, rho0=1.0,
+              bricks=(1, 1, 1)):
     """SedovBlast_3D/makeIC.py:24-58 on a perturbed lattice: E0 shared by the
     15 particles nearest the centre."""
-    ic = jittered_box(L, abi.SCHEME_MINIMAL, jitter=0.1, seed=seed, eta=eta, rho=rho0, vamp=0.0)
-    n = L ** 3
+    ic = jittered_box(L, abi.SCHEME_MINIMAL, jitter=0.1, seed=seed, eta=eta, rho=rho0, vamp=0.0,
+                      bricks=bricks)
+    n = ic["x"].shape[0]
     u = np.full(n, P0 / ((HYDRO_GAMMA - 1.0) * rho0))
-    r2 = ((ic["x"] - 0.5) ** 2).sum(axis=1)
+    r2 = ((ic["x"] - 0.5 * np.array(bricks, dtype=np.float64)) ** 2).sum(axis=1)
     centre = np.argsort(r2)[:15]
     u[centre] = E0 / (15 * ic["mass"][0])
     ic["u"] = u.astype(np.float32)
@@ -237,14 +241,13 @@ def step_scalars(max_active_bin=56):
 # side is local, engine_maketasks.c:3562-3569).
 # ---------------------------------------------------------------------------
 def extract_rank(tree, parts_u8, layout, rank, periodic=True):
+    # parts_u8 may be None: pack the returned sub-tree with pack_parts() instead
     """Sub-tree + particles of `rank`: local top-level cells and their foreign
     neighbours. Returns (Tree, parts_u8, sel, is_local) where sel[k] is the
     index in the global (cell-ordered) particle array of local particle k."""
     cells, top = tree.cells, np.asarray(tree.top)
     ntop = top.shape[0]
     tc = cells[top]
-    cdim = np.maximum(np.floor(1.0 / 1.0 + 0.5), 1)  # placeholder, replaced below
-    width = tc["width"][0]
     idx3 = np.floor(tc["loc"] / tc["width"] + 0.5).astype(np.int64)
     cdim = idx3.max(axis=0) + 1
     grid = -np.ones(tuple(cdim), dtype=np.int64)
@@ -286,7 +289,9 @@ def extract_rank(tree, parts_u8, layout, rank, periodic=True):
     sub["progeny"] = np.where(pr >= 0, new_index[np.maximum(pr, 0)], -1)
     sel = np.concatenate([np.arange(f, f + c) for f, c in zip(top_first[keep], counts)]) if len(counts) else np.zeros(0, np.int64)
     size = layout.size
-    sub_parts = np.ascontiguousarray(parts_u8.reshape(-1, size)[sel]).reshape(-1)
+    sub_parts = None
+    if parts_u8 is not None:
+        sub_parts = np.ascontiguousarray(parts_u8.reshape(-1, size)[sel]).reshape(-1)
     new_top = new_index[kept_top].astype(np.int32)
     is_local = np.repeat(cells["nodeID"][kept_top] == rank, counts)
     return Tree(sub, new_top, tree.perm[sel], tree.depth_h[sel]), sub_parts, sel, is_local

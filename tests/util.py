@@ -20,13 +20,14 @@ def golden_layout(variant):
     return abi.PartLayout.from_dict(d)
 
 
-def make_config(scheme, layout, rank=0, nranks=1, h_tolerance=1e-4, max_iter=30, h_max=1e10):
+def make_config(scheme, layout, rank=0, nranks=1, h_tolerance=1e-4, max_iter=30, h_max=1e10,
+                dim=(1.0, 1.0, 1.0)):
     cfg = abi.Config()
     cfg.abi_version = 1
     cfg.scheme = scheme
     cfg.device = 0
     cfg.periodic = 1
-    cfg.dim[:] = [1.0, 1.0, 1.0]
+    cfg.dim[:] = list(dim)
     cfg.eta_neighbours = 1.2348
     cfg.h_tolerance = h_tolerance
     cfg.h_max = h_max
@@ -55,17 +56,18 @@ class Case:
     pass
 
 
-def make_case(scheme_name, ic, cdim, layout=None, max_active_bin=56, rank_grid=(1, 1, 1), rank=0, **cfg_kw):
+def make_case(scheme_name, ic, cdim, layout=None, max_active_bin=56, rank_grid=(1, 1, 1), rank=0,
+              dim=(1.0, 1.0, 1.0), pack=True, **cfg_kw):
     c = Case()
     c.scheme_name = scheme_name
     c.scheme = abi.SCHEMES[scheme_name]
     c.layout = layout if layout is not None else golden_layout(scheme_name)
     nranks = rank_grid[0] * rank_grid[1] * rank_grid[2]
-    c.cfg = make_config(c.scheme, c.layout, rank=rank, nranks=nranks, **cfg_kw)
+    c.cfg = make_config(c.scheme, c.layout, rank=rank, nranks=nranks, dim=dim, **cfg_kw)
     c.step = make_step(max_active_bin)
-    c.tree = host.build_tree(ic["x"], ic["h"], ic["time_bin"], (1.0, 1.0, 1.0), cdim,
+    c.tree = host.build_tree(ic["x"], ic["h"], ic["time_bin"], tuple(dim), cdim,
                              c.step.max_active_bin, c.step.ti_current, rank_grid=rank_grid)
-    c.parts = host.pack_parts(c.layout, c.scheme, c.tree, ic)
+    c.parts = host.pack_parts(c.layout, c.scheme, c.tree, ic) if pack else None
     c.n = ic["x"].shape[0]
     c.ic = ic
     return c
