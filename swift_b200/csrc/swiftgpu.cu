@@ -22,7 +22,7 @@
 #include <vector>
 
 #include "../../include/swiftgpu.h"
-#include "loops.cuh"
+#include "loops_cta.cuh"
 
 using namespace swiftgpu;
 
@@ -1201,6 +1201,33 @@ static int read_counter(H *h, int k, int64_t *out) {
   return 0;
 }
 
+/* CTA-cooperative type-1 loops (loops_cta.cuh); SWIFTGPU_WARP_LOOPS=1 selects the
+ * warp-private kernels of loops.cuh instead (kept for A/B measurements). */
+static bool use_cta_loops() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SWIFTGPU_WARP_LOOPS");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <int LOOP, bool SUBSET>
+static cudaError_t launch_loop1(H *h, const LoopArgs &A) {
+  if (use_cta_loops()) {
+    constexpr int bytes = CtaSmem<(LOOP == LOOP_GRADIENT ? 2 : 1), SUBSET>::kBytes;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(k_cta1<LOOP, SUBSET>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    k_cta1<LOOP, SUBSET><<<A.ntasks, CTA_THREADS, bytes, h->stream>>>(A);
+  } else {
+    k_loop1<LOOP, SUBSET><<<A.ntasks, 32, Tile1<LOOP, SUBSET>::kBytes, h->stream>>>(A);
+  }
+  return cudaGetLastError();
+}
+
 extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   if (!h) return 1;
   if (ensure_lists(h)) return 1;
@@ -1218,9 +1245,8 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   if (build_targets(h, h->L_density)) return 1;
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->nd, 0);
-    k_loop1<LOOP_DENSITY, false><<<A.ntasks, 32, Tile1<LOOP_DENSITY, false>::kBytes, h->stream>>>(A);
+    CK((launch_loop1<LOOP_DENSITY, false>(h, A)));
     h->stats.n_launches++;
-    CK(cudaGetLastError());
   }
   h->phases_done |= SWIFTGPU_PHASE_DENSITY;
   h->phases_done &= ~(uint32_t)(SWIFTGPU_PHASE_GHOST | SWIFTGPU_PHASE_GRADIENT |
@@ -1293,9 +1319,8 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
        * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
       CK(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long), h->stream));
       LoopArgs A = loop_args(h, D, h->nd, 4);
-      k_loop1<LOOP_DENSITY, true><<<A.ntasks, 32, Tile1<LOOP_DENSITY, true>::kBytes, h->stream>>>(A);
+      CK((launch_loop1<LOOP_DENSITY, true>(h, A)));
       h->stats.n_launches++;
-      CK(cudaGetLastError());
       int64_t nn = 0;
       if (read_counter(h, 4, &nn)) return 1;
       extra_density += nn;
@@ -1320,9 +1345,8 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->ng, 1);
-    k_loop1<LOOP_GRADIENT, false><<<A.ntasks, 32, Tile1<LOOP_GRADIENT, false>::kBytes, h->stream>>>(A);
+    CK((launch_loop1<LOOP_GRADIENT, false>(h, A)));
     h->stats.n_launches++;
-    CK(cudaGetLastError());
   }
   h->phases_done |= SWIFTGPU_PHASE_GRADIENT;
   if (phase_end(h, &h->stats.ms_gradient)) return 1;
