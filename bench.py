@@ -106,9 +106,10 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []   # (host time, csv line)
         self.stop_flag = False
         self.proc = None
+        self.window = (0.0, float("inf"))
 
     def run(self):
         try:
@@ -116,7 +117,7 @@ class ClockSampler(threading.Thread):
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.samples.append(line.strip())
+                self.samples.append((time.time(), line.strip()))
                 if self.stop_flag:
                     break
         except Exception:
@@ -133,7 +134,10 @@ class ClockSampler(threading.Thread):
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for s in self.samples:
+        inside = [s for (t, s) in self.samples if self.window[0] <= t <= self.window[1] + 0.15]
+        if not inside:  # timed region shorter than the sampling period: nearest samples under load
+            inside = [s for (t, s) in self.samples if t >= self.window[0] - 1.0]
+        for s in inside:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -300,12 +304,13 @@ def main():
 
     with torch.cuda.stream(stream):
         # ---- device-resident timing ----
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(args.warmup):
             step_device()
         l0 = g.stats().n_launches
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         barrier()
+        t_begin = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         phase_ms = {k: 0.0 for k in ("sort", "density", "ghost", "gradient", "extra_ghost", "force", "end_force")}
         e0.record(stream)
@@ -316,7 +321,7 @@ def main():
                 phase_ms[k] += getattr(st, "ms_" + k)
         e1.record(stream)
         barrier()
-        sampler.stop()
+        sampler.window = (t_begin, time.time())
         ms_total = e0.elapsed_time(e1)
         st = g.stats()
         launches = st.n_launches - l0
@@ -333,6 +338,7 @@ def main():
             step_e2e()
         f1.record(stream)
         barrier()
+        sampler.stop()
         ms_e2e = f0.elapsed_time(f1)
 
     # max over ranks
@@ -365,7 +371,7 @@ def main():
     kms, kflops, kbytes = kernels[dom]
     achieved_tf = kflops / (kms * 1e-3) / 1e12
     achieved_gbs = kbytes / (kms * 1e-3) / 1e9
-    roofline = {"bound": "fp32", "kernel": "k_loop2<%s> (force)" % scheme if dom == "force" else "k_loop1<density>",
+    roofline = {"bound": "fp32", "kernel": "k_cta<FORCE,%s>" % scheme if dom == "force" else "k_cta<DENSITY>",
                 "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
                 "traffic": None,
                 "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peak_src})",

@@ -47,7 +47,7 @@ namespace swiftgpu {
 
 #define FULL_MASK 0xffffffffu
 
-/* Device view of one cell (72 bytes). */
+/* Device view of one cell (80 bytes). */
 struct DevCell {
   double loc[3];
   int32_t first;
@@ -63,8 +63,10 @@ struct DevCell {
   int8_t depth;
   uint8_t flags; /* bit0 active, bit1 local, bit2 split */
   float width;   /* max_k width[k] */
+  float dx_max_part; /* how far a particle may sit outside the cell box */
+  int32_t pad_;
 };
-static_assert(sizeof(DevCell) == 72, "DevCell layout");
+static_assert(sizeof(DevCell) == 80, "DevCell layout");
 
 __device__ __forceinline__ int64_t sort_offset(const DevCell &c, int sid) {
   return c.sort_base + (int64_t)__popc((unsigned)c.sort_mask & ((1u << sid) - 1u)) * c.count;

@@ -981,6 +981,7 @@ static int build_lists(H *h, bool force_only) {
     d.sort_mask = 0;
     d.depth = (int8_t)s.depth;
     d.width = (float)std::max(s.width[0], std::max(s.width[1], s.width[2]));
+    d.dx_max_part = s.dx_max_part;
     d.flags = (uint8_t)((s.ti_end_min == h->step.ti_current ? 1 : 0) |
                         (s.nodeID == h->cfg.rank ? 2 : 0) | (s.split ? 4 : 0));
   }
@@ -1211,20 +1212,31 @@ static bool use_cta_loops() {
   }
   return v == 1;
 }
+template <int LOOP, bool SUBSET, int SCHEME>
+static cudaError_t launch_cta(H *h, const LoopArgs &A) {
+  constexpr bool FORCE = (LOOP == LOOP_FORCE);
+  constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
+  constexpr int bytes = CtaSmem<NP, SUBSET, FORCE>::kBytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_cta<LOOP, SUBSET, SCHEME>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  k_cta<LOOP, SUBSET, SCHEME><<<A.ntasks, CTA_THREADS, bytes, h->stream>>>(A);
+  return cudaGetLastError();
+}
 template <int LOOP, bool SUBSET>
 static cudaError_t launch_loop1(H *h, const LoopArgs &A) {
-  if (use_cta_loops()) {
-    constexpr int bytes = CtaSmem<(LOOP == LOOP_GRADIENT ? 2 : 1), SUBSET>::kBytes;
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(k_cta1<LOOP, SUBSET>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      if (e != cudaSuccess) return e;
-      configured = true;
-    }
-    k_cta1<LOOP, SUBSET><<<A.ntasks, CTA_THREADS, bytes, h->stream>>>(A);
-  } else {
-    k_loop1<LOOP, SUBSET><<<A.ntasks, 32, Tile1<LOOP, SUBSET>::kBytes, h->stream>>>(A);
-  }
+  if (use_cta_loops()) return launch_cta<LOOP, SUBSET, 0>(h, A);
+  k_loop1<LOOP, SUBSET><<<A.ntasks, 32, Tile1<LOOP, SUBSET>::kBytes, h->stream>>>(A);
+  return cudaGetLastError();
+}
+template <int SCHEME>
+static cudaError_t launch_loop2(H *h, const LoopArgs &A) {
+  if (use_cta_loops()) return launch_cta<LOOP_FORCE, false, SCHEME>(h, A);
+  k_loop2<SCHEME><<<A.ntasks, 32, Tile2<SCHEME>::kBytes, h->stream>>>(A);
   return cudaGetLastError();
 }
 
@@ -1433,14 +1445,12 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   if (build_targets(h, h->L_force)) return 1;
   if (h->L_force.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_force, h->nf, 2);
-    const unsigned grid = A.ntasks;
     switch (h->cfg.scheme) {
-      case SCH_MINIMAL: k_loop2<SCH_MINIMAL><<<grid, 32, Tile2<SCH_MINIMAL>::kBytes, h->stream>>>(A); break;
-      case SCH_GADGET2: k_loop2<SCH_GADGET2><<<grid, 32, Tile2<SCH_GADGET2>::kBytes, h->stream>>>(A); break;
-      default: k_loop2<SCH_SPHENIX><<<grid, 32, Tile2<SCH_SPHENIX>::kBytes, h->stream>>>(A); break;
+      case SCH_MINIMAL: CK(launch_loop2<SCH_MINIMAL>(h, A)); break;
+      case SCH_GADGET2: CK(launch_loop2<SCH_GADGET2>(h, A)); break;
+      default: CK(launch_loop2<SCH_SPHENIX>(h, A)); break;
     }
     h->stats.n_launches++;
-    CK(cudaGetLastError());
   }
   h->phases_done |= SWIFTGPU_PHASE_FORCE;
   if (phase_end(h, &h->stats.ms_force)) return 1;
