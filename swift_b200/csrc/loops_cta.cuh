@@ -95,7 +95,8 @@ template <int LOOP, bool SUBSET, int SCHEME>
 __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_cta(const LoopArgs A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  typedef CtaSmem<NP, SUBSET, FORCE> SM;
+  constexpr bool STAGE_D = false; /* doubles of dbl-mode candidates come from global memory (L1/L2) */
+  typedef CtaSmem<NP, STAGE_D, FORCE> SM;
   extern __shared__ __align__(16) char smem[];
   float4 *const sF = (float4 *)(smem + SM::kF);
   float4 *const sP0 = (float4 *)(smem + SM::kP);
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
       if (__any_sync(FULL_MASK, dbl)) {
         if (dbl) {
           double sxd, syd, szd;
-          if (SUBSET) {
+          if (STAGE_D) {
             sxd = sD[slot];
             syd = sD[POOL + slot];
             szd = sD[2 * POOL + slot];
@@ -633,8 +634,10 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
             sP2[slot] = q2;
             if (SCHEME == SCH_SPHENIX) sP3[slot] = A.fq3[sj];
           } else {
+            /* w: the sorted-axis condition folded into ONE compare "w < thr":
+             * kc 1 (key < thr): w = key; kc 2 (key > thr): w = -key, thr = -thr; none: w = -inf */
             if (ii.kc) key = sort_key(sx, sy, sz, ii.sid);
-            w = key;
+            w = ii.kc == 1 ? key : (ii.kc == 2 ? -key : -3.4e38f);
             sP0[slot] = A.mv[sj];
             if (LOOP == LOOP_GRADIENT) {
               const float4 q1 = A.fq1[sj];
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
               sP1[slot] = make_float4(q2.z /*u*/, q1.x /*rho*/, q1.w /*cs*/, q3.x /*alpha*/);
             }
           }
-          if (SUBSET) {
+          if (STAGE_D) {
             sD[slot] = sx;
             sD[POOL + slot] = sy;
             sD[2 * POOL + slot] = sz;
@@ -678,7 +681,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
       /* ---------------- cull + test (per warp) ---------------- */
       if (warp_has_targets) {
         int cur = -1;
-        float tpx = 3.0e30f, tpy = 0.f, tpz = 0.f, thr_lo = -3.4e38f, thr_hi = 3.4e38f, r2e = 0.f;
+        float tpx = 3.0e30f, tpy = 0.f, tpz = 0.f, thr_hi = 3.4e38f, r2e = 0.f;
+        int nsub_ub = nsub; /* warp-uniform upper bound of every lane's nsub */
         bool skip = true;
         for (int ob = 0; ob < noct; ob += 32) {
           const int o = ob + lane;
@@ -718,8 +722,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
               tpx = tp.x;
               tpy = tp.y;
               tpz = tp.z;
-              thr_lo = ii.kc == 2 ? tp.w : -3.4e38f;
-              thr_hi = ii.kc == 1 ? tp.w : 3.4e38f;
+              thr_hi = ii.kc == 1 ? tp.w : (ii.kc == 2 ? -tp.w : 3.4e38f);
               if (ii.dbl) {
                 const float re = fmaf(thg, PREFILTER_REL, ii.margin);
                 r2e = re * re;
@@ -729,14 +732,21 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
               skip = !__any_sync(FULL_MASK, tpx < 1.0e30f);
             }
             if (skip) continue;
-            if (__any_sync(FULL_MASK, nsub > SUBCAP - 2)) drain();
+            if (nsub_ub > SUBCAP - 2) {
+              nsub_ub = __reduce_max_sync(FULL_MASK, nsub);
+              if (nsub_ub > SUBCAP - 2) {
+                drain();
+                nsub_ub = 0;
+              }
+            }
+            nsub_ub += 2;
             const int sl = o2 * 8 + 2 * s4;
             const float4 a = sF[sl], c = sF[sl + 1];
-            ntests += 2;
+            ntests++;
             {
               const float dx = tpx - a.x, dy = tpy - a.y, dz = tpz - a.z;
               const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-              const bool ok = FORCE ? (r2 < fmaxf(r2e, a.w)) : (r2 < r2e && a.w < thr_hi && a.w > thr_lo);
+              const bool ok = FORCE ? (r2 < fmaxf(r2e, a.w)) : (r2 < r2e && a.w < thr_hi);
               if (ok) {
                 mylist[nsub * CTA_THREADS] = (uint16_t)sl;
                 nsub++;
@@ -745,7 +755,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
             {
               const float dx = tpx - c.x, dy = tpy - c.y, dz = tpz - c.z;
               const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-              const bool ok = FORCE ? (r2 < fmaxf(r2e, c.w)) : (r2 < r2e && c.w < thr_hi && c.w > thr_lo);
+              const bool ok = FORCE ? (r2 < fmaxf(r2e, c.w)) : (r2 < r2e && c.w < thr_hi);
               if (ok) {
                 mylist[nsub * CTA_THREADS] = (uint16_t)(sl + 1);
                 nsub++;
@@ -829,7 +839,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
     tt += __shfl_xor_sync(FULL_MASK, tt, o);
   }
   if (lane == 0 && tot) atomicAdd(A.total, (unsigned long long)tot);
-  if (lane == 0 && tt) atomicAdd(A.tests, (unsigned long long)tt);
+  if (lane == 0 && tt) atomicAdd(A.tests, 2ull * (unsigned long long)tt);
 }
 
 }  // namespace swiftgpu
