@@ -249,6 +249,12 @@ int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density,
                              int32_t *n_gradient, int32_t *n_force,
                              int64_t nparts);
 int swiftgpu_get_stats(swiftgpu_t *h, swiftgpu_stats *out);
+/* The sorted index array of (cell, sid) - c->hydro.sort of the reference
+ * (sort_part.h:32, runner_sort.c:203; indices relative to the cell's first
+ * particle, ascending key) - and its first / last key. The step itself only
+ * consumes the extrema; the full arrays are produced on demand by this call. */
+int swiftgpu_download_sort(swiftgpu_t *h, int32_t cell, int32_t sid, int32_t *idx_out,
+                           float *key_min, float *key_max);
 
 /* Host-only (no CUDA call): flattens the reference's recursive task functions
  * (DOSUB_SELF1/PAIR1 for loop 0 = density/gradient, DOSUB_SELF2/PAIR2 for loop

@@ -64,10 +64,15 @@ struct DevCell {
   uint8_t flags; /* bit0 active, bit1 local, bit2 split */
   float width;   /* max_k width[k] */
   float dx_max_part; /* how far a particle may sit outside the cell box */
-  int32_t pad_;
+  int32_t seg_base;  /* index of this cell's first (cell, sid) segment, see seg_index() */
 };
 static_assert(sizeof(DevCell) == 80, "DevCell layout");
 
+/* Index of the (cell, sid) segment: key extrema and sorted index arrays are
+ * stored per requested segment, a cell's segments are consecutive. */
+__device__ __forceinline__ int seg_index(const DevCell &c, int sid) {
+  return c.seg_base + __popc((unsigned)c.sort_mask & ((1u << sid) - 1u));
+}
 __device__ __forceinline__ int64_t sort_offset(const DevCell &c, int sid) {
   return c.sort_base + (int64_t)__popc((unsigned)c.sort_mask & ((1u << sid) - 1u)) * c.count;
 }
@@ -83,6 +88,7 @@ struct LoopArgs {
   const int32_t *tgt_first; /* per group: offset into tgt_list */
   const int32_t *tgt_count; /* per group */
   const uint32_t *sort_idx;
+  const float2 *ext; /* per (cell, sid) segment: (min, max) sort key = sort[0].d, sort[count-1].d */
   /* particle state */
   const double *x;       /* 3n */
   const float4 *mv;      /* (m, vx, vy, vz) */

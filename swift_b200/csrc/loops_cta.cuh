@@ -415,12 +415,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_c
               __dmul_rn(shz, c_runner_shift[sid][2]));
           const double oix = __dadd_rn(cj.loc[0], shx), oiy = __dadd_rn(cj.loc[1], shy),
                        oiz = __dadd_rn(cj.loc[2], shz);
-          const int j0 = cj.first + (int)A.sort_idx[sort_offset(cj, sid)];
-          const int i1 = ci.first + (int)A.sort_idx[sort_offset(ci, sid) + ci.count - 1];
-          const double dj_min = (double)sort_key(A.x[3 * (size_t)j0], A.x[3 * (size_t)j0 + 1],
-                                                 A.x[3 * (size_t)j0 + 2], sid);
-          const double di_max = (double)sort_key(A.x[3 * (size_t)i1], A.x[3 * (size_t)i1 + 1],
-                                                 A.x[3 * (size_t)i1 + 2], sid);
+          /* sort_j[0].d and sort_i[count-1].d of the reference = key extrema */
+          const double dj_min = (double)A.ext[seg_index(cj, sid)].x;
+          const double di_max = (double)A.ext[seg_index(ci, sid)].y;
           if (FORCE) {
             ii.hi_max_g = __dmul_rn((double)ci.h_max, (double)KERNEL_GAMMA);
             ii.hj_max_g = __dmul_rn((double)cj.h_max, (double)KERNEL_GAMMA);

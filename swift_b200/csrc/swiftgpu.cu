@@ -97,6 +97,10 @@ struct swiftgpu_handle {
   int64_t sort_total = 0;
   SortSeg *d_segs = nullptr;
   int nsegs = 0;
+  float2 *d_ext = nullptr;        /* key extrema per segment */
+  int32_t *d_ext_cells = nullptr; /* cells that own at least one segment */
+  int n_ext_cells = 0;
+  bool full_sorted = false;       /* sort_idx holds the full sorted arrays */
   unsigned long long *d_counters = nullptr; /* [0] density [1] gradient [2] force [3] redo */
   int32_t *d_flag = nullptr;
   uint8_t *d_force_bits = nullptr;
@@ -298,6 +302,48 @@ __global__ void __launch_bounds__(256)
   }
   if (in_smem)
     for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = sidx[i];
+}
+
+/* ======================================================================== */
+/* Kernel: key extrema. The loops only need sort[0].d and sort[count-1].d of  */
+/* every (cell, sid) array (dj_min / di_max, functions_hydro.h:1286,1418): the */
+/* candidate culling is done with boxes, not with the sorted order. One warp  */
+/* per cell computes the extrema of all its requested sids in one pass.       */
+/* ======================================================================== */
+__global__ void __launch_bounds__(128)
+    k_extrema(const int32_t *ext_cells, int ncells, const DevCell *cells, const double *x, float2 *ext) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= ncells) return;
+  const DevCell c = cells[ext_cells[w]];
+  const unsigned mask = c.sort_mask;
+  float mn[13], mx[13];
+#pragma unroll
+  for (int s = 0; s < 13; s++) {
+    mn[s] = 3.402823466e+38f;
+    mx[s] = -3.402823466e+38f;
+  }
+  for (int k = lane; k < c.count; k += 32) {
+    const size_t p = (size_t)c.first + k;
+    const double px = x[3 * p], py = x[3 * p + 1], pz = x[3 * p + 2];
+#pragma unroll
+    for (int s = 0; s < 13; s++) {
+      if ((mask >> s) & 1u) {
+        const float key = sort_key(px, py, pz, s);
+        mn[s] = fminf(mn[s], key);
+        mx[s] = fmaxf(mx[s], key);
+      }
+    }
+  }
+  int rank = 0;
+#pragma unroll
+  for (int s = 0; s < 13; s++) {
+    if ((mask >> s) & 1u) {
+      const float a = warp_min(mn[s]), b = warp_max(mx[s]);
+      if (lane == 0) ext[c.seg_base + rank] = make_float2(a, b);
+      rank++;
+    }
+  }
 }
 
 /* ======================================================================== */
@@ -838,7 +884,7 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   free_parts(h);
   h->L_density.release(); h->L_subset.release(); h->L_force.release();
   halo_release(h);
-  cudaFree(h->d_cells); cudaFree(h->d_cells_init); cudaFree(h->d_dmin); cudaFree(h->d_dxp); cudaFree(h->sort_idx); cudaFree(h->d_sort_keys); cudaFree(h->d_segs); cudaFree(h->d_counters);
+  cudaFree(h->d_cells); cudaFree(h->d_cells_init); cudaFree(h->d_dmin); cudaFree(h->d_dxp); cudaFree(h->sort_idx); cudaFree(h->d_sort_keys); cudaFree(h->d_segs); cudaFree(h->d_ext); cudaFree(h->d_ext_cells); cudaFree(h->d_counters);
   cudaFree(h->d_flag); cudaFree(h->d_force_bits);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -986,12 +1032,17 @@ static int build_lists(H *h, bool force_only) {
                         (s.nodeID == h->cfg.rank ? 2 : 0) | (s.split ? 4 : 0));
   }
   std::vector<SortSeg> segs;
+  std::vector<int32_t> ext_cells;
   segs.reserve(req.size());
   int64_t off = 0;
   int max_seg = 0;
   for (uint64_t r : req) {
     const int c = (int)(r >> 4), sid = (int)(r & 15);
-    if (dc[c].sort_base < 0) dc[c].sort_base = off;
+    if (dc[c].sort_base < 0) {
+      dc[c].sort_base = off;
+      dc[c].seg_base = (int32_t)segs.size();
+      ext_cells.push_back(c);
+    }
     dc[c].sort_mask |= (uint16_t)(1u << sid);
     SortSeg s;
     s.cell = c;
@@ -1038,6 +1089,12 @@ static int build_lists(H *h, bool force_only) {
   CK(to_device(&h->d_cells, dc));
   CK(to_device(&h->d_segs, segs));
   h->nsegs = (int)segs.size();
+  CK(to_device(&h->d_ext_cells, ext_cells));
+  h->n_ext_cells = (int)ext_cells.size();
+  cudaFree(h->d_ext);
+  h->d_ext = nullptr;
+  CK(cudaMalloc((void **)&h->d_ext, std::max<size_t>(segs.size(), 1) * sizeof(float2)));
+  h->full_sorted = false;
   if (off != h->sort_total || !h->sort_idx) {
     cudaFree(h->sort_idx);
     h->sort_idx = nullptr;
@@ -1140,11 +1197,21 @@ static int phase_end(H *h, double *ms_out) {
   return 0;
 }
 
-static int launch_sort(H *h) {
-  if (h->nsegs > 0) {
+static bool use_cta_loops();
+/* full = the 13-axis sorted index arrays of runner_do_hydro_sort; the CTA
+ * loops only consume the key extrema. */
+static int launch_sort(H *h, bool full) {
+  if (h->n_ext_cells > 0) {
+    k_extrema<<<(h->n_ext_cells * 32 + 127) / 128, 128, 0, h->stream>>>(h->d_ext_cells, h->n_ext_cells,
+                                                                        h->d_cells, h->x, h->d_ext);
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+  }
+  if (full && h->nsegs > 0) {
     k_sort<<<h->nsegs, 256, 0, h->stream>>>(h->d_segs, h->d_cells, h->x, h->sort_idx, h->d_sort_keys);
     h->stats.n_launches++;
     CK(cudaGetLastError());
+    h->full_sorted = true;
   }
   return 0;
 }
@@ -1152,7 +1219,8 @@ static int launch_sort(H *h) {
 extern "C" int swiftgpu_run_sort(swiftgpu_t *h) {
   if (!h) return 1;
   if (phase_begin(h)) return 1;
-  if (launch_sort(h)) return 1;
+  h->full_sorted = false;
+  if (launch_sort(h, !use_cta_loops())) return 1;
   h->sorted = true;
   h->phases_done |= SWIFTGPU_PHASE_SORT;
   return phase_end(h, &h->stats.ms_sort);
@@ -1171,6 +1239,7 @@ static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
   A.tgt_first = D.tgt_first;
   A.tgt_count = D.tgt_count;
   A.sort_idx = h->sort_idx;
+  A.ext = h->d_ext;
   A.x = h->x; A.mv = h->mv; A.h = h->hh; A.depth_h = h->depth_h; A.time_bin = h->time_bin;
   A.fq1 = h->fq1; A.fq2 = h->fq2; A.fq3 = h->fq3;
   A.dA = h->dA; A.dB = h->dB; A.g_vsig = h->g_vsig; A.g_lap = h->g_lap; A.g_amax = h->g_amax;
@@ -1436,7 +1505,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
       }
       if (rc) return 1;
       /* new (cell, sid) segments may exist: sort again */
-      if (launch_sort(h)) return 1;
+      if (launch_sort(h, !use_cta_loops())) return 1;
       h->sorted = true;
     }
   }
@@ -1548,6 +1617,30 @@ extern "C" int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density, int32
   if (n_density) CK(cudaMemcpy(n_density, h->nd, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
   if (n_gradient) CK(cudaMemcpy(n_gradient, h->ng, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
   if (n_force) CK(cudaMemcpy(n_force, h->nf, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int swiftgpu_download_sort(swiftgpu_t *h, int32_t cell, int32_t sid, int32_t *idx_out,
+                                      float *key_min, float *key_max) {
+  if (!h || cell < 0 || cell >= h->ncells || sid < 0 || sid > 12) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (!h->sorted) return h->fail("download_sort before run_sort");
+  std::vector<DevCell> one(1);
+  CK(cudaMemcpy(one.data(), h->d_cells + cell, sizeof(DevCell), cudaMemcpyDeviceToHost));
+  const DevCell &c = one[0];
+  if (!((c.sort_mask >> sid) & 1)) return h->fail("(cell, sid) has no sorted array: no item needs it");
+  if (!h->full_sorted) {
+    if (launch_sort(h, true)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  const int rank = __builtin_popcount((unsigned)c.sort_mask & ((1u << sid) - 1u));
+  if (idx_out)
+    CK(cudaMemcpy(idx_out, h->sort_idx + c.sort_base + (int64_t)rank * c.count, sizeof(int32_t) * c.count,
+                  cudaMemcpyDeviceToHost));
+  float2 e;
+  CK(cudaMemcpy(&e, h->d_ext + c.seg_base + rank, sizeof(e), cudaMemcpyDeviceToHost));
+  if (key_min) *key_min = e.x;
+  if (key_max) *key_max = e.y;
   return 0;
 }
 

@@ -123,6 +123,15 @@ class SwiftGPU:
                                                    self.nparts), "download_counts")
         return nd, ng, nf
 
+    def download_sort(self, cell, sid):
+        """(indices, key_min, key_max) of the sorted array of (cell, sid)."""
+        n = int(self._cells["count"][cell])
+        idx = np.zeros(n, np.int32)
+        kmin, kmax = C.c_float(), C.c_float()
+        self._ck(self.lib.swiftgpu_download_sort(self.h, cell, sid, idx.ctypes.data, C.addressof(kmin),
+                                                 C.addressof(kmax)), "download_sort")
+        return idx, kmin.value, kmax.value
+
     def stats(self):
         s = abi.Stats()
         self._ck(self.lib.swiftgpu_get_stats(self.h, C.byref(s)), "get_stats")

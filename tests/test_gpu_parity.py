@@ -190,3 +190,36 @@ def test_roundtrip_untouched_fields():
     assert np.array_equal(x0, x1)
     assert np.array_equal(host.field(c.parts, c.layout, "v"), host.field(got, c.layout, "v"))
     g.close()
+
+
+def test_sort_matches_reference():
+    """runner_do_hydro_sort (runner_sort.c:203): for every sid the sorted keys
+    of the on-demand GPU sort and the key extrema the loops consume are the
+    reference's c->hydro.sort entries bit for bit (the permutation may differ
+    among equal keys only)."""
+    from oracle import ref
+    if not ref.available("minimal"):
+        pytest.skip("oracle/_ref not present")
+    ic = host.jittered_box(12, abi.SCHEME_MINIMAL, jitter=0.3, seed=21)
+    c = util.make_case("minimal", ic, (3, 3, 3))
+    g = util.run_gpu(c, abi.PHASE_SORT)
+    o = ref.Reference("minimal", c.cfg, c.step, c.tree.cells, c.tree.top, c.parts)
+    o.run(abi.PHASE_SORT, threads=1)
+    shifts = np.array([[1, 1, 1], [1, 1, 0], [1, 1, -1], [1, 0, 1], [1, 0, 0], [1, 0, -1], [1, -1, 1], [1, -1, 0],
+                       [1, -1, -1], [0, 1, 1], [0, 1, 0], [0, 1, -1], [0, 0, 1]], dtype=np.float64)
+    shifts /= np.linalg.norm(shifts, axis=1)[:, None]
+    checked = 0
+    for cell in (int(c.tree.top[0]), int(c.tree.top[13]), int(c.tree.top[26])):
+        first, count = int(c.tree.cells["first_part"][cell]), int(c.tree.cells["count"][cell])
+        for sid in range(13):
+            d, i = o.sort(cell, sid)
+            idx, kmin, kmax = g.download_sort(cell, sid)
+            assert sorted(idx.tolist()) == list(range(count))
+            # keys in GPU order, recomputed by the reference's own sort entries
+            key_of = np.empty(count, np.float32)
+            key_of[i] = d
+            assert np.array_equal(key_of[idx], d), (cell, sid)
+            assert kmin == d[0] and kmax == d[-1]
+            checked += 1
+    assert checked == 39
+    g.close()
