@@ -5,7 +5,7 @@ import csv, io, subprocess, sys
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "--kernel-name", f"regex:{kern}"],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "--kernel-name", "regex:k_"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = None; files = []; cur = None; fname = ""
@@ -23,7 +23,8 @@ for r in rows:
     except ValueError:
         pass
 # group per kernel function occurrence: the report lists each (file, function) once per launch
-fns = sorted(set(f["fn"] for f in files))
+import re
+fns = sorted(set(f["fn"] for f in files if re.search(kern, f["fn"])))
 sel_fn = fns[0]
 launches = {}
 for f in files:
