@@ -82,6 +82,8 @@ def make_workload(name, world=1, rank=0):
     else:
         ic = host.jittered_box(L, sid, jitter=0.2, seed=42, bricks=bricks)
     tg = host.default_top_grid(L)
+    if os.environ.get("SWIFTGPU_TOPGRID"):  # experiments: other leaf sizes
+        tg = (int(os.environ["SWIFTGPU_TOPGRID"]),) * 3
     cdim = tuple(t * b for t, b in zip(tg, bricks))
     dim = tuple(float(b) for b in bricks)
     c = util.make_case(scheme, ic, cdim, rank_grid=bricks, rank=rank, dim=dim, pack=(world == 1))

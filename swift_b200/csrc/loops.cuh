@@ -99,6 +99,15 @@ struct LoopArgs {
   const float4 *fq1; /* (rho, P, f, cs) */
   const float4 *fq2; /* (balsara, h, u, time_bin) */
   const float4 *fq3; /* (alpha_visc, alpha_diff, -, -) */
+  /* tile pipeline (loops_tile.cuh): TMA-copyable source records */
+  const float4 *xf;   /* (float x, y, z of the absolute position, (h gamma REL + margin)^2) */
+  const double *xs0, *xs1, *xs2; /* SoA copies of the double positions (8-byte TMA columns) */
+  const float4 *gq;   /* gradient payload (u, rho, cs, alpha_visc) */
+  const float4 *boxes; /* per cell octet: lo.xyz_, hi.xyz_ */
+  const int32_t *cell_box_first;
+  float keyE;   /* r-margin below which the sorted-axis conditions are implied */
+  float margin; /* absolute widening of the float prefilter */
+  int hold;     /* stages a consumer warp holds before it drains (<= NS - 1) */
   /* outputs */
   float4 *dA;      /* (rho, rho_dh, wcount, wcount_dh) */
   float4 *dB;      /* (div_v, rot_v) */

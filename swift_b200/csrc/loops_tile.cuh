@@ -1,0 +1,873 @@
+/*
+ * loops_tile.cuh - the neighbour loops as a TMA-fed producer/consumer pipeline.
+ *
+ * One CTA = 8 consumer warps (64 TARGET particles of one target cell, 8 per
+ * warp) + 1 producer warp. No __syncthreads() after the prologue.
+ *
+ *   PRODUCER  walks the items of the target cell's group, culls source cells
+ *             that are out of reach of the CTA's target box and cuts the rest
+ *             into fragments. A ring STAGE holds up to 256 source slots / 8
+ *             fragments. The source data are copied as they lie in HBM by
+ *             bulk TMA (cp.async.bulk -> mbarrier complete_tx): the
+ *             prefilter record xf = (float x, y, z, reach^2), the payload
+ *             columns (mv, fq1, fq2, fq3) and the precomputed OCTET boxes of
+ *             the source cell. No per-source arithmetic is done at staging.
+ *   CONSUMER  per stage: lane = octet box-box cull against the warp's target
+ *             box (one ballot), then per accepted octet every lane
+ *             (t = lane & 7 target, s = lane >> 3) tests its target against
+ *             sources 2s, 2s+1 with a conservative float prefilter on
+ *             absolute-position floats and appends candidates to its
+ *             sub-list. Stages are held (not released) until the lists are
+ *             drained; a drain merges the 4 sub-lists of a target over its 4
+ *             lanes, re-evaluates every candidate with the reference's EXACT
+ *             arithmetic from the double positions (frames, un-fused r2) and
+ *             applies the interaction; then the held stages are released.
+ *
+ * Exactness. The reference decides a pair by r2 < h^2 gamma^2 in the float
+ * frame of the leaf-level item (functions_hydro.h:1327-1347) AND by the
+ * sorted-axis conditions of DOPAIR1/DOPAIR2 (:1296-1332, :1420-1448,
+ * :1652-1735, :1806-2238). The sorted-axis conditions are geometrically
+ * implied by the distance condition up to the rounding of the float sort keys
+ * (|error| < 5e-7 * max(dim)); the drain therefore evaluates them only for
+ * candidates whose r lies within keyE = 2e-6 * max(dim) of the cut-off (or
+ * whose h exceeds the cell's h_max cap) - exact_type1()/exact_type2(), a
+ * rare divergent path that re-derives the item constants from global memory
+ * exactly as the reference does. Everything else takes the fast path, whose
+ * accept set is provably the reference's.
+ */
+#ifndef SWIFTGPU_LOOPS_TILE_CUH
+#define SWIFTGPU_LOOPS_TILE_CUH
+
+#include "loops.cuh"
+
+namespace swiftgpu {
+
+#define TL_CWARPS 8                       /* consumer warps */
+#define TL_THREADS (32 * (TL_CWARPS + 1)) /* + producer warp */
+#define TL_TARGETS 64
+#define TL_SLOTS 256 /* source slots per stage */
+#define TL_OCT (TL_SLOTS / 8)
+#define TL_FRAGS 8   /* fragments per stage */
+#define TL_SUBCAP 14 /* sub-list capacity per lane */
+#define TL_DCOL (TL_SLOTS + 2 * TL_FRAGS) /* double column: 2 spare entries per fragment (alignment) */
+
+/* ---- mbarrier / bulk-TMA PTX ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint64_t *b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+/* Bounded wait: a protocol error traps instead of hanging the GPU. */
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+  if (mbar_try(b, parity)) return;
+  unsigned ns = 32;
+  for (unsigned spins = 0; !mbar_try(b, parity); spins++) {
+    __nanosleep(ns);
+    if (ns < 256) ns <<= 1;
+    if (spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(b))
+      : "memory");
+}
+
+/* Constants of one fragment's item, written by the producer for the consumers. */
+struct __align__(8) TileItem {
+  double ot[3]; /* drain: subtracted from the target double */
+  double fs[3]; /* drain: frame origin of the source (0 for the double modes) */
+  float d[3];   /* prefilter: target absolute float - d is compared with the source absolute float */
+  float rsrc;   /* force: h_max * gamma of the source cell (also the source-side cap) */
+  float hcap;   /* target-side cap of h * gamma under which the key conditions are implied */
+  int32_t gi_base; /* global particle index = gi_base + slot-in-stage */
+  int32_t item;    /* global item index (slow path) */
+  int8_t mode, sid, min_depth, max_depth;
+  int8_t dbl, nokey, dofs, pad1_; /* dofs: slot -> index into the staged double columns */
+};
+static_assert(sizeof(TileItem) == 88, "TileItem");
+
+template <int NP, int NS>
+struct TileSmem {
+  static constexpr int kStageF = 0;
+  static constexpr int kStageP = kStageF + TL_SLOTS * 16;
+  static constexpr int kStageD = kStageP + NP * TL_SLOTS * 16; /* 3 double columns of TL_DCOL entries */
+  static constexpr int kStageOB = kStageD + 3 * TL_DCOL * 8;
+  static constexpr int kStageIT = kStageOB + TL_OCT * 32;
+  static constexpr int kStageO2F = kStageIT + TL_FRAGS * (int)sizeof(TileItem);
+  static constexpr int kStageMeta = kStageO2F + TL_OCT;
+  static constexpr int kStageBytes = ((kStageMeta + 16) + 127) & ~127;
+  static constexpr int kList = NS * kStageBytes;
+  static constexpr int kBar = kList + TL_SUBCAP * 32 * TL_CWARPS * 2;
+  static constexpr int kBox = kBar + 2 * NS * 8;
+  static constexpr int kWin = kBox + (TL_CWARPS + 1) * 32; /* producer: constants of 32 items */
+  static constexpr int kWinAux = kWin + 32 * (int)sizeof(TileItem);
+  static constexpr int kBytes = kWinAux + 32 * 8;
+};
+
+/* ---- exact sorted-axis conditions (rare path) ---- */
+
+/* Type-1 loops, functions_hydro.h:1296-1332 / :1420-1448 (DOPAIR1) and
+ * :891-1000 (DOPAIR_SUBSET): does the reference reach source s from target t
+ * along the sorted axis? Same arithmetic as the reference, constants
+ * re-derived from the cells. */
+struct SlowArgs {
+  const Item *items;
+  const DevCell *cells;
+  const float2 *ext;
+  double dim[3];
+};
+__device__ __noinline__ bool exact_type1(const SlowArgs A, int item, double tx, double ty, double tz,
+                                         float thg, double sx, double sy, double sz) {
+  const Item I = A.items[item];
+  const DevCell tc = A.cells[I.tcell];
+  const DevCell sc = A.cells[I.scell];
+  const int mode = I.mode, sid = I.sid;
+  const double shx = I.shift[0] * A.dim[0], shy = I.shift[1] * A.dim[1], shz = I.shift[2] * A.dim[2];
+  const float skey = sort_key(sx, sy, sz, sid);
+  if (mode == MODE_PAIR_L || mode == MODE_PAIR_R) {
+    const DevCell &ci = (mode == MODE_PAIR_L) ? tc : sc;
+    const DevCell &cj = (mode == MODE_PAIR_L) ? sc : tc;
+    const double rshift = __dadd_rn(
+        __dadd_rn(__dmul_rn(shx, c_runner_shift[sid][0]), __dmul_rn(shy, c_runner_shift[sid][1])),
+        __dmul_rn(shz, c_runner_shift[sid][2]));
+    const double dj_min = (double)A.ext[seg_index(cj, sid)].x;
+    const double di_max = (double)A.ext[seg_index(ci, sid)].y;
+    const float h_max_lim = (I.flags & 1) ? ci.h_max_allowed : 3.402823466e+38f;
+    const float dx_max = __fadd_rn(ci.dx_max_sort, cj.dx_max_sort);
+    const float tkey = sort_key(tx, ty, tz, sid);
+    if (mode == MODE_PAIR_L) {
+      const double lim_a =
+          __dsub_rn((double)__fmul_rn(fminf(h_max_lim, ci.h_max_active), KERNEL_GAMMA), rshift);
+      const bool in_loop = __dadd_rn(__dadd_rn((double)tkey, lim_a), (double)dx_max) > dj_min;
+      const double di = __dsub_rn((double)__fadd_rn(__fadd_rn(tkey, thg), dx_max), rshift);
+      return in_loop && !(di < dj_min) && ((double)skey < di);
+    } else {
+      const double lim_a = (double)__fmul_rn(fminf(h_max_lim, cj.h_max_active), KERNEL_GAMMA);
+      const double lim_b = __dsub_rn(di_max, rshift);
+      const bool in_loop = __dsub_rn(__dsub_rn((double)tkey, lim_a), (double)dx_max) < lim_b;
+      const double dj = __dadd_rn((double)__fsub_rn(__fsub_rn(tkey, thg), dx_max), rshift);
+      return in_loop && !(__dsub_rn(dj, rshift) > lim_b) && ((double)skey > dj);
+    }
+  }
+  if (mode == MODE_SUB_PAIR || mode == MODE_SUB_PAIR_F) {
+    const double tdx = __dsub_rn(tx, shx), tdy = __dsub_rn(ty, shy), tdz = __dsub_rn(tz, shz);
+    const float dx_max = sc.dx_max_sort;
+    const float f0 = (mode == MODE_SUB_PAIR) ? __fadd_rn(thg, dx_max) : __fsub_rn(-thg, dx_max);
+    const double di = __dadd_rn(__dadd_rn(__dadd_rn((double)f0, __dmul_rn(tdx, c_runner_shift[sid][0])),
+                                          __dmul_rn(tdy, c_runner_shift[sid][1])),
+                                __dmul_rn(tdz, c_runner_shift[sid][2]));
+    return (mode == MODE_SUB_PAIR) ? ((double)skey < di) : ((double)skey > di);
+  }
+  return true;
+}
+
+/* Type-2 loop, DOPAIR2 functions_hydro.h:1652-1735 (ranges) and :1806-2238
+ * (the two passes): is the pair taken, given the exact r2? */
+__device__ __noinline__ bool exact_type2(const SlowArgs A, int item, double tx, double ty, double tz,
+                                         float thg, float thg2, double sx, double sy, double sz,
+                                         float shg, float shg2, float r2) {
+  const Item I = A.items[item];
+  const DevCell tc = A.cells[I.tcell];
+  const DevCell sc = A.cells[I.scell];
+  const int mode = I.mode, sid = I.sid;
+  const bool tleft = (mode == MODE_PAIR_L);
+  const DevCell &ci = tleft ? tc : sc;
+  const DevCell &cj = tleft ? sc : tc;
+  const double shx = I.shift[0] * A.dim[0], shy = I.shift[1] * A.dim[1], shz = I.shift[2] * A.dim[2];
+  const double rshift =
+      __dadd_rn(__dadd_rn(__dmul_rn(shx, c_runner_shift[sid][0]), __dmul_rn(shy, c_runner_shift[sid][1])),
+                __dmul_rn(shz, c_runner_shift[sid][2]));
+  const double dj_min = (double)A.ext[seg_index(cj, sid)].x;
+  const double di_max = (double)A.ext[seg_index(ci, sid)].y;
+  const double hi_max_g = __dmul_rn((double)ci.h_max, (double)KERNEL_GAMMA);
+  const double hj_max_g = __dmul_rn((double)cj.h_max, (double)KERNEL_GAMMA);
+  const double dx_max = (double)__fadd_rn(ci.dx_max_sort, cj.dx_max_sort);
+  const double di_max_sh = __dsub_rn(di_max, rshift);
+  const float tkey = sort_key(tx, ty, tz, sid);
+  const float skey = sort_key(sx, sy, sz, sid);
+  if (tleft) {
+    const bool inA = __dsub_rn(__dadd_rn(__dadd_rn((double)tkey, hi_max_g), dx_max), rshift) > dj_min;
+    const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(tkey, thg), dx_max), rshift);
+    const double t_di = (inA && !(di < dj_min)) ? di : -1.0e300;
+    const double t_keysh = __dsub_rn((double)tkey, rshift);
+    const bool inB = __dsub_rn(__dsub_rn((double)skey, hj_max_g), dx_max) < di_max_sh;
+    const double dj = __dsub_rn((double)__fsub_rn(skey, shg), dx_max);
+    const double s_dj = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
+    const bool c1 = ((double)skey < t_di) && (r2 < thg2);
+    const bool c2 = (t_keysh > s_dj) && (r2 < shg2) && !(r2 < thg2);
+    return c1 || c2;
+  } else {
+    const bool inB = __dsub_rn(__dsub_rn((double)tkey, hj_max_g), dx_max) < di_max_sh;
+    const double dj = __dsub_rn((double)__fsub_rn(tkey, thg), dx_max);
+    const double t_dj = (inB && !(dj > di_max_sh)) ? dj : 1.0e300;
+    const bool inA = __dsub_rn(__dadd_rn(__dadd_rn((double)skey, hi_max_g), dx_max), rshift) > dj_min;
+    const double di = __dsub_rn(__dadd_rn((double)__fadd_rn(skey, shg), dx_max), rshift);
+    const double s_di = (inA && !(di < dj_min)) ? di : -1.0e300;
+    const double s_keysh = __dsub_rn((double)skey, rshift);
+    const bool c1 = ((double)tkey < s_di) && (r2 < shg2);
+    const bool c2 = (s_keysh > t_dj) && (r2 < thg2) && !(r2 < shg2);
+    return c1 || c2;
+  }
+}
+
+/* (max(a - E, 0))^2 shaved by 2^-19: below it, r < a - E certainly. */
+__device__ __forceinline__ float sure_r2(float a, float E) {
+  const float b = a - E;
+  return b > 0.f ? b * b * 0.999998f : 0.f;
+}
+
+template <int LOOP, int SCHEME, int NS>
+__global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_tile(const LoopArgs A) {
+  constexpr bool FORCE = (LOOP == LOOP_FORCE);
+  constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
+  typedef TileSmem<NP, NS> SM;
+  extern __shared__ __align__(128) char smem_tl[];
+  char *const smem = smem_tl;
+  uint16_t *const sList = (uint16_t *)(smem + SM::kList);
+  uint64_t *const sFull = (uint64_t *)(smem + SM::kBar);
+  uint64_t *const sEmpty = sFull + NS;
+  float *const sBox = (float *)(smem + SM::kBox);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int t8 = lane & 7;
+  const int s4 = lane >> 3;
+  const int task = blockIdx.x;
+
+  const int g = A.task_group[task];
+  const int chunk = A.task_chunk[task];
+  const int nt = A.tgt_count[g];
+  if (chunk * TL_TARGETS >= nt) return;
+  const Group G = A.groups[g];
+  const int nt_here = min(TL_TARGETS, nt - chunk * TL_TARGETS);
+  const int nwarps_used = (nt_here + 7) >> 3; /* consumer warps that own targets */
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; s++) {
+      mbar_init(sFull + s, 1);
+      mbar_init(sEmpty + s, nwarps_used);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+
+  /* ---- my target (4 lanes share one); the producer warp has none ---- */
+  const bool consumer = warp < TL_CWARPS;
+  const int slot_t = chunk * TL_TARGETS + warp * 8 + t8;
+  const bool tvalid = consumer && slot_t < nt;
+  const int ti = tvalid ? A.tgt_list[A.tgt_first[g] + slot_t] : -1;
+  double tx = 0., ty = 0., tz = 0.;
+  float th = 1.f, tvx = 0.f, tvy = 0.f, tvz = 0.f, tu = 0.f, tcs = 0.f;
+  ForceQ tq;
+  tq.m = tq.vx = tq.vy = tq.vz = 0.f;
+  tq.rho = 1.f;
+  tq.P = tq.f = tq.cs = tq.balsara = 0.f;
+  tq.h = 1.f;
+  tq.u = tq.alpha_visc = tq.alpha_diff = 0.f;
+  tq.time_bin = 0;
+  int tdepth = 0;
+  if (tvalid) {
+    tx = A.x[3 * (size_t)ti];
+    ty = A.x[3 * (size_t)ti + 1];
+    tz = A.x[3 * (size_t)ti + 2];
+    const float4 q = A.mv[ti];
+    tvx = q.y;
+    tvy = q.z;
+    tvz = q.w;
+    tdepth = A.depth_h[ti];
+    if (FORCE) {
+      const float4 q1 = A.fq1[ti], q2 = A.fq2[ti];
+      tq.m = q.x; tq.vx = q.y; tq.vy = q.z; tq.vz = q.w;
+      tq.rho = q1.x; tq.P = q1.y; tq.f = q1.z; tq.cs = q1.w;
+      tq.balsara = q2.x; tq.h = q2.y; tq.u = q2.z; tq.time_bin = __float_as_int(q2.w);
+      if (SCHEME == SCH_SPHENIX) {
+        const float4 q3 = A.fq3[ti];
+        tq.alpha_visc = q3.x;
+        tq.alpha_diff = q3.y;
+      }
+      th = tq.h;
+    } else {
+      th = A.h[ti];
+      if (LOOP == LOOP_GRADIENT) {
+        tu = A.fq2[ti].z;
+        tcs = A.fq1[ti].w;
+      }
+    }
+  }
+  const float thg2 = hg2_exact(th);
+  const float th_inv = 1.f / th;
+  const float thg = __fmul_rn(th, KERNEL_GAMMA);
+  const float tsure2 = sure_r2(thg, A.keyE);
+  const float tfx = __double2float_rn(tx), tfy = __double2float_rn(ty), tfz = __double2float_rn(tz);
+
+  /* the warp's target box (absolute floats) and its reach */
+  float blo[3], bhi[3], rmax;
+  {
+    blo[0] = tvalid ? tfx : 3.0e30f;
+    blo[1] = tvalid ? tfy : 3.0e30f;
+    blo[2] = tvalid ? tfz : 3.0e30f;
+    bhi[0] = tvalid ? tfx : -3.0e30f;
+    bhi[1] = tvalid ? tfy : -3.0e30f;
+    bhi[2] = tvalid ? tfz : -3.0e30f;
+    rmax = tvalid ? thg : 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      blo[k] = warp_min(blo[k]);
+      bhi[k] = warp_max(bhi[k]);
+    }
+    rmax = warp_max(rmax);
+    if (lane == 0) {
+      float *b = sBox + warp * 8;
+      b[0] = blo[0]; b[1] = blo[1]; b[2] = blo[2];
+      b[3] = bhi[0]; b[4] = bhi[1]; b[5] = bhi[2];
+      b[6] = rmax;
+    }
+  }
+  __syncthreads(); /* barriers initialised, boxes visible: the only CTA-wide barrier */
+
+  /* ===================================================================== */
+  /* PRODUCER                                                               */
+  /* ===================================================================== */
+  if (!consumer) {
+    float clo[3], chi[3], crmax = 0.f;
+    clo[0] = clo[1] = clo[2] = 3.0e30f;
+    chi[0] = chi[1] = chi[2] = -3.0e30f;
+#pragma unroll
+    for (int w = 0; w < TL_CWARPS; w++) {
+      const float *b = sBox + w * 8;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        clo[k] = fminf(clo[k], b[k]);
+        chi[k] = fmaxf(chi[k], b[3 + k]);
+      }
+      crmax = fmaxf(crmax, b[6]);
+    }
+    const DevCell tcell = A.cells[G.tcell];
+    TileItem *const sWin = (TileItem *)(smem + SM::kWin);
+    int2 *const sWinAux = (int2 *)(smem + SM::kWinAux); /* (first particle, first octet box) of the source cell */
+    int win_base = -32; /* first item of the window held in sWin */
+    unsigned km = 0u;   /* kept items of the window */
+    int wcount = 0;     /* my window item's source count */
+    int j = 32;         /* next position in the window */
+    int off = 0;        /* source offset inside the current item */
+    bool exhausted = false;
+    for (int it = 0;; it++) {
+      const int s = it % NS;
+      const uint32_t ph = (uint32_t)((it / NS) & 1);
+      /* ---- assemble the fragments of this stage (warp-uniform) ---- */
+      int used = 0, nfr = 0;
+      int my_w = 0, my_off = 0, my_n = 0, my_pool = 0;
+      while (!exhausted && nfr < TL_FRAGS && used < TL_SLOTS) {
+        const unsigned mm = j >= 32 ? 0u : (km >> j) << j;
+        if (!mm) {
+          if (nfr > 0) break; /* the window table is still referenced by this stage's fragments */
+          win_base += 32;
+          if (win_base >= G.item_count) {
+            exhausted = true;
+            break;
+          }
+          /* ---- load the constants of the next 32 items (lane = item) ---- */
+          bool keep = false;
+          wcount = 0;
+          if (win_base + lane < G.item_count) {
+            const int item = G.item_first + win_base + lane;
+            const Item I = A.items[item];
+            const DevCell sc = A.cells[I.scell];
+            wcount = sc.count;
+            const int mode = I.mode;
+            const double shx = I.shift[0] * A.dim[0], shy = I.shift[1] * A.dim[1],
+                         shz = I.shift[2] * A.dim[2];
+            TileItem ti_;
+            ti_.mode = (int8_t)mode;
+            ti_.sid = (int8_t)I.sid;
+            ti_.min_depth = I.min_depth;
+            ti_.max_depth = I.max_depth;
+            ti_.dbl = 0;
+            ti_.nokey = 0;
+            ti_.dofs = ti_.pad1_ = 0;
+            ti_.item = item;
+            ti_.gi_base = 0;
+            ti_.rsrc = FORCE ? __fmul_rn(sc.h_max, KERNEL_GAMMA) : 0.f;
+            ti_.hcap = 3.402823466e+38f;
+            double otx = 0., oty = 0., otz = 0., fsx = 0., fsy = 0., fsz = 0.;
+            if (mode == MODE_PAIR_L || mode == MODE_PAIR_R) {
+              const DevCell &ci = (mode == MODE_PAIR_L) ? tcell : sc;
+              const DevCell &cj = (mode == MODE_PAIR_L) ? sc : tcell;
+              const double oix = __dadd_rn(cj.loc[0], shx), oiy = __dadd_rn(cj.loc[1], shy),
+                           oiz = __dadd_rn(cj.loc[2], shz);
+              if (mode == MODE_PAIR_L) {
+                otx = oix; oty = oiy; otz = oiz;
+                fsx = cj.loc[0]; fsy = cj.loc[1]; fsz = cj.loc[2];
+              } else {
+                otx = cj.loc[0]; oty = cj.loc[1]; otz = cj.loc[2];
+                fsx = oix; fsy = oiy; fsz = oiz;
+              }
+              if (FORCE) {
+                ti_.hcap = __fmul_rn(tcell.h_max, KERNEL_GAMMA);
+              } else {
+                const float h_max_lim = (I.flags & 1) ? ci.h_max_allowed : 3.402823466e+38f;
+                ti_.hcap = __fmul_rn(fminf(h_max_lim, tcell.h_max_active), KERNEL_GAMMA);
+              }
+              ti_.d[0] = (float)__dsub_rn(otx, fsx);
+              ti_.d[1] = (float)__dsub_rn(oty, fsy);
+              ti_.d[2] = (float)__dsub_rn(otz, fsz);
+            } else if (mode == MODE_SUB_SELF) {
+              otx = fsx = sc.loc[0];
+              oty = fsy = sc.loc[1];
+              otz = fsz = sc.loc[2];
+              ti_.d[0] = ti_.d[1] = ti_.d[2] = 0.f;
+              ti_.nokey = 1;
+            } else {
+              ti_.dbl = 1;
+              if (mode != MODE_SELF) {
+                otx = shx; oty = shy; otz = shz;
+              } else {
+                ti_.nokey = 1;
+              }
+              ti_.d[0] = (float)otx;
+              ti_.d[1] = (float)oty;
+              ti_.d[2] = (float)otz;
+            }
+            ti_.ot[0] = otx; ti_.ot[1] = oty; ti_.ot[2] = otz;
+            ti_.fs[0] = fsx; ti_.fs[1] = fsy; ti_.fs[2] = fsz;
+            sWin[lane] = ti_;
+            sWinAux[lane] = make_int2(sc.first, A.cell_box_first[I.scell]);
+            /* item-level cull: source cell box against the CTA's target box */
+            const float r = fmaf(fmaxf(crmax, ti_.rsrc), PREFILTER_REL, A.margin) + sc.dx_max_part;
+            const float c0[3] = {(float)sc.loc[0], (float)sc.loc[1], (float)sc.loc[2]};
+            float q2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const float a = c0[k] - (chi[k] - ti_.d[k]), b = (clo[k] - ti_.d[k]) - (c0[k] + sc.width);
+              const float gk = fmaxf(0.f, fmaxf(a, b));
+              q2 = fmaf(gk, gk, q2);
+            }
+            keep = (q2 < r * r) && wcount > 0;
+          }
+          __syncwarp();
+          km = __ballot_sync(FULL_MASK, keep);
+          j = 0;
+          continue;
+        }
+        const int jj = __ffs(mm) - 1;
+        const int cnt = __shfl_sync(FULL_MASK, wcount, jj);
+        const int left = cnt - off, room = TL_SLOTS - used;
+        const int take = left <= room ? left : (room & ~7);
+        if (take == 0) break;
+        if (lane == nfr) {
+          my_w = jj;
+          my_off = off;
+          my_n = take;
+          my_pool = used;
+        }
+        used += (take + 7) & ~7;
+        nfr++;
+        if (take == left) {
+          j = jj + 1;
+          off = 0;
+        } else {
+          off += take;
+          break;
+        }
+      }
+      char *const st = smem + s * SM::kStageBytes;
+      int32_t *const meta = (int32_t *)(st + SM::kStageMeta);
+      mbar_wait(sEmpty + s, ph ^ 1u);
+      if (nfr == 0) { /* terminator */
+        if (lane == 0) {
+          meta[0] = 0;
+          meta[1] = 0;
+          mbar_arrive(sFull + s);
+        }
+        break;
+      }
+      uint32_t bytes = 0;
+      if (lane < nfr) {
+        TileItem ti_ = sWin[my_w];
+        const int2 aux = sWinAux[my_w];
+        const int first = aux.x + my_off;
+        const int dpar = first & 1; /* the double columns are copied from an even index */
+        ti_.gi_base = first - my_pool;
+        ti_.dofs = (int8_t)(2 * lane + dpar);
+        ((TileItem *)(st + SM::kStageIT))[lane] = ti_;
+        /* octet -> fragment map, sentinel records of the padding slots */
+        const int o0 = my_pool >> 3, o1 = (my_pool + my_n + 7) >> 3;
+        uint8_t *o2f = (uint8_t *)(st + SM::kStageO2F);
+        for (int o = o0; o < o1; o++) o2f[o] = (uint8_t)lane;
+        float4 *F = (float4 *)(st + SM::kStageF);
+        for (int k = my_pool + my_n; k < o1 * 8; k++)
+          F[k] = make_float4(-3.0e30f, -3.0e30f, -3.0e30f, 0.f);
+        /* bulk copies */
+        const uint32_t n16 = (uint32_t)my_n * 16u;
+        tma_load(F + my_pool, A.xf + first, n16, sFull + s);
+        float4 *P = (float4 *)(st + SM::kStageP);
+        tma_load(P + my_pool, A.mv + first, n16, sFull + s);
+        bytes = 2u * n16;
+        if (LOOP == LOOP_GRADIENT) {
+          tma_load(P + TL_SLOTS + my_pool, A.gq + first, n16, sFull + s);
+          bytes += n16;
+        }
+        if (FORCE) {
+          tma_load(P + TL_SLOTS + my_pool, A.fq1 + first, n16, sFull + s);
+          tma_load(P + 2 * TL_SLOTS + my_pool, A.fq2 + first, n16, sFull + s);
+          bytes += 2u * n16;
+          if (SCHEME == SCH_SPHENIX) {
+            tma_load(P + 3 * TL_SLOTS + my_pool, A.fq3 + first, n16, sFull + s);
+            bytes += n16;
+          }
+        }
+        const uint32_t n8 = (uint32_t)((my_n + dpar + 1) & ~1) * 8u;
+        double *D = (double *)(st + SM::kStageD) + my_pool + 2 * lane;
+        tma_load(D, A.xs0 + (first - dpar), n8, sFull + s);
+        tma_load(D + TL_DCOL, A.xs1 + (first - dpar), n8, sFull + s);
+        tma_load(D + 2 * TL_DCOL, A.xs2 + (first - dpar), n8, sFull + s);
+        bytes += 3u * n8;
+        const uint32_t nb32 = (uint32_t)(o1 - o0) * 32u;
+        tma_load(st + SM::kStageOB + o0 * 32, A.boxes + 2 * ((size_t)aux.y + (size_t)(my_off >> 3)), nb32,
+                 sFull + s);
+        bytes += nb32;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(FULL_MASK, bytes, o);
+      __syncwarp();
+      if (lane == 0) {
+        meta[0] = nfr;
+        meta[1] = used >> 3;
+        mbar_arrive_tx(sFull + s, bytes);
+      }
+    }
+    return;
+  }
+
+  /* ===================================================================== */
+  /* CONSUMERS                                                              */
+  /* ===================================================================== */
+  if (warp >= nwarps_used) return; /* no targets: not counted in the empty barriers */
+  SlowArgs SA;
+  SA.items = A.items;
+  SA.cells = A.cells;
+  SA.ext = A.ext;
+  SA.dim[0] = A.dim[0];
+  SA.dim[1] = A.dim[1];
+  SA.dim[2] = A.dim[2];
+
+  DensityAcc dacc;
+  dacc.zero();
+  GradientAcc gacc;
+  gacc.v_sig = 0.f;
+  gacc.laplace_u = 0.f;
+  gacc.alpha_max = 0.f;
+  ForceAcc facc;
+  facc.ax = facc.ay = facc.az = facc.u_dt = facc.h_dt = 0.f;
+  facc.v_sig = 0.f;
+  facc.min_ngb = NUM_TIME_BINS + 1;
+  int nhit = 0;
+  int ntests = 0;
+  int nsub = 0; /* entries in my sub-list */
+  uint16_t *const wlist = sList + warp * (TL_SUBCAP * 32);
+  uint16_t *const mylist = wlist + lane;
+
+  /* ---- INTERACT: merge the 4 sub-lists of each target and drain ---- */
+  auto drain = [&]() {
+    __syncwarp();
+    const int n0 = __shfl_sync(FULL_MASK, nsub, t8);
+    const int n1 = __shfl_sync(FULL_MASK, nsub, t8 + 8);
+    const int n2 = __shfl_sync(FULL_MASK, nsub, t8 + 16);
+    const int n3 = __shfl_sync(FULL_MASK, nsub, t8 + 24);
+    const int c1 = n0 + n1, c2 = c1 + n2, total = c2 + n3;
+    const int steps = (__reduce_max_sync(FULL_MASK, total) + 3) >> 2;
+    for (int jstep = 0; jstep < steps; jstep++) {
+      const int m = 4 * jstep + s4;
+      const bool act = m < total;
+      const int q = (m >= n0) + (m >= c1) + (m >= c2);
+      const int base = q == 0 ? 0 : (q == 1 ? n0 : (q == 2 ? c1 : c2));
+      const int kk = act ? m - base : 0;
+      const int entry = act ? (int)wlist[kk * 32 + t8 + 8 * q] : 0;
+      const int slot = entry & 2047;
+      const char *const st = smem + (slot >> 8) * SM::kStageBytes;
+      const int sl = slot & (TL_SLOTS - 1);
+      const TileItem &ii = ((const TileItem *)(st + SM::kStageIT))[entry >> 11];
+      const int gi = ii.gi_base + sl;
+      const double *const D = (const double *)(st + SM::kStageD) + sl + ii.dofs;
+      const double Xx = D[0], Xy = D[TL_DCOL], Xz = D[2 * TL_DCOL];
+      float dx, dy, dz;
+      {
+        const double ax = __dsub_rn(tx, ii.ot[0]), ay = __dsub_rn(ty, ii.ot[1]), az = __dsub_rn(tz, ii.ot[2]);
+        if (ii.dbl) {
+          dx = dsubf(ax, Xx);
+          dy = dsubf(ay, Xy);
+          dz = dsubf(az, Xz);
+        } else {
+          dx = __fsub_rn(__double2float_rn(ax), dsubf(Xx, ii.fs[0]));
+          dy = __fsub_rn(__double2float_rn(ay), dsubf(Xy, ii.fs[1]));
+          dz = __fsub_rn(__double2float_rn(az), dsubf(Xz, ii.fs[2]));
+        }
+      }
+      const float r2 = r2_exact(dx, dy, dz);
+      const bool part = act && tdepth >= ii.min_depth && tdepth <= ii.max_depth && gi != ti;
+      const float4 *const P = (const float4 *)(st + SM::kStageP);
+      if (!FORCE) {
+        bool hit = part && (r2 < thg2);
+        if (hit && !ii.nokey && !(r2 < tsure2 && thg <= ii.hcap))
+          hit = exact_type1(SA, ii.item, tx, ty, tz, thg, Xx, Xy, Xz);
+        if (hit) {
+          const float4 f0 = P[sl];
+          if (LOOP == LOOP_DENSITY) {
+            iact_density(dacc, r2, dx, dy, dz, th_inv, tvx, tvy, tvz, f0.x, f0.y, f0.z, f0.w);
+          } else {
+            const float4 f1 = P[TL_SLOTS + sl];
+            iact_gradient(gacc, r2, dx, dy, dz, th, tvx, tvy, tvz, tu, tcs, f0.x, f0.y, f0.z, f0.w,
+                          f1.x, f1.y, f1.z, f1.w, A.a2_Hubble);
+          }
+          nhit++;
+        }
+      } else {
+        const float4 q2 = P[2 * TL_SLOTS + sl];
+        const float sh = act ? q2.y : 1.f;
+        const float shg2 = hg2_exact(sh);
+        const bool a1 = r2 < thg2, a2 = r2 < shg2;
+        bool ok = part && (a1 || a2);
+        if (ok && !ii.nokey) {
+          /* DOSELF2 (nokey) takes r2 < hig2 || r2 < hjg2 as is (:2792) */
+          const float shg = __fmul_rn(sh, KERNEL_GAMMA);
+          const bool sure = (!a1 || (r2 < tsure2 && thg <= ii.hcap)) &&
+                            (!a2 || (r2 < sure_r2(shg, A.keyE) && shg <= ii.rsrc));
+          if (!sure) ok = exact_type2(SA, ii.item, tx, ty, tz, thg, thg2, Xx, Xy, Xz, shg, shg2, r2);
+        }
+        if (ok) {
+          ForceQ sq;
+          const float4 q0 = P[sl], q1 = P[TL_SLOTS + sl];
+          sq.m = q0.x; sq.vx = q0.y; sq.vy = q0.z; sq.vz = q0.w;
+          sq.rho = q1.x; sq.P = q1.y; sq.f = q1.z; sq.cs = q1.w;
+          sq.balsara = q2.x; sq.h = q2.y; sq.u = q2.z; sq.time_bin = __float_as_int(q2.w);
+          sq.alpha_visc = sq.alpha_diff = 0.f;
+          if (SCHEME == SCH_SPHENIX) {
+            const float4 q3 = P[3 * TL_SLOTS + sl];
+            sq.alpha_visc = q3.x;
+            sq.alpha_diff = q3.y;
+          }
+          iact_force<SCHEME>(facc, r2, dx, dy, dz, tq, sq, A.a2_Hubble);
+          nhit++;
+        }
+      }
+    }
+    nsub = 0;
+    __syncwarp();
+  };
+
+#ifdef TL_TIMING
+  long long tm_t0 = clock64(), tm_wait = 0, tm_drain = 0, tm_first = 0;
+  int tm_nwait = 0, tm_ndrain = 0;
+#define TM(x) x
+#else
+#define TM(x)
+#endif
+  int held = 0; /* stages tested but not yet released */
+  const int hold_max = min(NS - 1, max(1, A.hold));
+  for (int it = 0;; it++) {
+    const int s = it % NS;
+    const uint32_t ph = (uint32_t)((it / NS) & 1);
+    if (held >= hold_max) { /* drain and give the held stages back */
+      TM(long long td0 = clock64();)
+      drain();
+      TM(tm_drain += clock64() - td0; tm_ndrain++;)
+      if (lane == 0)
+        for (int k = 1; k <= held; k++) mbar_arrive(sEmpty + ((it - k) % NS));
+      held = 0;
+    }
+    TM(long long tw0 = clock64();)
+    mbar_wait(sFull + s, ph);
+    TM(long long tw1 = clock64(); tm_wait += tw1 - tw0; tm_nwait++; if (it == 0) tm_first = tw1 - tm_t0;)
+    const char *const st = smem + s * SM::kStageBytes;
+    const int32_t *const meta = (const int32_t *)(st + SM::kStageMeta);
+    const int nfr = meta[0];
+    if (nfr == 0) break;
+    const int noct = meta[1];
+    const float4 *const F = (const float4 *)(st + SM::kStageF);
+    const uint8_t *const o2f = (const uint8_t *)(st + SM::kStageO2F);
+    const TileItem *const IT = (const TileItem *)(st + SM::kStageIT);
+    held++;
+
+    /* ---- cull: lane = octet ---- */
+    bool acc = false;
+    if (lane < noct) {
+      const float4 lo = ((const float4 *)(st + SM::kStageOB))[2 * lane];
+      const float4 hi = ((const float4 *)(st + SM::kStageOB))[2 * lane + 1];
+      const TileItem &ii = IT[o2f[lane]];
+      const float r = fmaf(FORCE ? fmaxf(rmax, ii.rsrc) : rmax, PREFILTER_REL, A.margin);
+      float d2;
+      {
+        const float a = lo.x - (bhi[0] - ii.d[0]), b = (blo[0] - ii.d[0]) - hi.x;
+        const float gx = fmaxf(0.f, fmaxf(a, b));
+        d2 = gx * gx;
+      }
+      {
+        const float a = lo.y - (bhi[1] - ii.d[1]), b = (blo[1] - ii.d[1]) - hi.y;
+        const float gy = fmaxf(0.f, fmaxf(a, b));
+        d2 = fmaf(gy, gy, d2);
+      }
+      {
+        const float a = lo.z - (bhi[2] - ii.d[2]), b = (blo[2] - ii.d[2]) - hi.z;
+        const float gz = fmaxf(0.f, fmaxf(a, b));
+        d2 = fmaf(gz, gz, d2);
+      }
+      acc = d2 < r * r;
+    }
+    unsigned m = __ballot_sync(FULL_MASK, acc);
+
+    /* ---- test the accepted octets ---- */
+    int cur = -1;
+    float tpx = 3.0e30f, tpy = 0.f, tpz = 0.f, r2e = 0.f;
+    int nsub_ub = __reduce_max_sync(FULL_MASK, nsub);
+    bool skip = true;
+    while (m) {
+      const int o = __ffs(m) - 1;
+      m &= m - 1u;
+      const int fl = o2f[o];
+      if (fl != cur) {
+        cur = fl;
+        const TileItem &ii = IT[fl];
+        const bool part = tvalid && tdepth >= ii.min_depth && tdepth <= ii.max_depth;
+        tpx = part ? tfx - ii.d[0] : 3.0e30f;
+        tpy = tfy - ii.d[1];
+        tpz = tfz - ii.d[2];
+        const float re = fmaf(thg, PREFILTER_REL, A.margin);
+        r2e = re * re;
+        skip = !__any_sync(FULL_MASK, part);
+      }
+      if (skip) continue;
+      if (nsub_ub > TL_SUBCAP - 2) {
+        nsub_ub = __reduce_max_sync(FULL_MASK, nsub);
+        if (nsub_ub > TL_SUBCAP - 2) {
+          drain();
+          nsub_ub = 0;
+        }
+      }
+      nsub_ub += 2;
+      const int sl = o * 8 + 2 * s4;
+      const float4 a = F[sl], c = F[sl + 1];
+      const int code = (fl << 11) | (s << 8) | sl;
+      ntests++;
+      {
+        const float dx = tpx - a.x, dy = tpy - a.y, dz = tpz - a.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const bool ok = FORCE ? (r2 < fmaxf(r2e, a.w)) : (r2 < r2e);
+        if (ok) {
+          mylist[nsub * 32] = (uint16_t)code;
+          nsub++;
+        }
+      }
+      {
+        const float dx = tpx - c.x, dy = tpy - c.y, dz = tpz - c.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const bool ok = FORCE ? (r2 < fmaxf(r2e, c.w)) : (r2 < r2e);
+        if (ok) {
+          mylist[nsub * 32] = (uint16_t)(code + 1);
+          nsub++;
+        }
+      }
+    }
+  }
+  TM(long long td0 = clock64();)
+  drain();
+  TM(tm_drain += clock64() - td0; tm_ndrain++;
+     if (lane == 0 && warp == 0 && (blockIdx.x % 2048) == 7)
+       printf("TM cta %d life %lld first %lld wait %lld (%d) drain %lld (%d) tests %d hits %d\n", (int)blockIdx.x,
+              clock64() - tm_t0, tm_first, tm_wait, tm_nwait, tm_drain, tm_ndrain, ntests, nhit);)
+
+  /* ---- combine the 4 partial sums of each target and flush ---- */
+  int nh = nhit;
+#pragma unroll
+  for (int o = 8; o < 32; o <<= 1) nh += __shfl_xor_sync(FULL_MASK, nh, o);
+  if (LOOP == LOOP_DENSITY) {
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+      dacc.rho += __shfl_xor_sync(FULL_MASK, dacc.rho, o);
+      dacc.rho_dh += __shfl_xor_sync(FULL_MASK, dacc.rho_dh, o);
+      dacc.wcount += __shfl_xor_sync(FULL_MASK, dacc.wcount, o);
+      dacc.wcount_dh += __shfl_xor_sync(FULL_MASK, dacc.wcount_dh, o);
+      dacc.div_v += __shfl_xor_sync(FULL_MASK, dacc.div_v, o);
+      dacc.rot[0] += __shfl_xor_sync(FULL_MASK, dacc.rot[0], o);
+      dacc.rot[1] += __shfl_xor_sync(FULL_MASK, dacc.rot[1], o);
+      dacc.rot[2] += __shfl_xor_sync(FULL_MASK, dacc.rot[2], o);
+    }
+    if (tvalid && s4 == 0) {
+      float *pa = (float *)&A.dA[ti];
+      float *pb = (float *)&A.dB[ti];
+      atomicAdd(pa + 0, dacc.rho);
+      atomicAdd(pa + 1, dacc.rho_dh);
+      atomicAdd(pa + 2, dacc.wcount);
+      atomicAdd(pa + 3, dacc.wcount_dh);
+      atomicAdd(pb + 0, dacc.div_v);
+      atomicAdd(pb + 1, dacc.rot[0]);
+      atomicAdd(pb + 2, dacc.rot[1]);
+      atomicAdd(pb + 3, dacc.rot[2]);
+    }
+  } else if (LOOP == LOOP_GRADIENT) {
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+      gacc.v_sig = fmaxf(gacc.v_sig, __shfl_xor_sync(FULL_MASK, gacc.v_sig, o));
+      gacc.laplace_u += __shfl_xor_sync(FULL_MASK, gacc.laplace_u, o);
+      gacc.alpha_max = fmaxf(gacc.alpha_max, __shfl_xor_sync(FULL_MASK, gacc.alpha_max, o));
+    }
+    if (tvalid && s4 == 0) {
+      atomic_max_pos(&A.g_vsig[ti], gacc.v_sig);
+      atomicAdd(&A.g_lap[ti], gacc.laplace_u);
+      atomic_max_pos(&A.g_amax[ti], gacc.alpha_max);
+    }
+  } else {
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+      facc.ax += __shfl_xor_sync(FULL_MASK, facc.ax, o);
+      facc.ay += __shfl_xor_sync(FULL_MASK, facc.ay, o);
+      facc.az += __shfl_xor_sync(FULL_MASK, facc.az, o);
+      facc.u_dt += __shfl_xor_sync(FULL_MASK, facc.u_dt, o);
+      facc.h_dt += __shfl_xor_sync(FULL_MASK, facc.h_dt, o);
+      facc.v_sig = fmaxf(facc.v_sig, __shfl_xor_sync(FULL_MASK, facc.v_sig, o));
+      facc.min_ngb = min(facc.min_ngb, __shfl_xor_sync(FULL_MASK, facc.min_ngb, o));
+    }
+    if (tvalid && s4 == 0) {
+      float *po = (float *)&A.fo1[ti];
+      atomicAdd(po + 0, facc.ax);
+      atomicAdd(po + 1, facc.ay);
+      atomicAdd(po + 2, facc.az);
+      atomicAdd(po + 3, facc.u_dt);
+      atomicAdd(&A.f_hdt[ti], facc.h_dt);
+      if (SCHEME != SCH_SPHENIX) atomic_max_pos(&A.f_vsig[ti], facc.v_sig);
+      atomicMin(&A.f_minngb[ti], facc.min_ngb);
+    }
+  }
+  if (tvalid && s4 == 0 && nh) atomicAdd(&A.count[ti], nh);
+  int tot = nhit, tt = ntests;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(FULL_MASK, tot, o);
+    tt += __shfl_xor_sync(FULL_MASK, tt, o);
+  }
+  if (lane == 0 && tot) atomicAdd(A.total, (unsigned long long)tot);
+  if (lane == 0 && tt) atomicAdd(A.tests, 2ull * (unsigned long long)tt);
+}
+
+}  // namespace swiftgpu
+#endif

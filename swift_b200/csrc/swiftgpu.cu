@@ -23,6 +23,7 @@
 
 #include "../../include/swiftgpu.h"
 #include "loops_cta.cuh"
+#include "loops_tile.cuh"
 
 using namespace swiftgpu;
 
@@ -92,6 +93,11 @@ struct swiftgpu_handle {
         *gleft = nullptr, *gright = nullptr;
   int8_t *time_bin = nullptr, *depth_h = nullptr;
   int32_t *f_minngb = nullptr, *nd = nullptr, *ng = nullptr, *nf = nullptr;
+  /* tile pipeline records (loops_tile.cuh) */
+  float4 *xf = nullptr, *gq = nullptr, *boxes = nullptr;
+  double *xs = nullptr; /* 3 columns of n + 4 doubles */
+  int32_t *d_box_first = nullptr;
+  int64_t nboxes = 0;
   uint32_t *sort_idx = nullptr;
   float *d_sort_keys = nullptr; /* key scratch, only when a requested segment exceeds SORT_SMEM_MAX */
   int64_t sort_total = 0;
@@ -343,6 +349,62 @@ __global__ void __launch_bounds__(128)
       if (lane == 0) ext[c.seg_base + rank] = make_float2(a, b);
       rank++;
     }
+  }
+}
+
+/* ======================================================================== */
+/* Kernels: the TMA-copyable source records of the tile pipeline             */
+/* (loops_tile.cuh). xf/x4 follow the positions (once per upload / xv halo), */
+/* xf.w follows h (again before the force loop), the octet boxes follow xf.  */
+/* ======================================================================== */
+__device__ __forceinline__ float reach2(float h, float margin) {
+  const float re = fmaf(__fmul_rn(h, KERNEL_GAMMA), PREFILTER_REL, margin);
+  return re * re;
+}
+__global__ void k_prep_tiles(const double *x, const float *h, int64_t n, float margin, float4 *xf,
+                             double *xs) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double px = x[3 * p], py = x[3 * p + 1], pz = x[3 * p + 2];
+  xf[p] = make_float4(__double2float_rn(px), __double2float_rn(py), __double2float_rn(pz),
+                      reach2(h[p], margin));
+  xs[p] = px;
+  xs[(n + 4) + p] = py;
+  xs[2 * (n + 4) + p] = pz;
+}
+__global__ void k_refresh_reach(const float *h, int64_t n, float margin, float4 *xf) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  xf[p].w = reach2(h[p], margin);
+}
+/* gradient payload of every particle: (u, rho, soundspeed, alpha_visc) */
+__global__ void k_prep_gq(const float4 *fq1, const float4 *fq2, const float4 *fq3, int64_t n, float4 *gq) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float4 q1 = fq1[p];
+  gq[p] = make_float4(fq2[p].z, q1.x, q1.w, fq3[p].x);
+}
+/* One warp per cell (every level): the axis-aligned box of each octet of 8
+ * consecutive particles of the cell, in absolute floats. */
+__global__ void __launch_bounds__(128)
+    k_octet_boxes(const DevCell *cells, int ncells, const int32_t *box_first, const float4 *xf,
+                  float4 *boxes) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= ncells) return;
+  const int first = cells[c].first, count = cells[c].count;
+  const int noct = (count + 7) >> 3;
+  float4 *out = boxes + 2 * (size_t)box_first[c];
+  for (int o = lane; o < noct; o += 32) {
+    float lo0 = 3.0e30f, lo1 = 3.0e30f, lo2 = 3.0e30f, hi0 = -3.0e30f, hi1 = -3.0e30f, hi2 = -3.0e30f;
+    const int k1 = min(count, 8 * o + 8);
+    for (int k = 8 * o; k < k1; k++) {
+      const float4 f = xf[first + k];
+      lo0 = fminf(lo0, f.x); lo1 = fminf(lo1, f.y); lo2 = fminf(lo2, f.z);
+      hi0 = fmaxf(hi0, f.x); hi1 = fmaxf(hi1, f.y); hi2 = fmaxf(hi2, f.z);
+    }
+    out[2 * o] = make_float4(lo0, lo1, lo2, 0.f);
+    out[2 * o + 1] = make_float4(hi0, hi1, hi2, 0.f);
   }
 }
 
@@ -860,6 +922,8 @@ static void free_parts(H *h) {
   cudaFree(h->div_v_prev); cudaFree(h->div_v_dt); cudaFree(h->div_v); cudaFree(h->gleft);
   cudaFree(h->gright); cudaFree(h->time_bin); cudaFree(h->depth_h); cudaFree(h->f_minngb);
   cudaFree(h->nd); cudaFree(h->ng); cudaFree(h->nf);
+  cudaFree(h->xf); cudaFree(h->xs); cudaFree(h->gq);
+  h->xf = h->gq = nullptr; h->xs = nullptr;
   h->d_aos = nullptr; h->x = nullptr;
   h->n = 0;
 }
@@ -886,6 +950,7 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   halo_release(h);
   cudaFree(h->d_cells); cudaFree(h->d_cells_init); cudaFree(h->d_dmin); cudaFree(h->d_dxp); cudaFree(h->sort_idx); cudaFree(h->d_sort_keys); cudaFree(h->d_segs); cudaFree(h->d_ext); cudaFree(h->d_ext_cells); cudaFree(h->d_counters);
   cudaFree(h->d_flag); cudaFree(h->d_force_bits);
+  cudaFree(h->boxes); cudaFree(h->d_box_first);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1087,6 +1152,23 @@ static int build_lists(H *h, bool force_only) {
     CK(to_device(&h->d_dxp, dxp));
   }
   CK(to_device(&h->d_cells, dc));
+  {
+    /* octet boxes of every cell (tile pipeline) */
+    std::vector<int32_t> bf(h->ncells);
+    int64_t nb = 0;
+    for (int c = 0; c < h->ncells; c++) {
+      bf[c] = (int32_t)nb;
+      nb += (dc[c].count + 7) / 8;
+    }
+    if (nb > 0x7fffffffLL) return h->fail("too many octet boxes");
+    CK(to_device(&h->d_box_first, bf));
+    if (nb != h->nboxes || !h->boxes) {
+      cudaFree(h->boxes);
+      h->boxes = nullptr;
+      CK(cudaMalloc((void **)&h->boxes, std::max<int64_t>(nb, 1) * 2 * sizeof(float4)));
+      h->nboxes = nb;
+    }
+  }
   CK(to_device(&h->d_segs, segs));
   h->nsegs = (int)segs.size();
   CK(to_device(&h->d_ext_cells, ext_cells));
@@ -1138,6 +1220,8 @@ static int alloc_parts(H *h, int64_t n) {
   AL(h->div_v_dt, float, n); AL(h->div_v, float, n); AL(h->gleft, float, n); AL(h->gright, float, n);
   AL(h->time_bin, int8_t, n); AL(h->depth_h, int8_t, n);
   AL(h->f_minngb, int32_t, n); AL(h->nd, int32_t, n); AL(h->ng, int32_t, n); AL(h->nf, int32_t, n);
+  AL(h->xf, float4, n + 2); AL(h->xs, double, 3 * (n + 4));
+  if (h->cfg.scheme == SCH_SPHENIX) AL(h->gq, float4, n + 2);
 #undef AL
   h->n = n;
   h->lists_built = false;
@@ -1198,9 +1282,28 @@ static int phase_end(H *h, double *ms_out) {
 }
 
 static bool use_cta_loops();
+static int loop_kind();
+static float tile_maxdim(const H *h) {
+  return (float)std::max(h->cfg.dim[0], std::max(h->cfg.dim[1], h->cfg.dim[2]));
+}
+/* absolute widening of the float prefilter on absolute-position floats (error < 4.2e-7 * dim) */
+static float tile_margin(const H *h) { return 1.0e-6f * tile_maxdim(h); }
+/* r-margin under which the sorted-axis conditions are implied (key rounding < 5e-7 * dim) */
+static float tile_keyE(const H *h) { return 2.0e-6f * tile_maxdim(h); }
+static int prep_tiles(H *h) {
+  const int64_t n = h->n;
+  k_prep_tiles<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->x, h->hh, n, tile_margin(h), h->xf,
+                                                                  h->xs);
+  k_octet_boxes<<<(h->ncells * 32 + 127) / 128, 128, 0, h->stream>>>(h->d_cells, h->ncells,
+                                                                     h->d_box_first, h->xf, h->boxes);
+  h->stats.n_launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
 /* full = the 13-axis sorted index arrays of runner_do_hydro_sort; the CTA
  * loops only consume the key extrema. */
 static int launch_sort(H *h, bool full) {
+  if (loop_kind() == 2 && prep_tiles(h)) return 1;
   if (h->n_ext_cells > 0) {
     k_extrema<<<(h->n_ext_cells * 32 + 127) / 128, 128, 0, h->stream>>>(h->d_ext_cells, h->n_ext_cells,
                                                                         h->d_cells, h->x, h->d_ext);
@@ -1242,6 +1345,17 @@ static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
   A.ext = h->d_ext;
   A.x = h->x; A.mv = h->mv; A.h = h->hh; A.depth_h = h->depth_h; A.time_bin = h->time_bin;
   A.fq1 = h->fq1; A.fq2 = h->fq2; A.fq3 = h->fq3;
+  A.xf = h->xf; A.xs0 = h->xs; A.xs1 = h->xs + (h->n + 4); A.xs2 = h->xs + 2 * (h->n + 4); A.gq = h->gq; A.boxes = h->boxes; A.cell_box_first = h->d_box_first;
+  A.keyE = tile_keyE(h);
+  A.margin = tile_margin(h);
+  {
+    static int hold = -1;
+    if (hold < 0) {
+      const char *e = getenv("SWIFTGPU_HOLD");
+      hold = e ? atoi(e) : 8;
+    }
+    A.hold = hold;
+  }
   A.dA = h->dA; A.dB = h->dB; A.g_vsig = h->g_vsig; A.g_lap = h->g_lap; A.g_amax = h->g_amax;
   A.fo1 = h->fo1; A.f_hdt = h->f_hdt; A.f_vsig = h->f_vsig; A.f_minngb = h->f_minngb;
   A.count = count;
@@ -1273,13 +1387,36 @@ static int read_counter(H *h, int k, int64_t *out) {
 
 /* CTA-cooperative type-1 loops (loops_cta.cuh); SWIFTGPU_WARP_LOOPS=1 selects the
  * warp-private kernels of loops.cuh instead (kept for A/B measurements). */
-static bool use_cta_loops() {
+/* SWIFTGPU_LOOPS=tile (default: TMA pipeline, loops_tile.cuh) | cta (loops_cta.cuh) |
+ * warp (loops.cuh); the older kernels are kept for A/B measurements. */
+static int loop_kind() {
   static int v = -1;
   if (v < 0) {
-    const char *e = getenv("SWIFTGPU_WARP_LOOPS");
-    v = (e && e[0] == '1') ? 0 : 1;
+    const char *e = getenv("SWIFTGPU_LOOPS");
+    const char *w = getenv("SWIFTGPU_WARP_LOOPS");
+    v = 2;
+    if (e && !strcmp(e, "cta")) v = 1;
+    if (e && !strcmp(e, "warp")) v = 0;
+    if (w && w[0] == '1') v = 0;
   }
-  return v == 1;
+  return v;
+}
+static bool use_cta_loops() { return loop_kind() >= 1; }
+template <int LOOP, int SCHEME>
+static cudaError_t launch_tile(H *h, const LoopArgs &A) {
+  constexpr bool FORCE = (LOOP == LOOP_FORCE);
+  constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
+  constexpr int NS = FORCE ? (SCHEME == SCH_SPHENIX ? 3 : 4) : (LOOP == LOOP_GRADIENT ? 3 : 4);
+  constexpr int bytes = TileSmem<NP, NS>::kBytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_tile<LOOP, SCHEME, NS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  k_tile<LOOP, SCHEME, NS><<<A.ntasks, TL_THREADS, bytes, h->stream>>>(A);
+  return cudaGetLastError();
 }
 template <int LOOP, bool SUBSET, int SCHEME>
 static cudaError_t launch_cta(H *h, const LoopArgs &A) {
@@ -1298,12 +1435,14 @@ static cudaError_t launch_cta(H *h, const LoopArgs &A) {
 }
 template <int LOOP, bool SUBSET>
 static cudaError_t launch_loop1(H *h, const LoopArgs &A) {
+  if (loop_kind() == 2) return launch_tile<LOOP, 0>(h, A);
   if (use_cta_loops()) return launch_cta<LOOP, SUBSET, 0>(h, A);
   k_loop1<LOOP, SUBSET><<<A.ntasks, 32, Tile1<LOOP, SUBSET>::kBytes, h->stream>>>(A);
   return cudaGetLastError();
 }
 template <int SCHEME>
 static cudaError_t launch_loop2(H *h, const LoopArgs &A) {
+  if (loop_kind() == 2) return launch_tile<LOOP_FORCE, SCHEME>(h, A);
   if (use_cta_loops()) return launch_cta<LOOP_FORCE, false, SCHEME>(h, A);
   k_loop2<SCHEME><<<A.ntasks, 32, Tile2<SCHEME>::kBytes, h->stream>>>(A);
   return cudaGetLastError();
@@ -1424,6 +1563,10 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   if (phase_begin(h)) return 1;
   CK(cudaMemsetAsync(h->d_counters + 1, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
+  if (loop_kind() == 2) {
+    k_prep_gq<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->fq1, h->fq2, h->fq3, h->n, h->gq);
+    h->stats.n_launches++;
+  }
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->ng, 1);
     CK((launch_loop1<LOOP_GRADIENT, false>(h, A)));
@@ -1512,6 +1655,11 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(unsigned long long), h->stream));
   if (build_targets(h, h->L_force)) return 1;
+  if (loop_kind() == 2) { /* h changed in the ghost (and the rho halo): source reach of the prefilter */
+    k_refresh_reach<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->hh, h->n, tile_margin(h),
+                                                                          h->xf);
+    h->stats.n_launches++;
+  }
   if (h->L_force.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_force, h->nf, 2);
     switch (h->cfg.scheme) {
