@@ -56,6 +56,12 @@ struct DevList {
   }
 };
 
+struct LeafRec {
+  double loc[3];
+  float iwidth[3]; /* 32 / width */
+  int32_t first, count;
+};
+
 struct SortSeg {
   int32_t cell;
   int32_t sid;
@@ -93,6 +99,16 @@ struct swiftgpu_handle {
         *gleft = nullptr, *gright = nullptr;
   int8_t *time_bin = nullptr, *depth_h = nullptr;
   int32_t *f_minngb = nullptr, *nd = nullptr, *ng = nullptr, *nf = nullptr;
+  /* device order: particles of every LEAF are kept in Morton order of their
+   * position inside the leaf (compact octets for the box culling of the
+   * loops); d2h[device index] = host index, h2d the inverse. Cells stay
+   * contiguous ranges, so nothing but the AoS boundary sees the permutation. */
+  int32_t *d_d2h = nullptr, *d_h2d = nullptr;
+  int32_t *d_cnt_tmp = nullptr; /* download_counts scratch */
+  struct LeafRec *d_leaves = nullptr;
+  int nleaves = 0;
+  bool leaves_valid = false;
+  bool perm_stale = false; /* cells changed after the particles were transposed */
   /* tile pipeline records (loops_tile.cuh) */
   float4 *xf = nullptr, *gq = nullptr, *boxes = nullptr;
   double *xs = nullptr; /* 3 columns of n + 4 doubles */
@@ -167,11 +183,85 @@ struct Soa {
   int32_t *f_minngb;
 };
 
-__global__ void k_aos_to_soa(const char *aos, DevLayout D, Soa S, int64_t n) {
+__global__ void k_iota2(int32_t *a, int32_t *b, int64_t n) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  a[p] = (int32_t)p;
+  b[p] = (int32_t)p;
+}
+
+/* Morton order inside every leaf (one CTA per leaf, bitonic sort of
+ * (15-bit Morton code, index) in shared memory). Leaves above LEAF_SORT_MAX
+ * particles keep the host order. */
+#define LEAF_SORT_MAX 1024
+__device__ __forceinline__ uint32_t spread5(uint32_t v) {
+  /* 5 bits -> every third bit */
+  v = (v | (v << 8)) & 0x0000100fu;
+  v = (v | (v << 4)) & 0x000010c3u;
+  v = (v | (v << 2)) & 0x00001249u;
+  return v;
+}
+__global__ void __launch_bounds__(128)
+    k_leaf_order(const LeafRec *leaves, int nleaves, const char *aos, int part_size, int x_off,
+                 int32_t *d2h, int32_t *h2d) {
+  __shared__ uint32_t skey[LEAF_SORT_MAX];
+  const int l = blockIdx.x;
+  if (l >= nleaves) return;
+  const LeafRec R = leaves[l];
+  const int n = R.count;
+  if (n <= 1 || n > LEAF_SORT_MAX) return;
+  int N = 1;
+  while (N < n) N <<= 1;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    uint32_t key = 0xffffffffu;
+    if (i < n) {
+      const char *b = aos + (size_t)part_size * (size_t)(R.first + i);
+      uint32_t q[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float f = (float)(*(const double *)(b + x_off + 8 * k) - R.loc[k]) * R.iwidth[k];
+        q[k] = (uint32_t)min(31, max(0, (int)f));
+      }
+      const uint32_t mort = (spread5(q[0]) << 2) | (spread5(q[1]) << 1) | spread5(q[2]);
+      key = (mort << 10) | (uint32_t)i;
+    }
+    skey[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= N; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const uint32_t a = skey[i], c = skey[j];
+          const bool up = ((i & size) == 0);
+          if ((a > c) == up) {
+            skey[i] = c;
+            skey[j] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const int i = (int)(skey[r] & 1023u);
+    d2h[R.first + r] = R.first + i;
+    h2d[R.first + i] = R.first + r;
+  }
+}
+
+__global__ void k_scatter_i32(const int32_t *src, const int32_t *d2h, int64_t n, int32_t *dst) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  dst[d2h[p]] = src[p];
+}
+
+__global__ void k_aos_to_soa(const char *aos, DevLayout D, Soa S, int64_t n, const int32_t *d2h) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const swiftgpu_part_layout &L = D.L;
-  const char *b = aos + (size_t)L.size * p;
+  const char *b = aos + (size_t)L.size * (size_t)d2h[p];
   S.x[3 * p + 0] = rd<double>(b, L.x);
   S.x[3 * p + 1] = rd<double>(b, L.x + 8);
   S.x[3 * p + 2] = rd<double>(b, L.x + 16);
@@ -214,12 +304,12 @@ __global__ void k_aos_to_soa(const char *aos, DevLayout D, Soa S, int64_t n) {
 /* Writes back the fields the phases run so far have made valid, for ACTIVE
  * particles only (inactive particles are read-only on this path). */
 __global__ void k_soa_to_aos(char *aos, DevLayout D, Soa S, int64_t n, int max_active_bin,
-                             int density_only) {
+                             int density_only, const int32_t *d2h) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (S.time_bin[p] > max_active_bin) return;
   const swiftgpu_part_layout &L = D.L;
-  char *b = aos + (size_t)L.size * p;
+  char *b = aos + (size_t)L.size * (size_t)d2h[p];
   wr<float>(b, L.h, S.h[p]);
   wr<int8_t>(b, L.depth_h, S.depth_h[p]);
   const float4 a = S.dA[p], c = S.dB[p];
@@ -923,6 +1013,8 @@ static void free_parts(H *h) {
   cudaFree(h->gright); cudaFree(h->time_bin); cudaFree(h->depth_h); cudaFree(h->f_minngb);
   cudaFree(h->nd); cudaFree(h->ng); cudaFree(h->nf);
   cudaFree(h->xf); cudaFree(h->xs); cudaFree(h->gq);
+  cudaFree(h->d_d2h); cudaFree(h->d_h2d); cudaFree(h->d_cnt_tmp);
+  h->d_d2h = h->d_h2d = h->d_cnt_tmp = nullptr;
   h->xf = h->gq = nullptr; h->xs = nullptr;
   h->d_aos = nullptr; h->x = nullptr;
   h->n = 0;
@@ -950,7 +1042,7 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   halo_release(h);
   cudaFree(h->d_cells); cudaFree(h->d_cells_init); cudaFree(h->d_dmin); cudaFree(h->d_dxp); cudaFree(h->sort_idx); cudaFree(h->d_sort_keys); cudaFree(h->d_segs); cudaFree(h->d_ext); cudaFree(h->d_ext_cells); cudaFree(h->d_counters);
   cudaFree(h->d_flag); cudaFree(h->d_force_bits);
-  cudaFree(h->boxes); cudaFree(h->d_box_first);
+  cudaFree(h->boxes); cudaFree(h->d_box_first); cudaFree(h->d_leaves);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -992,6 +1084,8 @@ extern "C" int swiftgpu_upload_cells(swiftgpu_t *h, const swiftgpu_cell *cells, 
   h->lists_built = false;
   h->sorted = false;
   h->halo_ready = false; /* the send/receive lists follow the cells */
+  h->leaves_valid = false;
+  if (h->n > 0 && h->x) h->perm_stale = true; /* the device order follows the leaves */
   return 0;
 }
 
@@ -1199,7 +1293,11 @@ static int build_lists(H *h, bool force_only) {
   return 0;
 }
 
+static int transpose_in(H *h);
 static int ensure_lists(H *h) {
+  /* new cells after the particles were transposed: redo the device order from
+   * the AoS copy (the step restarts from the uploaded particle state) */
+  if (h->perm_stale && h->d_aos && h->n > 0 && transpose_in(h)) return 1;
   if (h->lists_built) return 0;
   return build_lists(h, false);
 }
@@ -1221,10 +1319,53 @@ static int alloc_parts(H *h, int64_t n) {
   AL(h->time_bin, int8_t, n); AL(h->depth_h, int8_t, n);
   AL(h->f_minngb, int32_t, n); AL(h->nd, int32_t, n); AL(h->ng, int32_t, n); AL(h->nf, int32_t, n);
   AL(h->xf, float4, n + 2); AL(h->xs, double, 3 * (n + 4));
+  AL(h->d_d2h, int32_t, n); AL(h->d_h2d, int32_t, n);
   if (h->cfg.scheme == SCH_SPHENIX) AL(h->gq, float4, n + 2);
 #undef AL
   h->n = n;
   h->lists_built = false;
+  return 0;
+}
+
+static bool use_leaf_order() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SWIFTGPU_NO_REORDER");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+/* Device order of the particles now in d_aos (host order). */
+static int build_device_order(H *h) {
+  const int64_t n = h->n;
+  k_iota2<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_d2h, h->d_h2d, n);
+  h->stats.n_launches++;
+  if (!use_leaf_order() || h->cells.empty()) return 0;
+  if (!h->leaves_valid) {
+    std::vector<LeafRec> lv;
+    for (const swiftgpu_cell &c : h->cells) {
+      if (c.split || c.count <= 1) continue;
+      if (c.first_part < 0 || c.first_part + c.count > n) return h->fail("cell range outside the particle array");
+      LeafRec R;
+      for (int k = 0; k < 3; k++) {
+        R.loc[k] = c.loc[k];
+        R.iwidth[k] = c.width[k] > 0. ? (float)(32. / c.width[k]) : 0.f;
+      }
+      R.first = (int32_t)c.first_part;
+      R.count = c.count;
+      lv.push_back(R);
+    }
+    CK(to_device(&h->d_leaves, lv));
+    h->nleaves = (int)lv.size();
+    h->leaves_valid = true;
+  }
+  if (h->nleaves > 0) {
+    k_leaf_order<<<h->nleaves, 128, 0, h->stream>>>(h->d_leaves, h->nleaves, h->d_aos, h->cfg.layout.size,
+                                                    h->cfg.layout.x, h->d_d2h, h->d_h2d);
+    h->stats.n_launches++;
+  }
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -1233,13 +1374,15 @@ static int transpose_in(H *h) {
   DevLayout D;
   D.L = h->cfg.layout;
   D.scheme = h->cfg.scheme;
+  if (build_device_order(h)) return 1;
+  h->perm_stale = false;
   CK(cudaMemsetAsync(h->nd, 0, sizeof(int32_t) * n, h->stream));
   CK(cudaMemsetAsync(h->ng, 0, sizeof(int32_t) * n, h->stream));
   CK(cudaMemsetAsync(h->nf, 0, sizeof(int32_t) * n, h->stream));
   CK(cudaMemsetAsync(h->dA, 0, sizeof(float4) * n, h->stream));
   CK(cudaMemsetAsync(h->dB, 0, sizeof(float4) * n, h->stream));
   CK(cudaMemsetAsync(h->fq3, 0, sizeof(float4) * n, h->stream));
-  k_aos_to_soa<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_aos, D, soa_of(h), n);
+  k_aos_to_soa<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_aos, D, soa_of(h), n, h->d_d2h);
   h->stats.n_launches++;
   CK(cudaGetLastError());
   h->phases_done = 0;
@@ -1715,7 +1858,7 @@ static int transpose_out(H *h) {
   D.scheme = h->cfg.scheme;
   const int density_only = (h->phases_done & SWIFTGPU_PHASE_GHOST) ? 0 : 1;
   k_soa_to_aos<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(
-      h->d_aos, D, soa_of(h), h->n, h->step.max_active_bin, density_only);
+      h->d_aos, D, soa_of(h), h->n, h->step.max_active_bin, density_only, h->d_d2h);
   h->stats.n_launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1762,9 +1905,18 @@ extern "C" int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density, int32
                                         int32_t *n_force, int64_t nparts) {
   if (!h || nparts != h->n) return 1;
   cudaSetDevice(h->cfg.device);
-  if (n_density) CK(cudaMemcpy(n_density, h->nd, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
-  if (n_gradient) CK(cudaMemcpy(n_gradient, h->ng, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
-  if (n_force) CK(cudaMemcpy(n_force, h->nf, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost));
+  if (!h->d_cnt_tmp) CK(cudaMalloc((void **)&h->d_cnt_tmp, sizeof(int32_t) * (size_t)nparts));
+  const int32_t *src[3] = {h->nd, h->ng, h->nf};
+  int32_t *dst[3] = {n_density, n_gradient, n_force};
+  for (int k = 0; k < 3; k++) {
+    if (!dst[k]) continue;
+    /* device order -> host order */
+    k_scatter_i32<<<(unsigned)((nparts + 255) / 256), 256, 0, h->stream>>>(src[k], h->d_d2h, nparts,
+                                                                          h->d_cnt_tmp);
+    h->stats.n_launches++;
+    CK(cudaMemcpyAsync(dst[k], h->d_cnt_tmp, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   return 0;
 }
 
@@ -1782,9 +1934,14 @@ extern "C" int swiftgpu_download_sort(swiftgpu_t *h, int32_t cell, int32_t sid, 
     CK(cudaStreamSynchronize(h->stream));
   }
   const int rank = __builtin_popcount((unsigned)c.sort_mask & ((1u << sid) - 1u));
-  if (idx_out)
+  if (idx_out) {
     CK(cudaMemcpy(idx_out, h->sort_idx + c.sort_base + (int64_t)rank * c.count, sizeof(int32_t) * c.count,
                   cudaMemcpyDeviceToHost));
+    /* indices are relative to the cell in DEVICE order: report them in the host's order */
+    std::vector<int32_t> d2h(c.count);
+    CK(cudaMemcpy(d2h.data(), h->d_d2h + c.first, sizeof(int32_t) * c.count, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < c.count; k++) idx_out[k] = d2h[idx_out[k]] - c.first;
+  }
   float2 e;
   CK(cudaMemcpy(&e, h->d_ext + c.seg_base + rank, sizeof(e), cudaMemcpyDeviceToHost));
   if (key_min) *key_min = e.x;
@@ -1945,7 +2102,7 @@ extern "C" int swiftgpu_halo_exchange(swiftgpu_t *h, int phase) {
   int64_t bytes = 0;
   for (HaloPeer &P : h->halo) {
     if (P.nsend > 0) {
-      k_halo_pack<<<(unsigned)((P.nsend + 255) / 256), 256, 0, h->stream>>>(F, P.d_send_idx, P.nsend,
+      k_halo_pack<<<(unsigned)((P.nsend + 255) / 256), 256, 0, h->stream>>>(F, P.d_send_idx, h->d_h2d, P.nsend,
                                                                           P.d_sendbuf);
       h->stats.n_launches++;
     }
@@ -1969,7 +2126,7 @@ extern "C" int swiftgpu_halo_exchange(swiftgpu_t *h, int phase) {
   if (rc != 0) return h->fail("ncclGroupEnd: %s", N->GetErrorString(rc));
   for (HaloPeer &P : h->halo) {
     if (P.nrecv > 0) {
-      k_halo_unpack<<<(unsigned)((P.nrecv + 255) / 256), 256, 0, h->stream>>>(F, P.d_recv_idx, P.nrecv,
+      k_halo_unpack<<<(unsigned)((P.nrecv + 255) / 256), 256, 0, h->stream>>>(F, P.d_recv_idx, h->d_h2d, P.nrecv,
                                                                             P.d_recvbuf);
       h->stats.n_launches++;
     }
