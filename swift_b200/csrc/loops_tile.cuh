@@ -48,7 +48,14 @@ namespace swiftgpu {
 #define TL_SLOTS 256 /* source slots per stage */
 #define TL_OCT (TL_SLOTS / 8)
 #define TL_FRAGS 8   /* fragments per stage */
-#define TL_SUBCAP 14 /* sub-list capacity per lane */
+#define TL_SUBCAP1 10 /* sub-list capacity per lane, type-1 loops (3 CTAs/SM) */
+#define TL_SUBCAP2 16 /* ... force loop (2 CTAs/SM) */
+#ifndef TL_DENS_BLOCKS
+#define TL_DENS_BLOCKS 3 /* resident CTAs per SM the type-1 kernels are compiled for */
+#endif
+#ifndef TL_DENS_NS
+#define TL_DENS_NS 4
+#endif
 #define TL_DCOL (TL_SLOTS + 2 * TL_FRAGS) /* double column: 2 spare entries per fragment (alignment) */
 
 /* ---- mbarrier / bulk-TMA PTX ---- */
@@ -106,7 +113,7 @@ struct __align__(8) TileItem {
 };
 static_assert(sizeof(TileItem) == 88, "TileItem");
 
-template <int NP, int NS>
+template <int NP, int NS, int QCAP>
 struct TileSmem {
   static constexpr int kStageF = 0;
   static constexpr int kStageP = kStageF + TL_SLOTS * 16;
@@ -117,11 +124,12 @@ struct TileSmem {
   static constexpr int kStageMeta = kStageO2F + TL_OCT;
   static constexpr int kStageBytes = ((kStageMeta + 16) + 127) & ~127;
   static constexpr int kList = NS * kStageBytes;
-  static constexpr int kBar = kList + TL_SUBCAP * 32 * TL_CWARPS * 2;
+  static constexpr int kBar = kList + QCAP * 32 * TL_CWARPS * 2;
   static constexpr int kBox = kBar + 2 * NS * 8;
   static constexpr int kWin = kBox + (TL_CWARPS + 1) * 32; /* producer: constants of 32 items */
   static constexpr int kWinAux = kWin + 32 * (int)sizeof(TileItem);
-  static constexpr int kBytes = kWinAux + 32 * 8;
+  static constexpr int kTX = kWinAux + 32 * 8; /* target doubles: 3 columns of TL_TARGETS */
+  static constexpr int kBytes = kTX + 3 * TL_TARGETS * 8;
 };
 
 /* ---- exact sorted-axis conditions (rare path) ---- */
@@ -237,10 +245,11 @@ __device__ __forceinline__ float sure_r2(float a, float E) {
 }
 
 template <int LOOP, int SCHEME, int NS>
-__global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_tile(const LoopArgs A) {
+__global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : TL_DENS_BLOCKS)) k_tile(const LoopArgs A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  typedef TileSmem<NP, NS> SM;
+  constexpr int QCAP = FORCE ? TL_SUBCAP2 : TL_SUBCAP1;
+  typedef TileSmem<NP, NS, QCAP> SM;
   extern __shared__ __align__(128) char smem_tl[];
   char *const smem = smem_tl;
   uint16_t *const sList = (uint16_t *)(smem + SM::kList);
@@ -320,10 +329,16 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_ti
   const float thg = __fmul_rn(th, KERNEL_GAMMA);
   const float tsure2 = sure_r2(thg, A.keyE);
   const float tfx = __double2float_rn(tx), tfy = __double2float_rn(ty), tfz = __double2float_rn(tz);
+  double *const sTX = (double *)(smem + SM::kTX) + (consumer ? warp * 8 + t8 : 0);
+  if (consumer && s4 == 0) {
+    sTX[0] = tx;
+    sTX[TL_TARGETS] = ty;
+    sTX[2 * TL_TARGETS] = tz;
+  }
 
   /* the warp's target box (absolute floats) and its reach */
-  float blo[3], bhi[3], rmax;
   {
+    float blo[3], bhi[3], rmax;
     blo[0] = tvalid ? tfx : 3.0e30f;
     blo[1] = tvalid ? tfy : 3.0e30f;
     blo[2] = tvalid ? tfz : 3.0e30f;
@@ -564,13 +579,16 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_ti
   /* CONSUMERS                                                              */
   /* ===================================================================== */
   if (warp >= nwarps_used) return; /* no targets: not counted in the empty barriers */
-  SlowArgs SA;
-  SA.items = A.items;
-  SA.cells = A.cells;
-  SA.ext = A.ext;
-  SA.dim[0] = A.dim[0];
-  SA.dim[1] = A.dim[1];
-  SA.dim[2] = A.dim[2];
+  auto slow_args = [&]() {
+    SlowArgs SA;
+    SA.items = A.items;
+    SA.cells = A.cells;
+    SA.ext = A.ext;
+    SA.dim[0] = A.dim[0];
+    SA.dim[1] = A.dim[1];
+    SA.dim[2] = A.dim[2];
+    return SA;
+  };
 
   DensityAcc dacc;
   dacc.zero();
@@ -585,7 +603,7 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_ti
   int nhit = 0;
   int ntests = 0;
   int nsub = 0; /* entries in my sub-list */
-  uint16_t *const wlist = sList + warp * (TL_SUBCAP * 32);
+  uint16_t *const wlist = sList + warp * (QCAP * 32);
   uint16_t *const mylist = wlist + lane;
 
   /* ---- INTERACT: merge the 4 sub-lists of each target and drain ---- */
@@ -613,6 +631,7 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_ti
       const double Xx = D[0], Xy = D[TL_DCOL], Xz = D[2 * TL_DCOL];
       float dx, dy, dz;
       {
+        const double tx = sTX[0], ty = sTX[TL_TARGETS], tz = sTX[2 * TL_TARGETS];
         const double ax = __dsub_rn(tx, ii.ot[0]), ay = __dsub_rn(ty, ii.ot[1]), az = __dsub_rn(tz, ii.ot[2]);
         if (ii.dbl) {
           dx = dsubf(ax, Xx);
@@ -630,7 +649,7 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_ti
       if (!FORCE) {
         bool hit = part && (r2 < thg2);
         if (hit && !ii.nokey && !(r2 < tsure2 && thg <= ii.hcap))
-          hit = exact_type1(SA, ii.item, tx, ty, tz, thg, Xx, Xy, Xz);
+          hit = exact_type1(slow_args(), ii.item, sTX[0], sTX[TL_TARGETS], sTX[2 * TL_TARGETS], thg, Xx, Xy, Xz);
         if (hit) {
           const float4 f0 = P[sl];
           if (LOOP == LOOP_DENSITY) {
@@ -653,7 +672,7 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_ti
           const float shg = __fmul_rn(sh, KERNEL_GAMMA);
           const bool sure = (!a1 || (r2 < tsure2 && thg <= ii.hcap)) &&
                             (!a2 || (r2 < sure_r2(shg, A.keyE) && shg <= ii.rsrc));
-          if (!sure) ok = exact_type2(SA, ii.item, tx, ty, tz, thg, thg2, Xx, Xy, Xz, shg, shg2, r2);
+          if (!sure) ok = exact_type2(slow_args(), ii.item, sTX[0], sTX[TL_TARGETS], sTX[2 * TL_TARGETS], thg, thg2, Xx, Xy, Xz, shg, shg2, r2);
         }
         if (ok) {
           ForceQ sq;
@@ -677,124 +696,147 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : 3)) k_ti
   };
 
 #ifdef TL_TIMING
-  long long tm_t0 = clock64(), tm_wait = 0, tm_drain = 0, tm_first = 0;
+#define TCLK(v) { __syncwarp(); asm volatile("" ::: "memory"); v = clock64(); asm volatile("" ::: "memory"); }
+  long long tm_t0, tm_wait = 0, tm_drain = 0, tm_first = 0, tm_cull = 0, tm_test = 0, tm_a, tm_b;
   int tm_nwait = 0, tm_ndrain = 0;
+  TCLK(tm_t0);
 #define TM(x) x
 #else
 #define TM(x)
 #endif
-  int held = 0; /* stages tested but not yet released */
+  /* ---- stage loop: one state machine with a single drain() call site, so
+   * that the test loop does not carry the drain's registers ---- */
   const int hold_max = min(NS - 1, max(1, A.hold));
-  for (int it = 0;; it++) {
-    const int s = it % NS;
-    const uint32_t ph = (uint32_t)((it / NS) & 1);
-    if (held >= hold_max) { /* drain and give the held stages back */
-      TM(long long td0 = clock64();)
+  const float r2e = [&]() {
+    const float re = fmaf(thg, PREFILTER_REL, A.margin);
+    return re * re;
+  }();
+  int held = 0;   /* stages tested but not yet released */
+  int it = 0;     /* next stage to wait for */
+  int s = 0;      /* ring slot of the stage under test */
+  unsigned m = 0; /* accepted octets of that stage still to test */
+  bool done = false;
+  for (;;) {
+    if (m == 0) {
+      /* ---- next stage ---- */
+      s = it % NS;
+      const uint32_t ph = (uint32_t)((it / NS) & 1);
+      TM(TCLK(tm_a);)
+      mbar_wait(sFull + s, ph);
+      TM(TCLK(tm_b); tm_wait += tm_b - tm_a; tm_nwait++; if (it == 0) tm_first = tm_b - tm_t0;)
+      const char *const st = smem + s * SM::kStageBytes;
+      const int32_t *const meta = (const int32_t *)(st + SM::kStageMeta);
+      if (meta[0] == 0) {
+        done = true;
+      } else {
+        const int noct = meta[1];
+        it++;
+        held++;
+        /* ---- cull: lane = octet ---- */
+        bool acc = false;
+        if (lane < noct) {
+          const float *const wb = sBox + warp * 8; /* the warp's target box and reach */
+          const float rmax = wb[6];
+          const float4 lo = ((const float4 *)(st + SM::kStageOB))[2 * lane];
+          const float4 hi = ((const float4 *)(st + SM::kStageOB))[2 * lane + 1];
+          const TileItem &ii = ((const TileItem *)(st + SM::kStageIT))[((const uint8_t *)(st + SM::kStageO2F))[lane]];
+          const float r = fmaf(FORCE ? fmaxf(rmax, ii.rsrc) : rmax, PREFILTER_REL, A.margin);
+          float d2;
+          {
+            const float a = lo.x - (wb[3] - ii.d[0]), b = (wb[0] - ii.d[0]) - hi.x;
+            const float gx = fmaxf(0.f, fmaxf(a, b));
+            d2 = gx * gx;
+          }
+          {
+            const float a = lo.y - (wb[4] - ii.d[1]), b = (wb[1] - ii.d[1]) - hi.y;
+            const float gy = fmaxf(0.f, fmaxf(a, b));
+            d2 = fmaf(gy, gy, d2);
+          }
+          {
+            const float a = lo.z - (wb[5] - ii.d[2]), b = (wb[2] - ii.d[2]) - hi.z;
+            const float gz = fmaxf(0.f, fmaxf(a, b));
+            d2 = fmaf(gz, gz, d2);
+          }
+          acc = d2 < r * r;
+        }
+        m = __ballot_sync(FULL_MASK, acc);
+        TM(TCLK(tm_a); tm_cull += tm_a - tm_b;)
+      }
+    }
+    if (m) {
+      /* ---- test the accepted octets (until done or a sub-list may overflow) ---- */
+      TM(TCLK(tm_a);)
+      const char *const st = smem + s * SM::kStageBytes;
+      const float4 *const F = (const float4 *)(st + SM::kStageF);
+      const uint8_t *const o2f = (const uint8_t *)(st + SM::kStageO2F);
+      const TileItem *const IT = (const TileItem *)(st + SM::kStageIT);
+      int cur = -1;
+      float tpx = 3.0e30f, tpy = 0.f, tpz = 0.f;
+      int nsub_ub = __reduce_max_sync(FULL_MASK, nsub);
+      bool skip = true;
+      while (m) {
+        const int o = __ffs(m) - 1;
+        const int fl = o2f[o];
+        if (fl != cur) {
+          cur = fl;
+          const TileItem &ii = IT[fl];
+          const bool part = tvalid && tdepth >= ii.min_depth && tdepth <= ii.max_depth;
+          tpx = part ? tfx - ii.d[0] : 3.0e30f;
+          tpy = tfy - ii.d[1];
+          tpz = tfz - ii.d[2];
+          skip = !__any_sync(FULL_MASK, part);
+        }
+        if (skip) {
+          m &= m - 1u;
+          continue;
+        }
+        if (nsub_ub > QCAP - 2) {
+          nsub_ub = __reduce_max_sync(FULL_MASK, nsub);
+          if (nsub_ub > QCAP - 2) break; /* drain first, then come back to this octet */
+        }
+        m &= m - 1u;
+        nsub_ub += 2;
+        const int sl = o * 8 + 2 * s4;
+        const float4 a = F[sl], c = F[sl + 1];
+        const int code = (fl << 11) | (s << 8) | sl;
+        ntests++;
+        {
+          const float dx = tpx - a.x, dy = tpy - a.y, dz = tpz - a.z;
+          const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          const bool ok = FORCE ? (r2 < fmaxf(r2e, a.w)) : (r2 < r2e);
+          if (ok) {
+            mylist[nsub * 32] = (uint16_t)code;
+            nsub++;
+          }
+        }
+        {
+          const float dx = tpx - c.x, dy = tpy - c.y, dz = tpz - c.z;
+          const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          const bool ok = FORCE ? (r2 < fmaxf(r2e, c.w)) : (r2 < r2e);
+          if (ok) {
+            mylist[nsub * 32] = (uint16_t)(code + 1);
+            nsub++;
+          }
+        }
+      }
+      TM(TCLK(tm_b); tm_test += tm_b - tm_a;)
+    }
+    if (m != 0 || held >= hold_max || done) {
+      TM(TCLK(tm_a);)
       drain();
-      TM(tm_drain += clock64() - td0; tm_ndrain++;)
-      if (lane == 0)
-        for (int k = 1; k <= held; k++) mbar_arrive(sEmpty + ((it - k) % NS));
-      held = 0;
-    }
-    TM(long long tw0 = clock64();)
-    mbar_wait(sFull + s, ph);
-    TM(long long tw1 = clock64(); tm_wait += tw1 - tw0; tm_nwait++; if (it == 0) tm_first = tw1 - tm_t0;)
-    const char *const st = smem + s * SM::kStageBytes;
-    const int32_t *const meta = (const int32_t *)(st + SM::kStageMeta);
-    const int nfr = meta[0];
-    if (nfr == 0) break;
-    const int noct = meta[1];
-    const float4 *const F = (const float4 *)(st + SM::kStageF);
-    const uint8_t *const o2f = (const uint8_t *)(st + SM::kStageO2F);
-    const TileItem *const IT = (const TileItem *)(st + SM::kStageIT);
-    held++;
-
-    /* ---- cull: lane = octet ---- */
-    bool acc = false;
-    if (lane < noct) {
-      const float4 lo = ((const float4 *)(st + SM::kStageOB))[2 * lane];
-      const float4 hi = ((const float4 *)(st + SM::kStageOB))[2 * lane + 1];
-      const TileItem &ii = IT[o2f[lane]];
-      const float r = fmaf(FORCE ? fmaxf(rmax, ii.rsrc) : rmax, PREFILTER_REL, A.margin);
-      float d2;
-      {
-        const float a = lo.x - (bhi[0] - ii.d[0]), b = (blo[0] - ii.d[0]) - hi.x;
-        const float gx = fmaxf(0.f, fmaxf(a, b));
-        d2 = gx * gx;
-      }
-      {
-        const float a = lo.y - (bhi[1] - ii.d[1]), b = (blo[1] - ii.d[1]) - hi.y;
-        const float gy = fmaxf(0.f, fmaxf(a, b));
-        d2 = fmaf(gy, gy, d2);
-      }
-      {
-        const float a = lo.z - (bhi[2] - ii.d[2]), b = (blo[2] - ii.d[2]) - hi.z;
-        const float gz = fmaxf(0.f, fmaxf(a, b));
-        d2 = fmaf(gz, gz, d2);
-      }
-      acc = d2 < r * r;
-    }
-    unsigned m = __ballot_sync(FULL_MASK, acc);
-
-    /* ---- test the accepted octets ---- */
-    int cur = -1;
-    float tpx = 3.0e30f, tpy = 0.f, tpz = 0.f, r2e = 0.f;
-    int nsub_ub = __reduce_max_sync(FULL_MASK, nsub);
-    bool skip = true;
-    while (m) {
-      const int o = __ffs(m) - 1;
-      m &= m - 1u;
-      const int fl = o2f[o];
-      if (fl != cur) {
-        cur = fl;
-        const TileItem &ii = IT[fl];
-        const bool part = tvalid && tdepth >= ii.min_depth && tdepth <= ii.max_depth;
-        tpx = part ? tfx - ii.d[0] : 3.0e30f;
-        tpy = tfy - ii.d[1];
-        tpz = tfz - ii.d[2];
-        const float re = fmaf(thg, PREFILTER_REL, A.margin);
-        r2e = re * re;
-        skip = !__any_sync(FULL_MASK, part);
-      }
-      if (skip) continue;
-      if (nsub_ub > TL_SUBCAP - 2) {
-        nsub_ub = __reduce_max_sync(FULL_MASK, nsub);
-        if (nsub_ub > TL_SUBCAP - 2) {
-          drain();
-          nsub_ub = 0;
-        }
-      }
-      nsub_ub += 2;
-      const int sl = o * 8 + 2 * s4;
-      const float4 a = F[sl], c = F[sl + 1];
-      const int code = (fl << 11) | (s << 8) | sl;
-      ntests++;
-      {
-        const float dx = tpx - a.x, dy = tpy - a.y, dz = tpz - a.z;
-        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        const bool ok = FORCE ? (r2 < fmaxf(r2e, a.w)) : (r2 < r2e);
-        if (ok) {
-          mylist[nsub * 32] = (uint16_t)code;
-          nsub++;
-        }
-      }
-      {
-        const float dx = tpx - c.x, dy = tpy - c.y, dz = tpz - c.z;
-        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        const bool ok = FORCE ? (r2 < fmaxf(r2e, c.w)) : (r2 < r2e);
-        if (ok) {
-          mylist[nsub * 32] = (uint16_t)(code + 1);
-          nsub++;
-        }
+      TM(TCLK(tm_b); tm_drain += tm_b - tm_a; tm_ndrain++;)
+      if (m == 0 && !done) { /* every held stage is fully tested and drained: give them back */
+        if (lane == 0)
+          for (int k = 1; k <= held; k++) mbar_arrive(sEmpty + ((it - k) % NS));
+        held = 0;
       }
     }
+    if (done) break;
   }
-  TM(long long td0 = clock64();)
-  drain();
-  TM(tm_drain += clock64() - td0; tm_ndrain++;
-     if (lane == 0 && warp == 0 && (blockIdx.x % 2048) == 7)
-       printf("TM cta %d life %lld first %lld wait %lld (%d) drain %lld (%d) tests %d hits %d\n", (int)blockIdx.x,
-              clock64() - tm_t0, tm_first, tm_wait, tm_nwait, tm_drain, tm_ndrain, ntests, nhit);)
+  TM(if (lane == 0 && warp == 0 && (blockIdx.x % 2048) == 7)
+       printf("TM cta %d life %lld first %lld wait %lld (%d) cull %lld test %lld drain %lld (%d) tests %d hits %d\n",
+              (int)blockIdx.x, tm_b - tm_t0, tm_first, tm_wait, tm_nwait, tm_cull, tm_test, tm_drain, tm_ndrain,
+              ntests, nhit);)
 
   /* ---- combine the 4 partial sums of each target and flush ---- */
   int nh = nhit;

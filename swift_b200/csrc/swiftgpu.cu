@@ -1495,7 +1495,7 @@ static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
     static int hold = -1;
     if (hold < 0) {
       const char *e = getenv("SWIFTGPU_HOLD");
-      hold = e ? atoi(e) : 8;
+      hold = e ? atoi(e) : 2; /* 2 of the 3-4 ring stages held, the rest in flight */
     }
     A.hold = hold;
   }
@@ -1549,8 +1549,8 @@ template <int LOOP, int SCHEME>
 static cudaError_t launch_tile(H *h, const LoopArgs &A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  constexpr int NS = FORCE ? (SCHEME == SCH_SPHENIX ? 3 : 4) : (LOOP == LOOP_GRADIENT ? 3 : 4);
-  constexpr int bytes = TileSmem<NP, NS>::kBytes;
+  constexpr int NS = FORCE ? (SCHEME == SCH_SPHENIX ? 3 : 4) : (LOOP == LOOP_GRADIENT ? 3 : TL_DENS_NS);
+  constexpr int bytes = TileSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1)>::kBytes;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_tile<LOOP, SCHEME, NS>,
