@@ -74,20 +74,17 @@ __device__ __forceinline__ void mbar_arrive_tx(uint64_t *b, uint32_t bytes) {
 }
 __device__ __forceinline__ bool mbar_try(uint64_t *b, uint32_t parity) {
   uint32_t ok;
+  /* the last operand lets the hardware keep the warp suspended (no issue slots) for up to ~2 us */
   asm volatile(
-      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
       : "=r"(ok)
-      : "r"(smem_u32(b)), "r"(parity)
+      : "r"(smem_u32(b)), "r"(parity), "r"(2000u)
       : "memory");
   return ok != 0;
 }
 /* Bounded wait: a protocol error traps instead of hanging the GPU. */
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
-  if (mbar_try(b, parity)) return;
-  unsigned ns = 32;
   for (unsigned spins = 0; !mbar_try(b, parity); spins++) {
-    __nanosleep(ns);
-    if (ns < 256) ns <<= 1;
     if (spins > (1u << 22)) __trap();
   }
 }
@@ -359,6 +356,17 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : TL_DENS_
       b[6] = rmax;
     }
   }
+  /* producer: the global loads of the first 32 items overlap the consumers' prologue */
+  Item preI;
+  DevCell preC;
+  int preB = 0;
+  memset(&preI, 0, sizeof(preI));
+  memset(&preC, 0, sizeof(preC));
+  if (!consumer && lane < G.item_count) {
+    preI = A.items[G.item_first + lane];
+    preC = A.cells[preI.scell];
+    preB = A.cell_box_first[preI.scell];
+  }
   __syncthreads(); /* barriers initialised, boxes visible: the only CTA-wide barrier */
 
   /* ===================================================================== */
@@ -407,8 +415,10 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : TL_DENS_
           wcount = 0;
           if (win_base + lane < G.item_count) {
             const int item = G.item_first + win_base + lane;
-            const Item I = A.items[item];
-            const DevCell sc = A.cells[I.scell];
+            const bool pre = (win_base == 0);
+            const Item I = pre ? preI : A.items[item];
+            const DevCell sc = pre ? preC : A.cells[I.scell];
+            const int bfirst = pre ? preB : A.cell_box_first[I.scell];
             wcount = sc.count;
             const int mode = I.mode;
             const double shx = I.shift[0] * A.dim[0], shy = I.shift[1] * A.dim[1],
@@ -467,7 +477,7 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : TL_DENS_
             ti_.ot[0] = otx; ti_.ot[1] = oty; ti_.ot[2] = otz;
             ti_.fs[0] = fsx; ti_.fs[1] = fsy; ti_.fs[2] = fsz;
             sWin[lane] = ti_;
-            sWinAux[lane] = make_int2(sc.first, A.cell_box_first[I.scell]);
+            sWinAux[lane] = make_int2(sc.first, bfirst);
             /* item-level cull: source cell box against the CTA's target box */
             const float r = fmaf(fmaxf(crmax, ti_.rsrc), PREFILTER_REL, A.margin) + sc.dx_max_part;
             const float c0[3] = {(float)sc.loc[0], (float)sc.loc[1], (float)sc.loc[2]};
