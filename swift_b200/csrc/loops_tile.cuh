@@ -42,9 +42,8 @@
 
 namespace swiftgpu {
 
-#define TL_CWARPS 8                       /* consumer warps */
-#define TL_THREADS (32 * (TL_CWARPS + 1)) /* + producer warp */
-#define TL_TARGETS 64
+#define TL_CWARPS 8 /* consumer warps of the standard CTA (template CW: 8, or 4 for sparse target sets) */
+#define TL_TARGETS 64 /* targets of a task chunk (host task list); a CW-warp CTA takes 8 * CW of them */
 #define TL_SLOTS 256 /* source slots per stage */
 #define TL_OCT (TL_SLOTS / 8)
 #define TL_FRAGS 8   /* fragments per stage */
@@ -110,7 +109,7 @@ struct __align__(8) TileItem {
 };
 static_assert(sizeof(TileItem) == 88, "TileItem");
 
-template <int NP, int NS, int QCAP>
+template <int NP, int NS, int QCAP, int CW>
 struct TileSmem {
   static constexpr int kStageF = 0;
   static constexpr int kStageP = kStageF + TL_SLOTS * 16;
@@ -121,9 +120,9 @@ struct TileSmem {
   static constexpr int kStageMeta = kStageO2F + TL_OCT;
   static constexpr int kStageBytes = ((kStageMeta + 16) + 127) & ~127;
   static constexpr int kList = NS * kStageBytes;
-  static constexpr int kBar = kList + QCAP * 32 * TL_CWARPS * 2;
+  static constexpr int kBar = kList + QCAP * 32 * CW * 2;
   static constexpr int kBox = kBar + 2 * NS * 8;
-  static constexpr int kWin = kBox + (TL_CWARPS + 1) * 32; /* producer: constants of 32 items */
+  static constexpr int kWin = kBox + (CW + 1) * 32; /* producer: constants of 32 items */
   static constexpr int kWinAux = kWin + 32 * (int)sizeof(TileItem);
   static constexpr int kTX = kWinAux + 32 * 8; /* target doubles: 3 columns of TL_TARGETS */
   static constexpr int kBytes = kTX + 3 * TL_TARGETS * 8;
@@ -241,12 +240,15 @@ __device__ __forceinline__ float sure_r2(float a, float E) {
   return b > 0.f ? b * b * 0.999998f : 0.f;
 }
 
-template <int LOOP, int SCHEME, int NS>
-__global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : TL_DENS_BLOCKS)) k_tile(const LoopArgs A) {
+template <int LOOP, int SCHEME, int NS, int CW>
+__global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE ? 2 : TL_DENS_BLOCKS) : 5))
+    k_tile(const LoopArgs A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
   constexpr int QCAP = FORCE ? TL_SUBCAP2 : TL_SUBCAP1;
-  typedef TileSmem<NP, NS, QCAP> SM;
+  typedef TileSmem<NP, NS, QCAP, CW> SM;
+  constexpr int CTA_TGT = 8 * CW;          /* targets of this CTA */
+  constexpr int SUBS = TL_CWARPS / CW;     /* CTAs per task chunk */
   extern __shared__ __align__(128) char smem_tl[];
   char *const smem = smem_tl;
   uint16_t *const sList = (uint16_t *)(smem + SM::kList);
@@ -259,14 +261,16 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : TL_DENS_
   const int warp = tid >> 5;
   const int t8 = lane & 7;
   const int s4 = lane >> 3;
-  const int task = blockIdx.x;
+  const int task = blockIdx.x / SUBS;
+  const int sub = blockIdx.x % SUBS;
 
   const int g = A.task_group[task];
   const int chunk = A.task_chunk[task];
   const int nt = A.tgt_count[g];
-  if (chunk * TL_TARGETS >= nt) return;
+  const int tgt0 = chunk * TL_TARGETS + sub * CTA_TGT; /* first target slot of this CTA */
+  if (tgt0 >= nt) return;
   const Group G = A.groups[g];
-  const int nt_here = min(TL_TARGETS, nt - chunk * TL_TARGETS);
+  const int nt_here = min(CTA_TGT, nt - tgt0);
   const int nwarps_used = (nt_here + 7) >> 3; /* consumer warps that own targets */
 
   if (tid == 0) {
@@ -279,8 +283,8 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : TL_DENS_
   }
 
   /* ---- my target (4 lanes share one); the producer warp has none ---- */
-  const bool consumer = warp < TL_CWARPS;
-  const int slot_t = chunk * TL_TARGETS + warp * 8 + t8;
+  const bool consumer = warp < CW;
+  const int slot_t = tgt0 + warp * 8 + t8;
   const bool tvalid = consumer && slot_t < nt;
   const int ti = tvalid ? A.tgt_list[A.tgt_first[g] + slot_t] : -1;
   double tx = 0., ty = 0., tz = 0.;
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(TL_THREADS, (LOOP == LOOP_FORCE ? 2 : TL_DENS_
     clo[0] = clo[1] = clo[2] = 3.0e30f;
     chi[0] = chi[1] = chi[2] = -3.0e30f;
 #pragma unroll
-    for (int w = 0; w < TL_CWARPS; w++) {
+    for (int w = 0; w < CW; w++) {
       const float *b = sBox + w * 8;
 #pragma unroll
       for (int k = 0; k < 3; k++) {

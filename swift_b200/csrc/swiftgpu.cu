@@ -503,16 +503,37 @@ __global__ void __launch_bounds__(128)
 /* ======================================================================== */
 __global__ void k_build_targets(const Group *groups, int ngroups, const DevCell *cells,
                                 const int8_t *time_bin, int max_active_bin, const int32_t *tgt_first,
-                                int32_t *tgt_count, int32_t *tgt_list) {
+                                int32_t *tgt_count, int32_t *tgt_list, const Item *items,
+                                const int8_t *depth_h) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (g >= ngroups) return;
-  const DevCell c = cells[groups[g].tcell];
+  const Group G = groups[g];
+  const DevCell c = cells[G.tcell];
+  /* A particle takes part in an item only if its depth_h lies in the item's
+   * range (limit_min_h / limit_max_h of the reference's recursion): targets
+   * outside the union of the group's ranges have nothing to do here. In a
+   * multi-level tree most particles of a non-leaf target cell are such. */
+  int lo = 127, hi = 0;
+  for (int k = lane; k < G.item_count; k += 32) {
+    const Item I = items[G.item_first + k];
+    lo = min(lo, (int)I.min_depth);
+    hi = max(hi, (int)I.max_depth);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+    hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+  }
   int32_t *out = tgt_list + tgt_first[g];
   int nout = 0;
   for (int base = 0; base < c.count; base += 32) {
     const int k = base + lane;
-    const bool act = (k < c.count) && (time_bin[c.first + k] <= max_active_bin);
+    bool act = (k < c.count) && (time_bin[c.first + k] <= max_active_bin);
+    if (act) {
+      const int d = depth_h[c.first + k];
+      act = d >= lo && d <= hi;
+    }
     const unsigned m = __ballot_sync(FULL_MASK, act);
     if (act) out[nout + __popc(m & ((1u << lane) - 1u))] = c.first + k;
     nout += __popc(m);
@@ -1514,7 +1535,7 @@ static int build_targets(H *h, DevList &D) {
   if (D.ngroups == 0) return 0;
   k_build_targets<<<(D.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(
       D.groups, D.ngroups, h->d_cells, h->time_bin, h->step.max_active_bin, D.tgt_first, D.tgt_count,
-      D.tgt_list);
+      D.tgt_list, D.items, h->depth_h);
   h->stats.n_launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1545,21 +1566,28 @@ static int loop_kind() {
   return v;
 }
 static bool use_cta_loops() { return loop_kind() >= 1; }
-template <int LOOP, int SCHEME>
-static cudaError_t launch_tile(H *h, const LoopArgs &A) {
+template <int LOOP, int SCHEME, int CW>
+static cudaError_t launch_tile_cw(H *h, const LoopArgs &A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  constexpr int NS = FORCE ? (SCHEME == SCH_SPHENIX ? 3 : 4) : (LOOP == LOOP_GRADIENT ? 3 : TL_DENS_NS);
-  constexpr int bytes = TileSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1)>::kBytes;
+  /* ring stages: as many as keep 3 (type-1) / 2 (force) standard CTAs, or 5 small CTAs, on an SM */
+  constexpr int NS = CW == 8 ? (FORCE ? (SCHEME == SCH_SPHENIX ? 3 : 4) : (LOOP == LOOP_GRADIENT ? 3 : TL_DENS_NS)) : 2;
+  constexpr int bytes = TileSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1), CW>::kBytes;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_tile<LOOP, SCHEME, NS>,
+    cudaError_t e = cudaFuncSetAttribute(k_tile<LOOP, SCHEME, NS, CW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k_tile<LOOP, SCHEME, NS><<<A.ntasks, TL_THREADS, bytes, h->stream>>>(A);
+  k_tile<LOOP, SCHEME, NS, CW><<<A.ntasks * (TL_CWARPS / CW), 32 * (CW + 1), bytes, h->stream>>>(A);
   return cudaGetLastError();
+}
+/* sparse: few targets per group (late ghost iterations): 4-consumer-warp CTAs, 5 per SM */
+template <int LOOP, int SCHEME>
+static cudaError_t launch_tile(H *h, const LoopArgs &A, bool sparse = false) {
+  if (sparse && LOOP == LOOP_DENSITY) return launch_tile_cw<LOOP_DENSITY, 0, 4>(h, A);
+  return launch_tile_cw<LOOP, SCHEME, 8>(h, A);
 }
 template <int LOOP, bool SUBSET, int SCHEME>
 static cudaError_t launch_cta(H *h, const LoopArgs &A) {
@@ -1577,8 +1605,8 @@ static cudaError_t launch_cta(H *h, const LoopArgs &A) {
   return cudaGetLastError();
 }
 template <int LOOP, bool SUBSET>
-static cudaError_t launch_loop1(H *h, const LoopArgs &A) {
-  if (loop_kind() == 2) return launch_tile<LOOP, 0>(h, A);
+static cudaError_t launch_loop1(H *h, const LoopArgs &A, bool sparse = false) {
+  if (loop_kind() == 2) return launch_tile<LOOP, 0>(h, A, sparse);
   if (use_cta_loops()) return launch_cta<LOOP, SUBSET, 0>(h, A);
   k_loop1<LOOP, SUBSET><<<A.ntasks, 32, Tile1<LOOP, SUBSET>::kBytes, h->stream>>>(A);
   return cudaGetLastError();
@@ -1682,7 +1710,14 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
        * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
       CK(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long), h->stream));
       LoopArgs A = loop_args(h, D, h->nd, 4);
-      CK((launch_loop1<LOOP_DENSITY, true>(h, A)));
+      /* few unconverged particles per leaf: smaller CTAs, more of them per SM */
+      static int sparse_thr = -1;
+      if (sparse_thr < 0) {
+        const char *e = getenv("SWIFTGPU_SPARSE");
+        sparse_thr = e ? atoi(e) : 28;
+      }
+      const bool sparse = redo < (int64_t)sparse_thr * D.ngroups;
+      CK((launch_loop1<LOOP_DENSITY, true>(h, A, sparse)));
       h->stats.n_launches++;
       int64_t nn = 0;
       if (read_counter(h, 4, &nn)) return 1;
@@ -1706,6 +1741,7 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   if (phase_begin(h)) return 1;
   CK(cudaMemsetAsync(h->d_counters + 1, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
+  if (build_targets(h, h->L_density)) return 1; /* depth_h changed in the ghost */
   if (loop_kind() == 2) {
     k_prep_gq<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->fq1, h->fq2, h->fq3, h->n, h->gq);
     h->stats.n_launches++;
