@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call: GPU parity tests, bench line, ncu launch list and one
-# ncu --set full capture of the neighbour-loop kernels. Outputs in gpurun_out/.
+# ncu --set full capture of the neighbour-loop kernels (density, 2 ghost re-runs, force). Outputs in gpurun_out/.
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_round.sh <tag> [workload]'
 TAG=${1:-r01}
 WL=${2:-sedov128}
@@ -14,7 +14,7 @@ echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/${TAG}_launches.csv python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline \
   > gpurun_out/${TAG}_ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_cta -s 3 -c 3 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile -s 4 -c 4 \
   -f -o gpurun_out/${TAG}_full python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline \
   > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out
