@@ -108,6 +108,7 @@ struct LoopArgs {
   float keyE;   /* r-margin below which the sorted-axis conditions are implied */
   float margin; /* absolute widening of the float prefilter */
   int hold;     /* stages a consumer warp holds before it drains (<= NS - 1) */
+  unsigned int *task_counter; /* persistent CTAs draw their tasks from here (zeroed per launch) */
   /* outputs */
   float4 *dA;      /* (rho, rho_dh, wcount, wcount_dh) */
   float4 *dB;      /* (div_v, rot_v) */

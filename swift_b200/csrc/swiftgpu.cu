@@ -1512,6 +1512,7 @@ static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
   A.xf = h->xf; A.xs0 = h->xs; A.xs1 = h->xs + (h->n + 4); A.xs2 = h->xs + 2 * (h->n + 4); A.gq = h->gq; A.boxes = h->boxes; A.cell_box_first = h->d_box_first;
   A.keyE = tile_keyE(h);
   A.margin = tile_margin(h);
+  A.task_counter = (unsigned int *)(h->d_counters + 14);
   {
     static int hold = -1;
     if (hold < 0) {
@@ -1580,7 +1581,22 @@ static cudaError_t launch_tile_cw(H *h, const LoopArgs &A) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k_tile<LOOP, SCHEME, NS, CW><<<A.ntasks * (TL_CWARPS / CW), 32 * (CW + 1), bytes, h->stream>>>(A);
+  /* persistent CTAs: as many as are resident at once, tasks drawn from a counter */
+  static int resident = 0;
+  if (!resident) {
+    int per_sm = 0, sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile<LOOP, SCHEME, NS, CW>,
+                                                                  32 * (CW + 1), bytes);
+    if (e != cudaSuccess) return e;
+    resident = std::max(1, per_sm) * std::max(1, sms);
+  }
+  const long long ncta = (long long)A.ntasks * (TL_CWARPS / CW);
+  const int grid = (int)std::min<long long>(ncta, resident);
+  cudaError_t e = cudaMemsetAsync(A.task_counter, 0, sizeof(unsigned int), h->stream);
+  if (e != cudaSuccess) return e;
+  k_tile<LOOP, SCHEME, NS, CW><<<grid, 32 * (CW + 1), bytes, h->stream>>>(A);
   return cudaGetLastError();
 }
 /* sparse: few targets per group (late ghost iterations): 4-consumer-warp CTAs, 5 per SM */
