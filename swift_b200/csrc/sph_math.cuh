@@ -107,6 +107,27 @@ __device__ __forceinline__ void kernel_deval(float u, float &W, float &dW_dx) {
 
 /* ------------------------- interaction bodies ------------------------- */
 
+/* r = sqrt(r2) and 1/r without the out-of-line IEEE sqrt/divide subroutines
+ * nvcc emits for sqrtf() and '/': MUFU.RSQ + one Newton step (|error| < 1 ulp)
+ * and the correctly rounded reciprocal rcp.rn. Quotients a / b of the
+ * reference become a * rcp_rn(b) (<= 1 ulp apart, the same order as the FMA
+ * contractions of this path). r2 == 0 (coincident particles) gives r_inv = 0
+ * like the reference's `r ? 1/r : 0`. */
+__device__ __forceinline__ void sqrt_and_inverse(float r2, float &r, float &r_inv) {
+  const float y = rsqrtf(r2);
+  const float r0 = r2 * y;
+  const float e = fmaf(-r0, r0, r2);
+  const float rr = fmaf(0.5f * y, e, r0);
+  r = r2 > 0.f ? rr : 0.f;
+  r_inv = r2 > 0.f ? __frcp_rn(r) : 0.f;
+}
+__device__ __forceinline__ float rcp_rn(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float sqrt_newton(float x) {
+  float r, r_inv;
+  sqrt_and_inverse(x, r, r_inv);
+  return r;
+}
+
 struct DensityAcc {
   float rho, rho_dh, wcount, wcount_dh, div_v, rot[3];
   __device__ __forceinline__ void zero() {
@@ -121,8 +142,8 @@ __device__ __forceinline__ void iact_density(DensityAcc &a, float r2, float dx, 
                                              float viz, float mj, float vjx, float vjy,
                                              float vjz) {
   float wi, wi_dx;
-  const float r = sqrtf(r2);
-  const float r_inv = r ? 1.0f / r : 0.0f;
+  float r, r_inv;
+  sqrt_and_inverse(r2, r, r_inv);
   const float ui = r * hi_inv;
   kernel_deval(ui, wi, wi_dx);
   const float t = HYDRO_DIMENSION * wi + ui * wi_dx;
@@ -150,8 +171,8 @@ __device__ __forceinline__ void iact_gradient(GradientAcc &a, float r2, float dx
                                               float vjx, float vjy, float vjz, float uj,
                                               float rhoj, float csj, float alphaj,
                                               float a2_Hubble) {
-  const float r = sqrtf(r2);
-  const float r_inv = r ? 1.0f / r : 0.0f;
+  float r, r_inv;
+  sqrt_and_inverse(r2, r, r_inv);
   const float fac_mu = 1.f; /* pow_three_gamma_minus_five_over_two, gamma = 5/3 */
   const float dvdr = (vix - vjx) * dx + (viy - vjy) * dy + (viz - vjz) * dz;
   const float dvdr_Hubble = dvdr + a2_Hubble * r2;
@@ -160,10 +181,10 @@ __device__ __forceinline__ void iact_gradient(GradientAcc &a, float r2, float dx
   const float new_v_sig = csi + csj - CONST_VISCOSITY_BETA * mu_ij;
   a.v_sig = fmaxf(a.v_sig, new_v_sig);
   float wi, wi_dx;
-  const float ui = r / hi;
+  const float ui = r * rcp_rn(hi);
   kernel_deval(ui, wi, wi_dx);
   const float delta_u_factor = (ui_ - uj) * r_inv;
-  a.laplace_u += mj * delta_u_factor * wi_dx / rhoj;
+  a.laplace_u += mj * delta_u_factor * wi_dx * rcp_rn(rhoj);
   a.alpha_max = fmaxf(a.alpha_max, alphaj);
 }
 
@@ -186,17 +207,18 @@ template <int SCHEME>
 __device__ __forceinline__ void iact_force(ForceAcc &a, float r2, float dx, float dy, float dz,
                                            const ForceQ &pi, const ForceQ &pj, float a2_Hubble) {
   const float fac_mu = 1.f;
-  const float r = sqrtf(r2);
-  const float r_inv = r ? 1.0f / r : 0.0f;
+  float r, r_inv;
+  sqrt_and_inverse(r2, r, r_inv);
   const float mj = pj.m;
   const float rhoi = pi.rho, rhoj = pj.rho;
-  const float hi_inv = 1.0f / pi.h;
+  const float rhoj_inv = rcp_rn(rhoj);
+  const float hi_inv = rcp_rn(pi.h);
   const float hid_inv = hi_inv * hi_inv * hi_inv * hi_inv;
   const float xi = r * hi_inv;
   float wi, wi_dx;
   kernel_deval(xi, wi, wi_dx);
   const float wi_dr = hid_inv * wi_dx;
-  const float hj_inv = 1.0f / pj.h;
+  const float hj_inv = rcp_rn(pj.h);
   const float hjd_inv = hj_inv * hj_inv * hj_inv * hj_inv;
   const float xj = r * hj_inv;
   float wj, wj_dx;
@@ -210,12 +232,12 @@ __device__ __forceinline__ void iact_force(ForceAcc &a, float r2, float dx, floa
   const float balsara_i = pi.balsara, balsara_j = pj.balsara;
   if (SCHEME == SCH_MINIMAL) {
     const float mi = pi.m;
-    const float f_ij = 1.f - pi.f / mj;
-    const float f_ji = 1.f - pj.f / mi;
-    const float P_over_rho2_i = pi.P / (rhoi * rhoi) * f_ij;
-    const float P_over_rho2_j = pj.P / (rhoj * rhoj) * f_ji;
+    const float f_ij = 1.f - pi.f * rcp_rn(mj);
+    const float f_ji = 1.f - pj.f * rcp_rn(mi); /* target-only: hoisted out of the candidate loop */
+    const float P_over_rho2_i = pi.P * rcp_rn(rhoi * rhoi) * f_ij;
+    const float P_over_rho2_j = pj.P * (rhoj_inv * rhoj_inv) * f_ji;
     const float rho_ij = 0.5f * (rhoi + rhoj);
-    const float visc = -0.25f * v_sig * (balsara_i + balsara_j) * mu_ij / rho_ij;
+    const float visc = -0.25f * v_sig * (balsara_i + balsara_j) * mu_ij * rcp_rn(rho_ij);
     const float visc_acc_term = 0.5f * visc * (wi_dr * f_ij + wj_dr * f_ji) * r_inv;
     const float sph_acc_term = (P_over_rho2_i * wi_dr + P_over_rho2_j * wj_dr) * r_inv;
     const float acc = sph_acc_term + visc_acc_term;
@@ -225,30 +247,31 @@ __device__ __forceinline__ void iact_force(ForceAcc &a, float r2, float dx, floa
     const float sph_du_term_i = P_over_rho2_i * dvdr * r_inv * wi_dr;
     const float visc_du_term = 0.5f * visc_acc_term * dvdr_Hubble;
     a.u_dt += (sph_du_term_i + visc_du_term) * mj;
-    a.h_dt -= mj * dvdr * r_inv / rhoj * wi_dr * f_ij;
+    a.h_dt -= mj * dvdr * r_inv * rhoj_inv * wi_dr * f_ij;
     a.v_sig = fmaxf(a.v_sig, v_sig);
   } else if (SCHEME == SCH_GADGET2) {
     const float rho_ij = 0.5f * (rhoi + rhoj);
-    const float visc = -0.25f * v_sig * mu_ij * (balsara_i + balsara_j) / rho_ij;
+    const float visc = -0.25f * v_sig * mu_ij * (balsara_i + balsara_j) * rcp_rn(rho_ij);
     const float visc_term = 0.5f * visc * (wi_dr + wj_dr) * r_inv;
     const float sph_term = (pi.f * pi.P * wi_dr + pj.f * pj.P * wj_dr) * r_inv;
     const float acc = visc_term + sph_term;
     a.ax -= mj * acc * dx;
     a.ay -= mj * acc * dy;
     a.az -= mj * acc * dz;
-    a.h_dt -= mj * dvdr * r_inv / rhoj * wi_dr;
+    a.h_dt -= mj * dvdr * r_inv * rhoj_inv * wi_dr;
     a.v_sig = fmaxf(a.v_sig, v_sig);
     a.u_dt += mj * visc_term * dvdr_Hubble; /* entropy_dt */
   } else {
     const float mi = pi.m;
-    const float f_ij = 1.f - pi.f / mj;
-    const float f_ji = 1.f - pj.f / mi;
+    const float f_ij = 1.f - pi.f * rcp_rn(mj);
+    const float f_ji = 1.f - pj.f * rcp_rn(mi); /* target-only: hoisted out of the candidate loop */
     const float rho_ij = rhoi + rhoj;
+    const float rho_ij_inv = rcp_rn(rho_ij);
     const float alpha = pi.alpha_visc + pj.alpha_visc;
-    const float visc = -0.25f * alpha * v_sig * mu_ij * (balsara_i + balsara_j) / rho_ij;
+    const float visc = -0.25f * alpha * v_sig * mu_ij * (balsara_i + balsara_j) * rho_ij_inv;
     const float visc_acc_term = 0.5f * visc * (wi_dr * f_ij + wj_dr * f_ji) * r_inv;
-    const float P_over_rho2_i = pi.P / (rhoi * rhoi) * f_ij;
-    const float P_over_rho2_j = pj.P / (rhoj * rhoj) * f_ji;
+    const float P_over_rho2_i = pi.P * rcp_rn(rhoi * rhoi) * f_ij;
+    const float P_over_rho2_j = pj.P * (rhoj_inv * rhoj_inv) * f_ji;
     const float sph_acc_term = (P_over_rho2_i * wi_dr + P_over_rho2_j * wj_dr) * r_inv;
     const float acc = sph_acc_term + visc_acc_term;
     a.ax -= mj * acc * dx;
@@ -256,14 +279,14 @@ __device__ __forceinline__ void iact_force(ForceAcc &a, float r2, float dx, floa
     a.az -= mj * acc * dz;
     const float sph_du_term_i = P_over_rho2_i * dvdr * r_inv * wi_dr;
     const float visc_du_term = 0.5f * visc_acc_term * dvdr_Hubble;
-    const float alpha_diff = (pi.P * pi.alpha_diff + pj.P * pj.alpha_diff) / (pi.P + pj.P);
+    const float alpha_diff = (pi.P * pi.alpha_diff + pj.P * pj.alpha_diff) * rcp_rn(pi.P + pj.P);
     const float v_diff = alpha_diff * 0.5f *
-                         (sqrtf(2.f * fabsf(pi.P - pj.P) / rho_ij) +
+                         (sqrt_newton(2.f * fabsf(pi.P - pj.P) * rho_ij_inv) +
                           fabsf(fac_mu * r_inv * dvdr_Hubble));
     const float diff_du_term =
-        v_diff * (pi.u - pj.u) * (f_ij * wi_dr / rhoi + f_ji * wj_dr / rhoj);
+        v_diff * (pi.u - pj.u) * (f_ij * wi_dr * rcp_rn(rhoi) + f_ji * wj_dr * rhoj_inv);
     a.u_dt += (sph_du_term_i + visc_du_term + diff_du_term) * mj;
-    a.h_dt -= mj * dvdr * r_inv / rhoj * wi_dr;
+    a.h_dt -= mj * dvdr * r_inv * rhoj_inv * wi_dr;
   }
   if (pj.time_bin > 0) a.min_ngb = min(a.min_ngb, pj.time_bin);
 }
