@@ -4,6 +4,9 @@
  * One CTA = 8 consumer warps (64 TARGET particles of one target cell, 8 per
  * warp) + 1 producer warp. No __syncthreads() after the prologue.
  *
+ * The CTAs are persistent: each draws tasks (8 targets per consumer warp of
+ * one group) from a global counter and the ring runs across task boundaries.
+ *
  *   PRODUCER  walks the items of the target cell's group, culls source cells
  *             that are out of reach of the CTA's target box and cuts the rest
  *             into fragments. A ring STAGE holds up to 256 source slots / 8
@@ -594,7 +597,8 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
         }
       }
       const float r2 = r2_exact(dx, dy, dz);
-      const bool part = act && tdepth >= ii.min_depth && tdepth <= ii.max_depth && gi != ti;
+      /* the depth-range rule was applied when the candidate was listed (test loop) */
+      const bool part = act && gi != ti;
       const float4 *const P = (const float4 *)(st + SM::kStageP);
       if (!FORCE) {
         bool hit = part && (r2 < thg2);
