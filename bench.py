@@ -54,6 +54,8 @@ WORKLOADS = {
     "sedov128": ("gadget2", 128, "sedov"),
     "sphenix128": ("sphenix", 128, "jitter"),
     "sphenix256": ("sphenix", 256, "jitter"),
+    # multi-time-step: ~5 % of the particles active (clustered in space), the rest are neighbours only
+    "sphenix128a5": ("sphenix", 128, "active5"),
     "clustered128": ("sphenix", 128, "clustered"),
     "clustered256": ("sphenix", 256, "clustered"),
 }
@@ -79,6 +81,10 @@ def make_workload(name, world=1, rank=0):
         ic = host.sedov_box(L, sid, bricks=bricks)
     elif gen == "clustered":
         ic = host.clustered_box(L, sid)
+    elif gen == "active5":
+        if world > 1:
+            raise SystemExit(f"workload {name} has no multi-GPU generator")
+        ic = host.jittered_box(L, sid, jitter=0.2, seed=42, active_fraction=0.05)
     else:
         ic = host.jittered_box(L, sid, jitter=0.2, seed=42, bricks=bricks)
     tg = host.default_top_grid(L)
@@ -86,7 +92,23 @@ def make_workload(name, world=1, rank=0):
         tg = (int(os.environ["SWIFTGPU_TOPGRID"]),) * 3
     cdim = tuple(t * b for t, b in zip(tg, bricks))
     dim = tuple(float(b) for b in bricks)
-    c = util.make_case(scheme, ic, cdim, rank_grid=bricks, rank=rank, dim=dim, pack=(world == 1))
+    if gen == "active5":
+        # inactive particles carry the force-union members of "their last step": take them from an
+        # all-active step of the same box (run here on the GPU), then apply the time bins
+        from swift_b200.engine import SwiftGPU
+        c_all = util.make_case(scheme, dict(ic, time_bin=np.ones_like(ic["time_bin"])), cdim)
+        g0 = SwiftGPU(c_all.cfg)
+        g0.upload_cells(c_all.tree.cells, c_all.tree.top)
+        g0.upload_parts(c_all.parts)
+        g0.set_step(c_all.step)
+        g0.run_step(abi.PHASE_ALL)
+        parts_all = g0.download_parts().copy()
+        g0.close()
+        c = util.make_case(scheme, ic, cdim, max_active_bin=1)
+        c.parts = parts_all
+        host.field(c.parts, c.layout, "time_bin")[:] = ic["time_bin"][c.tree.perm]
+    else:
+        c = util.make_case(scheme, ic, cdim, rank_grid=bricks, rank=rank, dim=dim, pack=(world == 1))
     c.sub_tree = c.tree
     if world > 1:
         sub, _, sel, is_local = host.extract_rank(c.tree, None, c.layout, rank)
@@ -397,7 +419,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload + ("" if world == 1 else " x%d bricks %s (weak scaling: one brick per GPU)" % (world, "x".join(map(str, GRIDS[world])))),
                    "scheme": scheme, "particles": int(c.n_local) * world, "particles_per_gpu_incl_halo": int(n),
-                   "active_fraction": 1.0,
+                   "active_fraction": 0.05 if WORKLOADS[args.workload][2] == "active5" else 1.0,
                    "l2": "inputs larger than L2 (%.0f MB AoS + SoA state per step)" % (n * psize / 1e6),
                    "top_grid": list(host.default_top_grid(WORKLOADS[args.workload][1])),
                    "ghost_iterations": int(st.ghost_iterations)},

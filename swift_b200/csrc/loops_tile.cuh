@@ -246,7 +246,7 @@ __device__ __forceinline__ float sure_r2(float a, float E) {
 #define TM(x) /* timing hooks of the development build */
 
 template <int LOOP, int SCHEME, int NS, int CW>
-__global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE ? 2 : TL_DENS_BLOCKS) : 5))
+__global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE ? 2 : TL_DENS_BLOCKS) : (LOOP == LOOP_FORCE ? 3 : 5)))
     k_tile(const LoopArgs A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);

@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(128)
 __global__ void k_build_targets(const Group *groups, int ngroups, const DevCell *cells,
                                 const int8_t *time_bin, int max_active_bin, const int32_t *tgt_first,
                                 int32_t *tgt_count, int32_t *tgt_list, const Item *items,
-                                const int8_t *depth_h) {
+                                const int8_t *depth_h, unsigned long long *totals) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (g >= ngroups) return;
@@ -538,7 +538,13 @@ __global__ void k_build_targets(const Group *groups, int ngroups, const DevCell 
     if (act) out[nout + __popc(m & ((1u << lane) - 1u))] = c.first + k;
     nout += __popc(m);
   }
-  if (lane == 0) tgt_count[g] = nout;
+  if (lane == 0) {
+    tgt_count[g] = nout;
+    if (nout) { /* totals[0] targets, totals[1] non-empty 64-target tasks: the launch picks the CTA size */
+      atomicAdd(totals, (unsigned long long)nout);
+      atomicAdd(totals + 1, (unsigned long long)((nout + TASK_TARGETS - 1) / TASK_TARGETS));
+    }
+  }
 }
 
 /* ======================================================================== */
@@ -1532,13 +1538,30 @@ static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
   return A;
 }
 
-static int build_targets(H *h, DevList &D) {
+/* sparse_out: fewer than SWIFTGPU_SPARSE targets per non-empty task on average */
+static int sparse_threshold() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SWIFTGPU_SPARSE");
+    v = e ? atoi(e) : 28;
+  }
+  return v;
+}
+static int build_targets(H *h, DevList &D, bool *sparse_out = nullptr) {
+  if (sparse_out) *sparse_out = false;
   if (D.ngroups == 0) return 0;
+  CK(cudaMemsetAsync(h->d_counters + 12, 0, 2 * sizeof(unsigned long long), h->stream));
   k_build_targets<<<(D.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(
       D.groups, D.ngroups, h->d_cells, h->time_bin, h->step.max_active_bin, D.tgt_first, D.tgt_count,
-      D.tgt_list, D.items, h->depth_h);
+      D.tgt_list, D.items, h->depth_h, h->d_counters + 12);
   h->stats.n_launches++;
   CK(cudaGetLastError());
+  if (sparse_out && loop_kind() == 2) {
+    unsigned long long t[2] = {0, 0};
+    CK(cudaMemcpyAsync(t, h->d_counters + 12, sizeof(t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *sparse_out = t[1] > 0 && t[0] < (unsigned long long)sparse_threshold() * t[1];
+  }
   return 0;
 }
 
@@ -1602,7 +1625,7 @@ static cudaError_t launch_tile_cw(H *h, const LoopArgs &A) {
 /* sparse: few targets per group (late ghost iterations): 4-consumer-warp CTAs, 5 per SM */
 template <int LOOP, int SCHEME>
 static cudaError_t launch_tile(H *h, const LoopArgs &A, bool sparse = false) {
-  if (sparse && LOOP == LOOP_DENSITY) return launch_tile_cw<LOOP_DENSITY, 0, 4>(h, A);
+  if (sparse) return launch_tile_cw<LOOP, SCHEME, 4>(h, A);
   return launch_tile_cw<LOOP, SCHEME, 8>(h, A);
 }
 template <int LOOP, bool SUBSET, int SCHEME>
@@ -1628,8 +1651,8 @@ static cudaError_t launch_loop1(H *h, const LoopArgs &A, bool sparse = false) {
   return cudaGetLastError();
 }
 template <int SCHEME>
-static cudaError_t launch_loop2(H *h, const LoopArgs &A) {
-  if (loop_kind() == 2) return launch_tile<LOOP_FORCE, SCHEME>(h, A);
+static cudaError_t launch_loop2(H *h, const LoopArgs &A, bool sparse = false) {
+  if (loop_kind() == 2) return launch_tile<LOOP_FORCE, SCHEME>(h, A, sparse);
   if (use_cta_loops()) return launch_cta<LOOP_FORCE, false, SCHEME>(h, A);
   k_loop2<SCHEME><<<A.ntasks, 32, Tile2<SCHEME>::kBytes, h->stream>>>(A);
   return cudaGetLastError();
@@ -1649,10 +1672,11 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   h->stats.n_launches++;
   CK(cudaMemsetAsync(h->d_counters + 0, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 8, 0, sizeof(unsigned long long), h->stream));
-  if (build_targets(h, h->L_density)) return 1;
+  bool sparse = false;
+  if (build_targets(h, h->L_density, &sparse)) return 1;
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->nd, 0);
-    CK((launch_loop1<LOOP_DENSITY, false>(h, A)));
+    CK((launch_loop1<LOOP_DENSITY, false>(h, A, sparse)));
     h->stats.n_launches++;
   }
   h->phases_done |= SWIFTGPU_PHASE_DENSITY;
@@ -1727,12 +1751,7 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
       CK(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long), h->stream));
       LoopArgs A = loop_args(h, D, h->nd, 4);
       /* few unconverged particles per leaf: smaller CTAs, more of them per SM */
-      static int sparse_thr = -1;
-      if (sparse_thr < 0) {
-        const char *e = getenv("SWIFTGPU_SPARSE");
-        sparse_thr = e ? atoi(e) : 28;
-      }
-      const bool sparse = redo < (int64_t)sparse_thr * D.ngroups;
+      const bool sparse = redo < (int64_t)sparse_threshold() * D.ngroups;
       CK((launch_loop1<LOOP_DENSITY, true>(h, A, sparse)));
       h->stats.n_launches++;
       int64_t nn = 0;
@@ -1757,14 +1776,15 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   if (phase_begin(h)) return 1;
   CK(cudaMemsetAsync(h->d_counters + 1, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
-  if (build_targets(h, h->L_density)) return 1; /* depth_h changed in the ghost */
+  bool sparse = false;
+  if (build_targets(h, h->L_density, &sparse)) return 1; /* depth_h changed in the ghost */
   if (loop_kind() == 2) {
     k_prep_gq<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->fq1, h->fq2, h->fq3, h->n, h->gq);
     h->stats.n_launches++;
   }
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->ng, 1);
-    CK((launch_loop1<LOOP_GRADIENT, false>(h, A)));
+    CK((launch_loop1<LOOP_GRADIENT, false>(h, A, sparse)));
     h->stats.n_launches++;
   }
   h->phases_done |= SWIFTGPU_PHASE_GRADIENT;
@@ -1849,7 +1869,8 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   }
   CK(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(unsigned long long), h->stream));
-  if (build_targets(h, h->L_force)) return 1;
+  bool sparse = false;
+  if (build_targets(h, h->L_force, &sparse)) return 1;
   if (loop_kind() == 2) { /* h changed in the ghost (and the rho halo): source reach of the prefilter */
     k_refresh_reach<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->hh, h->n, tile_margin(h),
                                                                           h->xf);
@@ -1858,9 +1879,9 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   if (h->L_force.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_force, h->nf, 2);
     switch (h->cfg.scheme) {
-      case SCH_MINIMAL: CK(launch_loop2<SCH_MINIMAL>(h, A)); break;
-      case SCH_GADGET2: CK(launch_loop2<SCH_GADGET2>(h, A)); break;
-      default: CK(launch_loop2<SCH_SPHENIX>(h, A)); break;
+      case SCH_MINIMAL: CK(launch_loop2<SCH_MINIMAL>(h, A, sparse)); break;
+      case SCH_GADGET2: CK(launch_loop2<SCH_GADGET2>(h, A, sparse)); break;
+      default: CK(launch_loop2<SCH_SPHENIX>(h, A, sparse)); break;
     }
     h->stats.n_launches++;
   }
