@@ -41,7 +41,8 @@ for l in dis.splitlines():
 n = len(rows) - 1
 def norm(s): return re.sub(r"\s+", " ", s.strip().rstrip(";").strip())
 best = None
-for f, mp in funcs.items():
+kbase = re.sub(r'^void\s+', '', name).split('<')[0].split('::')[-1]
+for f, mp in sorted(funcs.items(), key=lambda kv: (kbase not in kv[0])):
     if len(mp) != n: continue
     ok = all(norm(mp.get(16 * k, (None, ""))[1]) == norm(rows[1 + k][1]) for k in range(0, min(n, 40)))
     if ok: best = f; break

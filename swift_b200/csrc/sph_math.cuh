@@ -109,7 +109,7 @@ __device__ __forceinline__ void kernel_deval(float u, float &W, float &dW_dx) {
 
 /* r = sqrt(r2) and 1/r without the out-of-line IEEE sqrt/divide subroutines
  * nvcc emits for sqrtf() and '/': MUFU.RSQ + one Newton step (|error| < 1 ulp)
- * and the correctly rounded reciprocal rcp.rn. Quotients a / b of the
+ * and MUFU.RCP + one Newton step. Quotients a / b of the
  * reference become a * rcp_rn(b) (<= 1 ulp apart, the same order as the FMA
  * contractions of this path). r2 == 0 (coincident particles) gives r_inv = 0
  * like the reference's `r ? 1/r : 0`. */
@@ -119,9 +119,16 @@ __device__ __forceinline__ void sqrt_and_inverse(float r2, float &r, float &r_in
   const float e = fmaf(-r0, r0, r2);
   const float rr = fmaf(0.5f * y, e, r0);
   r = r2 > 0.f ? rr : 0.f;
-  r_inv = r2 > 0.f ? __frcp_rn(r) : 0.f;
+  /* 1/r from the refined root: y is 1/sqrt(r2) to 2 ulp, one Newton step on it */
+  const float yi = fmaf(y, fmaf(-rr, y, 1.f), y);
+  r_inv = r2 > 0.f ? yi : 0.f;
 }
-__device__ __forceinline__ float rcp_rn(float x) { return __frcp_rn(x); }
+/* 1/x: MUFU.RCP + one Newton step (|error| < 1 ulp; __frcp_rn costs ~10 instructions) */
+__device__ __forceinline__ float rcp_rn(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
 __device__ __forceinline__ float sqrt_newton(float x) {
   float r, r_inv;
   sqrt_and_inverse(x, r, r_inv);
