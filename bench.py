@@ -397,13 +397,13 @@ def main():
     achieved_gbs = kbytes / (kms * 1e-3) / 1e9
     kname = {"tile": "k_tile", "cta": "k_cta", "warp": "k_loop"}.get(os.environ.get("SWIFTGPU_LOOPS", "tile"), "k_tile")
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel, from the committed
-    # ncu --set full capture of this command (profiles/r01b_summary.md); null for workloads not captured
-    TRAFFIC = {("sedov128", "k_tile", "force"): 366.776064e6 + 61.030144e6,
-               ("sedov128", "k_tile", "density"): 301.902592e6 + 64.544256e6}
+    # ncu --set full capture of this command (profiles/r01c_summary.md); null for workloads not captured
+    TRAFFIC = {("sedov128", "k_tile", "force"): 366.891264e6 + 60.503808e6,
+               ("sedov128", "k_tile", "density"): 301.667328e6 + 64.605440e6}
     traffic = TRAFFIC.get((args.workload, kname, dom)) if world == 1 else None
     roofline = {"bound": "fp32", "kernel": (kname + "<FORCE,%s>" % scheme) if dom == "force" else (kname + "<DENSITY>"),
                 "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
-                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01b_summary.md)",
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01c_summary.md)",
                 "algorithmic_bytes": kbytes,
                 "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peak_src})",
                 "ms_per_launch": kms, "flops_per_interaction": fl_force if dom == "force" else FLOPS["density"],
