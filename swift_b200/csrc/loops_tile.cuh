@@ -50,6 +50,9 @@ namespace swiftgpu {
 #define TL_SLOTS 256 /* source slots per stage */
 #define TL_OCT (TL_SLOTS / 8)
 #define TL_FRAGS 8   /* fragments per stage */
+#ifndef TL_WAIT_HINT_NS
+#define TL_WAIT_HINT_NS 2000u /* try_wait suspend-time hint */
+#endif
 #define TL_SUBCAP1 10 /* sub-list capacity per lane, type-1 loops (3 CTAs/SM) */
 #define TL_SUBCAP2 16 /* ... force loop (2 CTAs/SM) */
 #ifndef TL_DENS_BLOCKS
@@ -57,6 +60,10 @@ namespace swiftgpu {
 #endif
 #ifndef TL_DENS_NS
 #define TL_DENS_NS 4
+#endif
+#ifndef TL_SPARSE_NS
+#define TL_SPARSE_NS 2 /* ring stages of the 4-warp CTAs */
+#define TL_SPARSE_BLOCKS 5
 #endif
 #define TL_DCOL (TL_SLOTS + 2 * TL_FRAGS) /* double column: 2 spare entries per fragment (alignment) */
 
@@ -80,7 +87,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t *b, uint32_t parity) {
   asm volatile(
       "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
       : "=r"(ok)
-      : "r"(smem_u32(b)), "r"(parity), "r"(2000u)
+      : "r"(smem_u32(b)), "r"(parity), "r"(TL_WAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -246,7 +253,7 @@ __device__ __forceinline__ float sure_r2(float a, float E) {
 #define TM(x) /* timing hooks of the development build */
 
 template <int LOOP, int SCHEME, int NS, int CW>
-__global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE ? 2 : TL_DENS_BLOCKS) : (LOOP == LOOP_FORCE ? 3 : 5)))
+__global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE ? 2 : TL_DENS_BLOCKS) : (LOOP == LOOP_FORCE ? 3 : TL_SPARSE_BLOCKS)))
     k_tile(const LoopArgs A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
