@@ -241,6 +241,14 @@ int swiftgpu_download_parts_device(swiftgpu_t *h, void *d_parts_aos,
                                    int64_t nparts);
 /* Per-cell h_max / h_max_active after the ghost (runner_ghost.c:1621-1632). */
 int swiftgpu_download_cells(swiftgpu_t *h, swiftgpu_cell *cells, int32_t ncells);
+/* hydro_compute_timestep (hydro/Minimal/hydro.h:440, Gadget2/hydro.h:444,
+ * SPHENIX/hydro.h:475): the CFL time-step 2 kernel_gamma CFL a h /
+ * (a_factor_sound_speed v_sig) of every ACTIVE particle, evaluated in the
+ * epilogue of swiftgpu_run_end_force from the h and signal velocity the step
+ * just produced (the host no longer needs v_sig back to get
+ * dt). Inactive particles get -1. dt_cfl holds nparts floats in the host's
+ * particle order. */
+int swiftgpu_download_timestep(swiftgpu_t *h, float *dt_cfl, int64_t nparts);
 /* Per-particle directed interaction counts of the last density / gradient /
  * force loops (the reference's N_density/N_gradient/N_force debugging counters,
  * hydro/SPHENIX/hydro_iact.h:121-126, minus the self term). Any pointer may be

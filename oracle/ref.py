@@ -37,6 +37,7 @@ def load(variant):
         lib.swiftref_get_cells.argtypes = [VP, VP]
         lib.swiftref_get_counts.argtypes = [VP, VP, VP, VP]
         lib.swiftref_get_sort.argtypes = [VP, C.c_int, C.c_int, VP, VP]
+        lib.swiftref_get_timesteps.argtypes = [VP, VP]
         lib.swiftref_layout.argtypes = [C.POINTER(abi.PartLayout)]
         _libs[variant] = lib
     return _libs[variant]
@@ -88,6 +89,12 @@ class Reference:
         if self.lib.swiftref_get_counts(self.h, nd.ctypes.data, ng.ctypes.data, nf.ctypes.data) != 0:
             return None
         return nd, ng, nf
+
+    def timesteps(self):
+        """hydro_compute_timestep of every particle (the reference's own function)."""
+        dt = np.zeros(self.nparts, np.float32)
+        self.lib.swiftref_get_timesteps(self.h, dt.ctypes.data)
+        return dt
 
     def sort(self, cell, sid):
         n = int(self._cells["count"][cell])

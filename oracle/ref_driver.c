@@ -661,6 +661,14 @@ int swiftref_get_counts(swiftref_t *s, int *n_density, int *n_gradient,
 #endif
 }
 
+/* The reference's own hydro_compute_timestep (hydro/<scheme>/hydro.h) for
+ * every particle, with the hydro_props / cosmology of this engine. */
+int swiftref_get_timesteps(swiftref_t *s, float *dt) {
+  for (long long k = 0; k < s->nparts; k++)
+    dt[k] = hydro_compute_timestep(&s->parts[k], NULL, &s->hp, &s->cosmo);
+  return 0;
+}
+
 /* Neighbour ID lists (Gadget2 + DEBUG_INTERACTIONS_SPH only). out has room
  * for max_ngb ids per particle. which: 0 density, 1 force. */
 int swiftref_get_ngb_ids(swiftref_t *s, int which, long long *out, int max_ngb) {

@@ -133,6 +133,7 @@ EXPORTS = [
     ("swiftgpu_download_parts_device", C.c_int, [VP, VP, I64]),
     ("swiftgpu_download_cells", C.c_int, [VP, VP, I32]),
     ("swiftgpu_download_counts", C.c_int, [VP, VP, VP, VP, I64]),
+    ("swiftgpu_download_timestep", C.c_int, [VP, VP, I64]),
     ("swiftgpu_get_stats", C.c_int, [VP, C.POINTER(Stats)]),
     ("swiftgpu_download_sort", C.c_int, [VP, I32, I32, VP, VP, VP]),
     ("swiftgpu_worklist_stats", C.c_int, [C.POINTER(Config), C.POINTER(Step), VP, I32, VP, I32, C.c_int, VP]),

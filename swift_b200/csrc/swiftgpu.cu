@@ -105,6 +105,7 @@ struct swiftgpu_handle {
    * contiguous ranges, so nothing but the AoS boundary sees the permutation. */
   int32_t *d_d2h = nullptr, *d_h2d = nullptr;
   int32_t *d_cnt_tmp = nullptr; /* download_counts scratch */
+  float *dt_cfl = nullptr;      /* hydro_compute_timestep of the active particles (end_force epilogue) */
   struct LeafRec *d_leaves = nullptr;
   int nleaves = 0;
   bool leaves_valid = false;
@@ -877,18 +878,25 @@ __global__ void __launch_bounds__(128) k_extra_ghost(const ExtraArgs E) {
   }
 }
 
-/* runner_do_end_hydro_force (runner_others.c:815): hydro_end_force */
+/* runner_do_end_hydro_force (runner_others.c:815): hydro_end_force, and in the
+ * same pass hydro_compute_timestep (Minimal hydro.h:440, Gadget2 :444, SPHENIX
+ * :475) with the reference's order of operations (separate IEEE multiplies and
+ * one divide), so that dt is bit-identical for identical h and v_sig. */
 __global__ void __launch_bounds__(128)
     k_end_force(const Group *groups, int ngroups, const DevCell *cells, Soa S, int max_active_bin,
-                int scheme) {
+                int scheme, float cfl, float a, float a_factor_sound_speed, float *dt_cfl) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (g >= ngroups) return;
   const DevCell c = cells[groups[g].tcell];
   for (int k = lane; k < c.count; k += 32) {
     const int p = c.first + k;
-    if (S.time_bin[p] > max_active_bin) continue;
-    S.f_hdt[p] *= S.h[p] * HYDRO_DIMENSION_INV;
+    if (S.time_bin[p] > max_active_bin) {
+      dt_cfl[p] = -1.f;
+      continue;
+    }
+    const float h = S.h[p];
+    S.f_hdt[p] *= h * HYDRO_DIMENSION_INV;
     if (scheme == SCH_GADGET2) {
       /* 0.5 * gas_entropy_from_internal_energy(rho, entropy_dt) */
       const float cbrt_inv = 1.f / cbrtf(S.rho[p]);
@@ -896,6 +904,9 @@ __global__ void __launch_bounds__(128)
       o.w = 0.5f * (HYDRO_GAMMA_MINUS_ONE * o.w * (cbrt_inv * cbrt_inv));
       S.fo1[p] = o;
     }
+    const float v_sig = scheme == SCH_SPHENIX ? S.g_vsig[p] : S.f_vsig[p];
+    const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(2.f, KERNEL_GAMMA), cfl), a), h);
+    dt_cfl[p] = __fdiv_rn(num, __fmul_rn(a_factor_sound_speed, v_sig));
   }
 }
 
@@ -1040,8 +1051,9 @@ static void free_parts(H *h) {
   cudaFree(h->gright); cudaFree(h->time_bin); cudaFree(h->depth_h); cudaFree(h->f_minngb);
   cudaFree(h->nd); cudaFree(h->ng); cudaFree(h->nf);
   cudaFree(h->xf); cudaFree(h->xs); cudaFree(h->gq);
-  cudaFree(h->d_d2h); cudaFree(h->d_h2d); cudaFree(h->d_cnt_tmp);
+  cudaFree(h->d_d2h); cudaFree(h->d_h2d); cudaFree(h->d_cnt_tmp); cudaFree(h->dt_cfl);
   h->d_d2h = h->d_h2d = h->d_cnt_tmp = nullptr;
+  h->dt_cfl = nullptr;
   h->xf = h->gq = nullptr; h->xs = nullptr;
   h->d_aos = nullptr; h->x = nullptr;
   h->n = 0;
@@ -1346,7 +1358,7 @@ static int alloc_parts(H *h, int64_t n) {
   AL(h->time_bin, int8_t, n); AL(h->depth_h, int8_t, n);
   AL(h->f_minngb, int32_t, n); AL(h->nd, int32_t, n); AL(h->ng, int32_t, n); AL(h->nf, int32_t, n);
   AL(h->xf, float4, n + 2); AL(h->xs, double, 3 * (n + 4));
-  AL(h->d_d2h, int32_t, n); AL(h->d_h2d, int32_t, n);
+  AL(h->d_d2h, int32_t, n); AL(h->d_h2d, int32_t, n); AL(h->dt_cfl, float, n);
   if (h->cfg.scheme == SCH_SPHENIX) AL(h->gq, float4, n + 2);
 #undef AL
   h->n = n;
@@ -1898,7 +1910,9 @@ extern "C" int swiftgpu_run_end_force(swiftgpu_t *h) {
   if (h->L_subset.ngroups > 0) {
     k_end_force<<<(h->L_subset.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(
         h->L_subset.groups, h->L_subset.ngroups, h->d_cells, soa_of(h), h->step.max_active_bin,
-        h->cfg.scheme);
+        h->cfg.scheme, h->cfg.CFL_condition, h->step.a,
+        /* cosmology.c: a_factor_sound_speed = a^(-1.5 (gamma - 1)) */
+        powf(h->step.a, -1.5f * HYDRO_GAMMA_MINUS_ONE), h->dt_cfl);
     h->stats.n_launches++;
     CK(cudaGetLastError());
   }
@@ -1990,6 +2004,20 @@ extern "C" int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density, int32
     CK(cudaMemcpyAsync(dst[k], h->d_cnt_tmp, sizeof(int32_t) * nparts, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
+  return 0;
+}
+
+extern "C" int swiftgpu_download_timestep(swiftgpu_t *h, float *dt_cfl, int64_t nparts) {
+  if (!h || !dt_cfl || nparts != h->n) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (!(h->phases_done & SWIFTGPU_PHASE_END_FORCE)) return h->fail("download_timestep before run_end_force");
+  if (!h->d_cnt_tmp) CK(cudaMalloc((void **)&h->d_cnt_tmp, sizeof(int32_t) * (size_t)nparts));
+  /* device order -> host order (floats moved as 32-bit words) */
+  k_scatter_i32<<<(unsigned)((nparts + 255) / 256), 256, 0, h->stream>>>((const int32_t *)h->dt_cfl, h->d_d2h,
+                                                                        nparts, h->d_cnt_tmp);
+  h->stats.n_launches++;
+  CK(cudaMemcpyAsync(dt_cfl, h->d_cnt_tmp, sizeof(float) * nparts, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -115,6 +115,12 @@ class SwiftGPU:
         self._ck(self.lib.swiftgpu_download_cells(self.h, out.ctypes.data, self.ncells), "download_cells")
         return out
 
+    def download_timestep(self):
+        """hydro_compute_timestep of the active particles (-1 for inactive ones)."""
+        dt = np.empty(self.nparts, dtype=np.float32)
+        self._ck(self.lib.swiftgpu_download_timestep(self.h, dt.ctypes.data, self.nparts), "download_timestep")
+        return dt
+
     def download_counts(self):
         nd = np.zeros(self.nparts, np.int32)
         ng = np.zeros_like(nd)

@@ -327,3 +327,39 @@ def test_full_size_properties_sedov128():
     st = g.stats()
     assert st.ghost_unconverged == 0
     g.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_cfl_timestep_epilogue(scheme):
+    """hydro_compute_timestep (Minimal hydro.h:440, Gadget2 :444,
+    SPHENIX :475) in the end_force epilogue. (1) the order of operations is the
+    reference's: dt is bit-identical to the float32 restatement evaluated on the
+    h and v_sig this library downloaded; (2) against the reference's own function
+    on the reference's particles it is within the 1e-5 bar (v_sig carries the
+    FMA-level differences of the force loop); (3) inactive particles get -1."""
+    ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.05, seed=21, active_fraction=0.6)
+    c = util.make_case(scheme, ic, (3, 3, 3), max_active_bin=1)
+    c_all = util.make_case(scheme, dict(ic, time_bin=np.ones_like(ic["time_bin"])), (3, 3, 3))
+    o_all, _ = util.run_oracle(c_all)
+    c.parts = o_all.parts()
+    tb = host.field(c.parts, c.layout, "time_bin")
+    tb[:] = ic["time_bin"][c.tree.perm]
+    g = util.run_gpu(c)
+    got = g.download_parts()
+    dt = g.download_timestep()
+    active = tb <= 1
+    assert np.all(dt[~active] == -1.0) and np.all(dt[active] > 0)
+    f32 = np.float32
+    h = host.field(got, c.layout, "h").astype(f32)
+    vs = host.field(got, c.layout, "v_sig").astype(f32)
+    gam = f32(1.825742)  # kernel_gamma, kernel_hydro.h:52
+    num = (((f32(2.0) * gam) * f32(c.cfg.CFL_condition)) * f32(c.step.a)) * h
+    want = num / (f32(1.0) * vs)  # a_factor_sound_speed = 1 without cosmology
+    assert np.array_equal(dt[active], want[active])
+    o, kind = util.run_oracle(c)
+    if kind == "reference":
+        ref_dt = o.timesteps()
+        rel = np.abs(dt[active] - ref_dt[active]) / ref_dt[active]
+        # particles whose h flipped one Newton step (tests/util.py) move dt by up to h_tolerance
+        assert np.quantile(rel, 0.99) < 1e-5 and rel.max() < 2.0 * c.cfg.h_tolerance, (rel.max(), kind)
+    g.close()
