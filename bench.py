@@ -54,6 +54,7 @@ WORKLOADS = {
     "sedov128": ("gadget2", 128, "sedov"),
     "sphenix128": ("sphenix", 128, "jitter"),
     "sphenix256": ("sphenix", 256, "jitter"),
+    "sphenix512": ("sphenix", 512, "jitter"),  # 134 M particles: ~110 GB of HBM with the bench's device copies
     # multi-time-step: ~5 % of the particles active (clustered in space), the rest are neighbours only
     "sphenix128a5": ("sphenix", 128, "active5"),
     "clustered128": ("sphenix", 128, "clustered"),
