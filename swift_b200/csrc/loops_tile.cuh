@@ -91,10 +91,22 @@ __device__ __forceinline__ bool mbar_try(uint64_t *b, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-/* Bounded wait: a protocol error traps instead of hanging the GPU. */
+/* Bounded wait: a protocol error traps (after 4 s of wall-clock time on the
+ * device) instead of hanging the GPU. */
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
-  for (unsigned spins = 0; !mbar_try(b, parity); spins++) {
-    if (spins > (1u << 22)) __trap();
+  if (mbar_try(b, parity)) return;
+  unsigned long long t0 = 0;
+  for (unsigned spins = 1; !mbar_try(b, parity); spins++) {
+    if ((spins & 1023u) == 0) {
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      if (t - t0 > 4000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
