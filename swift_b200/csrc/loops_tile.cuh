@@ -590,8 +590,10 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
     for (int jstep = 0; jstep < steps; jstep++) {
       const int m = 4 * jstep + s4;
       const bool act = m < total;
-      const int q = (m >= n0) + (m >= c1) + (m >= c2);
-      const int base = q == 0 ? 0 : (q == 1 ? n0 : (q == 2 ? c1 : c2));
+      /* sub-list q and index in it of position m of the concatenated list (selects, no branches) */
+      const bool q1 = m >= n0, q2 = m >= c1, q3 = m >= c2;
+      const int base = q3 ? c2 : (q2 ? c1 : (q1 ? n0 : 0));
+      const int q = (int)q1 + (int)q2 + (int)q3;
       const int kk = act ? m - base : 0;
       const int entry = act ? (int)wlist[kk * 32 + t8 + 8 * q] : 0;
       const int slot = entry & 2047;
