@@ -403,3 +403,16 @@ def test_full_size_properties_clustered128_sphenix():
     assert np.array_equal(nd, nd2) and np.array_equal(ng, ng2) and np.array_equal(nf, nf2)
     assert np.array_equal(host.field(g.download_parts(), lay, "h"), host.field(got, lay, "h"))
     g.close()
+
+
+@pytest.mark.parametrize("scheme", ("gadget2", "sphenix"))
+def test_full_step_64cubed_vs_reference(scheme):
+    """262 144 particles (the CPU baseline's sample size; 4^3 top cells split
+    twice, 64-particle leaves as in the benchmark box): the whole step against
+    the unmodified reference, neighbour counts against the C restatement."""
+    ic = host.jittered_box(64, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.03, seed=17)
+    c = util.make_case(scheme, ic, host.default_top_grid(64))
+    g = util.run_gpu(c)
+    rep = _check(c, g)
+    assert rep["n"] == 64 ** 3
+    g.close()
