@@ -399,8 +399,8 @@ def main():
     kname = {"tile": "k_tile", "cta": "k_cta", "warp": "k_loop"}.get(os.environ.get("SWIFTGPU_LOOPS", "tile"), "k_tile")
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel, from the committed
     # ncu --set full capture of this command (profiles/r01c_summary.md); null for workloads not captured
-    TRAFFIC = {("sedov128", "k_tile", "force"): 366.891264e6 + 60.503808e6,
-               ("sedov128", "k_tile", "density"): 301.667328e6 + 64.605440e6}
+    TRAFFIC = {("sedov128", "k_tile", "force"): 368.951552e6 + 60.983552e6,
+               ("sedov128", "k_tile", "density"): 301.467904e6 + 62.868992e6}
     traffic = TRAFFIC.get((args.workload, kname, dom)) if world == 1 else None
     roofline = {"bound": "fp32", "kernel": (kname + "<FORCE,%s>" % scheme) if dom == "force" else (kname + "<DENSITY>"),
                 "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
