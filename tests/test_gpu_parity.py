@@ -416,3 +416,18 @@ def test_full_step_64cubed_vs_reference(scheme):
     rep = _check(c, g)
     assert rep["n"] == 64 ** 3
     g.close()
+
+
+@pytest.mark.parametrize("scheme", ("minimal", "sphenix"))
+def test_non_periodic_box(scheme):
+    """periodic = 0 (space->periodic, space_getsid.h:47-80 without wrapping):
+    edge particles have one-sided neighbourhoods, so the ghost grows their h over
+    several iterations; no pair may be taken across the box faces."""
+    ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.05, seed=29)
+    c = util.make_case(scheme, ic, (4, 4, 4))
+    c.cfg.periodic = 0
+    g = util.run_gpu(c)
+    rep = _check(c, g)
+    st = g.stats()
+    assert st.ghost_iterations >= 3
+    g.close()
