@@ -431,3 +431,32 @@ def test_non_periodic_box(scheme):
     st = g.stats()
     assert st.ghost_iterations >= 3
     g.close()
+
+
+@pytest.mark.parametrize("scheme", ("minimal", "gadget2", "sphenix"))
+def test_ghost_limits_and_mass_weighting(scheme):
+    """The ghost's corner branches against the oracle: h clamped at h_max / h_min
+    (runner_ghost.c:1271-1352, 1430-1470: particles that want a larger h than
+    allowed are finished at the limit, rho_dh zeroed by hydro_prepare_force) and
+    the mass-weighted neighbour number (hydro_props use_mass_weighted_num_ngb,
+    :1246-1252)."""
+    ic = host.jittered_box(14, abi.SCHEMES[scheme], jitter=0.3, h_scatter=0.1, seed=41)
+    h0 = float(np.median(ic["h"]))
+    # (a) a tight h_max / h_min window around the initial guess (the drift clamps h into it before the
+    # ghost runs, cell_drift.c: p->h = min(p->h, h_max); p->h = max(p->h, h_min))
+    ic = dict(ic, h=np.clip(ic["h"], np.float32(0.97 * h0), np.float32(1.02 * h0)).astype(ic["h"].dtype))
+    c = util.make_case(scheme, ic, (3, 3, 3), h_max=1.02 * h0)
+    c.cfg.h_min = 0.97 * h0
+    g = util.run_gpu(c)
+    got = g.download_parts()
+    hh = host.field(got, c.layout, "h")
+    assert (hh >= np.float32(0.97 * h0)).all() and (hh <= np.float32(1.02 * h0)).all()
+    assert (hh == np.float32(1.02 * h0)).any() or (hh == np.float32(0.97 * h0)).any()
+    _check(c, g)
+    g.close()
+    # (b) mass-weighted neighbour number
+    c = util.make_case(scheme, ic, (3, 3, 3))
+    c.cfg.use_mass_weighted_num_ngb = 1
+    g = util.run_gpu(c)
+    _check(c, g)
+    g.close()
