@@ -262,11 +262,21 @@ __device__ __forceinline__ float sure_r2(float a, float E) {
   return b > 0.f ? b * b * 0.999998f : 0.f;
 }
 
-#define TM(x) /* timing hooks of the development build */
+/* Timing hooks of the development build (-DTL_TIMING): warp 0 of a few CTAs prints how its life splits
+ * into waits, cull, test and drain (fenced clock64 reads). */
+#ifdef TL_TIMING
+#define TM(...) __VA_ARGS__
+#define TCLK(v) { __syncwarp(); asm volatile("" ::: "memory"); v = clock64(); asm volatile("" ::: "memory"); }
+#else
+#define TM(...)
+#endif
 
+/* resident CTAs per SM the kernel is compiled for: 3 (type-1) / 2 (force) standard CTAs, 5 / 3 small ones */
+#define TL_MIN_BLOCKS(LOOP, CW)                                     \
+  ((CW) == 8 ? ((LOOP) == LOOP_FORCE ? 2 : TL_DENS_BLOCKS) \
+             : ((LOOP) == LOOP_FORCE ? 3 : TL_SPARSE_BLOCKS))
 template <int LOOP, int SCHEME, int NS, int CW>
-__global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE ? 2 : TL_DENS_BLOCKS) : (LOOP == LOOP_FORCE ? 3 : TL_SPARSE_BLOCKS)))
-    k_tile(const LoopArgs A) {
+__global__ void __launch_bounds__(32 * (CW + 1), TL_MIN_BLOCKS(LOOP, CW)) k_tile(const LoopArgs A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
   constexpr int QCAP = FORCE ? TL_SUBCAP2 : TL_SUBCAP1;
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
               const float r = fmaf(fmaxf(crmax, ti_.rsrc), PREFILTER_REL, A.margin) + sc.dx_max_part;
               const float c0[3] = {(float)sc.loc[0], (float)sc.loc[1], (float)sc.loc[2]};
               float q2 = 0.f;
-  #pragma unroll
+#pragma unroll
               for (int k = 0; k < 3; k++) {
                 const float a = c0[k] - (chi[k] - ti_.d[k]), b = (clo[k] - ti_.d[k]) - (c0[k] + sc.width);
                 const float gk = fmaxf(0.f, fmaxf(a, b));
@@ -517,7 +527,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
                    sFull + s);
           bytes += nb32;
         }
-  #pragma unroll
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(FULL_MASK, bytes, o);
         __syncwarp();
         if (lane == 0) {
@@ -672,13 +682,17 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
 
 
   const int hold_max = min(NS - 1, max(1, A.hold));
+  TM(long long tm_t0, tm_wait = 0, tm_peek = 0, tm_setup = 0, tm_drain = 0, tm_first = 0, tm_cull = 0, tm_test = 0, tm_a, tm_b;
+     int tm_nwait = 0, tm_ndrain = 0, tm_ntask = 0; TCLK(tm_t0);)
   int held = 0; /* stages tested but not yet released */
   int it = 0;   /* next stage to wait for (whole CTA life) */
   for (;;) {
     /* ---- next task: its first stage carries the task id ---- */
     {
       const int s0 = it % NS;
+      TM(TCLK(tm_a);)
       mbar_wait(sFull + s0, (uint32_t)((it / NS) & 1));
+      TM(TCLK(tm_b); tm_peek += tm_b - tm_a; tm_ntask++;)
       const int32_t *const meta0 = (const int32_t *)(smem + s0 * SM::kStageBytes + SM::kStageMeta);
       if (meta0[2] == 2) break;
       const int task = meta0[3];
@@ -769,6 +783,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
       facc.v_sig = 0.f;
       facc.min_ngb = NUM_TIME_BINS + 1;
       nhit = 0;
+      TM(TCLK(tm_a); tm_setup += tm_a - tm_b;)
     }
     const int first_it = it;
     /* ---- stage loop: one state machine with a single drain() call site, so
@@ -899,10 +914,10 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
     }
     /* ---- combine the 4 partial sums of each target and flush ---- */
     int nh = nhit;
-  #pragma unroll
+#pragma unroll
     for (int o = 8; o < 32; o <<= 1) nh += __shfl_xor_sync(FULL_MASK, nh, o);
     if (LOOP == LOOP_DENSITY) {
-  #pragma unroll
+#pragma unroll
       for (int o = 8; o < 32; o <<= 1) {
         dacc.rho += __shfl_xor_sync(FULL_MASK, dacc.rho, o);
         dacc.rho_dh += __shfl_xor_sync(FULL_MASK, dacc.rho_dh, o);
@@ -926,7 +941,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
         atomicAdd(pb + 3, dacc.rot[2]);
       }
     } else if (LOOP == LOOP_GRADIENT) {
-  #pragma unroll
+#pragma unroll
       for (int o = 8; o < 32; o <<= 1) {
         gacc.v_sig = fmaxf(gacc.v_sig, __shfl_xor_sync(FULL_MASK, gacc.v_sig, o));
         gacc.laplace_u += __shfl_xor_sync(FULL_MASK, gacc.laplace_u, o);
@@ -938,7 +953,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
         atomic_max_pos(&A.g_amax[ti], gacc.alpha_max);
       }
     } else {
-  #pragma unroll
+#pragma unroll
       for (int o = 8; o < 32; o <<= 1) {
         facc.ax += __shfl_xor_sync(FULL_MASK, facc.ax, o);
         facc.ay += __shfl_xor_sync(FULL_MASK, facc.ay, o);
@@ -962,6 +977,10 @@ __global__ void __launch_bounds__(32 * (CW + 1), (CW == 8 ? (LOOP == LOOP_FORCE 
     if (tvalid && s4 == 0 && nh) atomicAdd(&A.count[ti], nh);
     nhit_all += nhit;
   }
+  TM(TCLK(tm_b); if (lane == 0 && warp == 0 && (blockIdx.x % 64) == 5)
+       printf("TM cta %d life %lld tasks %d peek %lld setup %lld wait %lld (%d) cull %lld test %lld drain %lld (%d) first %lld\n",
+              (int)blockIdx.x, tm_b - tm_t0, tm_ntask, tm_peek, tm_setup, tm_wait, tm_nwait, tm_cull, tm_test, tm_drain,
+              tm_ndrain, tm_first);)
   int tot = nhit_all, tt = ntests;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
