@@ -47,7 +47,9 @@ namespace swiftgpu {
 
 #define TL_CWARPS 8 /* consumer warps of the standard CTA (template CW: 8, or 4 for sparse target sets) */
 #define TL_TARGETS 64 /* targets of a task chunk (host task list); a CW-warp CTA takes 8 * CW of them */
-#define TL_SLOTS 256 /* source slots per stage */
+#ifndef TL_SLOTS
+#define TL_SLOTS 256 /* source slots per stage (<= 256: 8-bit slot field of the list entries) */
+#endif
 #define TL_OCT (TL_SLOTS / 8)
 #define TL_FRAGS 8   /* fragments per stage */
 #ifndef TL_WAIT_HINT_NS
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), TL_MIN_BLOCKS(LOOP, CW)) k_tile
       const int entry = act ? (int)wlist[kk * 32 + t8 + 8 * q] : 0;
       const int slot = entry & 2047;
       const char *const st = smem + (slot >> 8) * SM::kStageBytes;
-      const int sl = slot & (TL_SLOTS - 1);
+      const int sl = slot & 255;
       const TileItem &ii = ((const TileItem *)(st + SM::kStageIT))[entry >> 11];
       const int gi = ii.gi_base + sl;
       const double *const D = (const double *)(st + SM::kStageD) + sl + ii.dofs;

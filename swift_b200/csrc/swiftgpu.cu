@@ -1602,12 +1602,15 @@ static int loop_kind() {
   return v;
 }
 static bool use_cta_loops() { return loop_kind() >= 1; }
+#ifndef TL_FORCE_NS
+#define TL_FORCE_NS 4 /* ring stages of the force kernel (SPHENIX: one less, 4 payload columns) */
+#endif
 template <int LOOP, int SCHEME, int CW>
 static cudaError_t launch_tile_cw(H *h, const LoopArgs &A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
   /* ring stages: as many as keep 3 (type-1) / 2 (force) standard CTAs, or 5 small CTAs, on an SM */
-  constexpr int NS = CW == 8 ? (FORCE ? (SCHEME == SCH_SPHENIX ? 3 : 4) : (LOOP == LOOP_GRADIENT ? 3 : TL_DENS_NS)) : (FORCE ? 2 : TL_SPARSE_NS);
+  constexpr int NS = CW == 8 ? (FORCE ? (SCHEME == SCH_SPHENIX ? TL_FORCE_NS - 1 : TL_FORCE_NS) : (LOOP == LOOP_GRADIENT ? 3 : TL_DENS_NS)) : (FORCE ? 2 : TL_SPARSE_NS);
   constexpr int bytes = TileSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1), CW>::kBytes;
   static bool configured = false;
   if (!configured) {
