@@ -1,11 +1,14 @@
 /*
  * swiftgpu.cu - libswiftgpu: C ABI (include/swiftgpu.h), device state and the
- * per-particle kernels (AoS<->SoA transposes, 13-axis sort, ghost, extra ghost,
- * end force). The neighbour loops live in loops.cuh.
+ * per-particle kernels (device order, AoS<->SoA transposes, tile records, 13-axis
+ * sort, ghost, extra ghost, end force + CFL time-step). The neighbour loops live
+ * in loops_tile.cuh (default), loops_cta.cuh and loops.cuh (A/B generations).
  *
- * Device state is SoA, particles in the host's cell order (every cell is a
- * contiguous index range, progeny partition their parent's range):
+ * Device state is SoA. Every cell is a contiguous index range exactly as on the
+ * host (progeny partition their parent's range); inside a leaf the particles are
+ * in Morton order (d2h / h2d map device <-> host indices at the AoS boundary):
  *   x[3n] f64 | mv[n] f32x4 (m,vx,vy,vz) | h,u,rho f32 | time_bin,depth_h i8
+ *   tile records xf (float position, reach^2), xs (3 f64 columns), octet boxes
  *   density sums dA (rho,rho_dh,wcount,wcount_dh), dB (div_v,rot_v)
  *   loop inputs  fq1 (rho,P,f,cs), fq2 (balsara,h,u,time_bin), fq3 (alpha,alpha_diff)
  *   force sums   fo1 (a_hydro,u_dt|entropy_dt), h_dt, v_sig, min_ngb_time_bin
