@@ -479,3 +479,40 @@ def test_two_gpu_halo_exchange_matches_single_rank():
                         os.path.join(root, "scripts", "multigpu_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MULTIGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("reach", (2.0, 5.0 ** 0.5, 8.0 ** 0.5, 3.0))
+@pytest.mark.parametrize("scheme", ("gadget2", "sphenix"))
+def test_cutoff_on_lattice_distances(scheme, reach):
+    """Adversarial for the exact path: a PERFECT lattice with h gamma equal (to
+    float rounding) to a lattice distance, so that whole shells of neighbours sit
+    on the cut-off r2 < h^2 gamma^2 and, for the axis-aligned pairs, on the
+    sorted-axis limits of DOPAIR1/DOPAIR2 (functions_hydro.h:1296-1332,
+    :1652-1735). Float rounding in the reference's frames decides every one of
+    them; the neighbour counts of the density and force loops must still equal
+    the oracle's bit for bit (fixed h: sort + density, then force with the ghost
+    skipped is not possible, so the force check runs the full step and relies
+    on identical h)."""
+    L = 16
+    ic = host.uniform_box(L, abi.SCHEMES[scheme])
+    gamma_k = np.float32(1.825742)
+    ic["h"][:] = np.float32(reach / L) / gamma_k
+    c = util.make_case(scheme, ic, (4, 4, 4))
+    mask = abi.PHASE_SORT | abi.PHASE_DENSITY
+    g = util.run_gpu(c, mask)
+    nd, _, _ = g.download_counts()
+    p = util.run_port(c, mask)
+    pnd, _, _ = p.counts()
+    assert np.array_equal(nd, pnd), f"{(nd != pnd).sum()} density counts differ, GPU {np.unique(nd)} oracle {np.unique(pnd)}"
+    if scheme == "sphenix":
+        # the reference's own integer counter (SWIFT_HYDRO_DENSITY_CHECKS build), when it travelled
+        lay = util.golden_layout("sphenix_chk")
+        c2 = util.make_case(scheme, ic, (4, 4, 4), layout=lay)
+        o2, kind = util.run_oracle(c2, mask, variant="sphenix_chk")
+        if kind == "reference" and o2.counts() is not None:
+            assert np.array_equal(nd, o2.counts()[0] - 1), "differs from the reference's own N_density"
+    g.close()
+    # the whole step (h moves away from the lattice value in the ghost; counts must still match)
+    g = util.run_gpu(c)
+    _check(c, g)
+    g.close()
