@@ -516,3 +516,14 @@ def test_cutoff_on_lattice_distances(scheme, reach):
     g = util.run_gpu(c)
     _check(c, g)
     g.close()
+    # type-2 loop on the cut-off: with h_tolerance ~ 1 the ghost accepts the lattice h as it is
+    # (runner_ghost.c:1388), so the force loop runs with r = h gamma shells too
+    c3 = util.make_case(scheme, ic, (4, 4, 4), h_tolerance=0.9)
+    g = util.run_gpu(c3)
+    got = g.download_parts()
+    assert np.array_equal(host.field(got, c3.layout, "h"), ic["h"][c3.tree.perm])
+    _, _, nf = g.download_counts()
+    p3 = util.run_port(c3)
+    assert np.array_equal(host.field(p3.parts(), c3.layout, "h"), host.field(got, c3.layout, "h"))
+    assert np.array_equal(nf, p3.counts()[2]), f"{(nf != p3.counts()[2]).sum()} force counts differ"
+    g.close()
