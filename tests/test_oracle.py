@@ -125,6 +125,32 @@ def test_port_counts_match_reference_counters():
 
 
 @needs_ref
+@pytest.mark.parametrize("reach", (2.0, 5.0 ** 0.5, 8.0 ** 0.5, 3.0))
+def test_port_counts_on_lattice_cutoff(reach):
+    """Pins the C restatement where it is most fragile: a perfect lattice with
+    h gamma equal to a lattice distance, so that whole shells sit on the cut-off
+    and on the sorted-axis limits (functions_hydro.h:1296-1332, :1652-1735) and
+    the reference's float frames decide each pair. Density (fixed h) and force
+    (ghost accepting the lattice h, h_tolerance ~ 1) counts against the
+    reference's own N_density / N_force counters."""
+    L = 16
+    ic = host.uniform_box(L, abi.SCHEME_SPHENIX)
+    ic["h"][:] = np.float32(reach / L) / np.float32(1.825742)
+    lay = util.golden_layout("sphenix_chk")
+    c = util.make_case("sphenix", ic, (4, 4, 4), layout=lay)
+    m = abi.PHASE_SORT | abi.PHASE_DENSITY
+    o, _ = util.run_oracle(c, m, variant="sphenix_chk")
+    p = util.run_port(c, m)
+    assert np.array_equal(p.counts()[0] + 1, o.counts()[0])
+    c3 = util.make_case("sphenix", ic, (4, 4, 4), layout=lay, h_tolerance=0.9)
+    o3, _ = util.run_oracle(c3, variant="sphenix_chk")
+    p3 = util.run_port(c3)
+    assert np.array_equal(host.field(p3.parts(), lay, "h"), host.field(o3.parts(), lay, "h"))
+    assert np.array_equal(p3.counts()[0] + 1, o3.counts()[0])
+    assert np.array_equal(p3.counts()[2], o3.counts()[2])
+
+
+@needs_ref
 @pytest.mark.parametrize("scheme", ("gadget2", "sphenix"))
 def test_port_matches_reference_active_subset(scheme):
     ic = host.jittered_box(12, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.02, seed=11, active_fraction=0.3)
