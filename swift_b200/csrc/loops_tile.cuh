@@ -2,7 +2,8 @@
  * loops_tile.cuh - the neighbour loops as a TMA-fed producer/consumer pipeline.
  *
  * One CTA = 8 consumer warps (64 TARGET particles of one target cell, 8 per
- * warp) + 1 producer warp. No __syncthreads() after the prologue.
+ * warp; 4 warps for sparse target sets) + 1 producer warp. No
+ * __syncthreads() after the prologue.
  *
  * The CTAs are persistent: each draws tasks (8 targets per consumer warp of
  * one group) from a global counter and the ring runs across task boundaries.
@@ -12,9 +13,10 @@
  *             into fragments. A ring STAGE holds up to 256 source slots / 8
  *             fragments. The source data are copied as they lie in HBM by
  *             bulk TMA (cp.async.bulk -> mbarrier complete_tx): the
- *             prefilter record xf = (float x, y, z, reach^2), the payload
- *             columns (mv, fq1, fq2, fq3) and the precomputed OCTET boxes of
- *             the source cell. No per-source arithmetic is done at staging.
+ *             prefilter record xf = (float x, y, z, reach^2), the three
+ *             double position columns xs, the payload columns (mv, gq or
+ *             fq1, fq2, fq3) and the precomputed OCTET boxes of the source
+ *             cell. No per-source arithmetic is done at staging.
  *   CONSUMER  per stage: lane = octet box-box cull against the warp's target
  *             box (one ballot), then per accepted octet every lane
  *             (t = lane & 7 target, s = lane >> 3) tests its target against
