@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SWIFTGPU_ABI_VERSION 1
+#define SWIFTGPU_ABI_VERSION 2
 
 /* --with-hydro=minimal|gadget2|sphenix (configure.ac:2233-2300). */
 enum swiftgpu_scheme {
@@ -118,7 +118,7 @@ typedef struct swiftgpu_config {
 typedef struct swiftgpu_step {
   int64_t ti_current;     /* engine->ti_current */
   int32_t max_active_bin; /* engine->max_active_bin (active.h:349) */
-  int32_t with_cosmology; /* must be 0 in this version */
+  int32_t with_cosmology; /* must be 0 in this version (and a = 1, H = 0) */
   double time_base;       /* engine->time_base (dt = 2^(bin+1) * time_base... timeline.h:91) */
   float a, H;             /* cosmology->a, cosmology->H (1, 0 without cosmology) */
 } swiftgpu_step;
@@ -171,6 +171,10 @@ typedef struct swiftgpu_stats {
   int64_t t_density, t_gradient, t_force;
   int32_t ghost_iterations;
   int32_t ghost_unconverged;
+  /* worklists rebuilt because the ghost changed a recursion predicate
+   * (cell.h:951,992 for the gradient loop, :966,1007 for the force loop) */
+  int32_t force_list_rebuilds, gradient_list_rebuilds;
+  int64_t n_host_syncs; /* cudaStreamSynchronize / event waits issued by the library */
 } swiftgpu_stats;
 
 /* Fills `out` with the struct part layout of the reference's default build of

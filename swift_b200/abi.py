@@ -10,6 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
+ABI_VERSION = 2  # SWIFTGPU_ABI_VERSION of include/swiftgpu.h
 SCHEME_MINIMAL, SCHEME_GADGET2, SCHEME_SPHENIX = 0, 1, 2
 SCHEMES = {"minimal": 0, "gadget2": 1, "sphenix": 2}
 
@@ -91,6 +92,8 @@ class Stats(C.Structure):
         ("n_force", C.c_int64), ("n_launches", C.c_int64),
         ("t_density", C.c_int64), ("t_gradient", C.c_int64), ("t_force", C.c_int64),
         ("ghost_iterations", C.c_int32), ("ghost_unconverged", C.c_int32),
+        ("force_list_rebuilds", C.c_int32), ("gradient_list_rebuilds", C.c_int32),
+        ("n_host_syncs", C.c_int64),
     ]
 
 

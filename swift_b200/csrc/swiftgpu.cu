@@ -83,6 +83,7 @@ struct swiftgpu_handle {
   float cells_uploaded_hmax_active(int c) const { return up_hmax_active[c]; }
   std::vector<int32_t> top;
   std::vector<uint8_t> force_bits; /* recursion predicate bits the force list was built with */
+  std::vector<uint8_t> loop1_bits; /* ... and the density list (cell.h:951,992), revalidated for the gradient loop */
   int64_t n = 0;
   int ncells = 0;
 
@@ -90,7 +91,11 @@ struct swiftgpu_handle {
   DevCell *d_cells = nullptr;
   DevCell *d_cells_init = nullptr; /* pristine copy: the ghost raises h_max in d_cells */
   float *d_dmin = nullptr, *d_dxp = nullptr;
-  std::vector<uint64_t> req_density, req_subset; /* sort requests of the static lists */
+  std::vector<uint64_t> req_density, req_subset, req_gradient, req_force; /* sort requests of the lists */
+  float *d_dxp_old = nullptr, *d_hmax_tmp = nullptr;
+  bool ext_valid = false; /* d_ext holds the key extrema of the current segments */
+  uint8_t *d_loop1_bits = nullptr, *d_grad_bits = nullptr;
+  bool gradient_own = false; /* L_gradient was rebuilt after the ghost (else the density list is used) */
   char *d_aos = nullptr;
   size_t aos_bytes = 0;
   double *x = nullptr;
@@ -131,7 +136,7 @@ struct swiftgpu_handle {
   int32_t *d_flag = nullptr;
   uint8_t *d_force_bits = nullptr;
 
-  DevList L_density, L_subset, L_force;
+  DevList L_density, L_subset, L_force, L_gradient;
 
   /* multi-GPU */
   std::vector<HaloPeer> halo;
@@ -925,17 +930,21 @@ __global__ void k_init_parts(Soa S, int32_t *nd, int64_t n, int max_active_bin, 
 }
 
 /* Which h_max-dependent recursion predicates does each cell satisfy NOW?
- * (cell.h:966 subpair2, :1007 subself2). Compared with the bits the force
- * worklist was built with; a mismatch triggers a rebuild on the host. */
-__global__ void k_force_bits(const DevCell *cells, const float *dmin, const float *dx_max_part,
-                             const uint8_t *bits, int ncells, int32_t *flag) {
+ * loop 2: cell.h:966 subpair2, :1007 subself2 (h_max, dx_max_part);
+ * loop 1: cell.h:951 subpair, :992 subself (h_max_active, dx_max_part_old).
+ * Compared with the bits the worklist was built with (Flattener::subpair*);
+ * a mismatch triggers a rebuild of that list on the host. */
+__global__ void k_pred_bits(const DevCell *cells, const float *dmin, const float *dx_max_part,
+                            const uint8_t *bits, int ncells, int use_active, int32_t *flag) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncells) return;
-  const float hm = cells[c].h_max;
-  const float gh = __fmul_rn(KERNEL_GAMMA, hm);
-  const float half = __fmul_rn(0.5f, dmin[c]);
-  const uint8_t b = (uint8_t)((__fadd_rn(gh, dx_max_part[c]) < half) ? 1 : 0) |
-                    (uint8_t)((((cells[c].flags >> 2) & 1) && (gh < half)) ? 2 : 0);
+  uint8_t b = 0;
+  if (((cells[c].flags >> 2) & 1) && cells[c].count >= 100) { /* Flattener::recursable */
+    const float hm = use_active ? cells[c].h_max_active : cells[c].h_max;
+    const float gh = __fmul_rn(KERNEL_GAMMA, hm);
+    const float half = __fmul_rn(0.5f, dmin[c]);
+    b = (uint8_t)((__fadd_rn(gh, dx_max_part[c]) < half) ? 1 : 0) | (uint8_t)((gh < half) ? 2 : 0);
+  }
   if (b != bits[c]) *flag = 1;
 }
 
@@ -1080,10 +1089,11 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   free_parts(h);
-  h->L_density.release(); h->L_subset.release(); h->L_force.release();
+  h->L_density.release(); h->L_subset.release(); h->L_force.release(); h->L_gradient.release();
   halo_release(h);
   cudaFree(h->d_cells); cudaFree(h->d_cells_init); cudaFree(h->d_dmin); cudaFree(h->d_dxp); cudaFree(h->sort_idx); cudaFree(h->d_sort_keys); cudaFree(h->d_segs); cudaFree(h->d_ext); cudaFree(h->d_ext_cells); cudaFree(h->d_counters);
-  cudaFree(h->d_flag); cudaFree(h->d_force_bits);
+  cudaFree(h->d_flag); cudaFree(h->d_force_bits); cudaFree(h->d_loop1_bits); cudaFree(h->d_grad_bits);
+  cudaFree(h->d_dxp_old); cudaFree(h->d_hmax_tmp);
   cudaFree(h->boxes); cudaFree(h->d_box_first); cudaFree(h->d_leaves);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1094,6 +1104,11 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
 extern "C" int swiftgpu_set_step(swiftgpu_t *h, const swiftgpu_step *step) {
   if (!h || !step) return 1;
   if (step->with_cosmology) return h->fail("cosmological time integration is not supported");
+  /* the cosmological factors (a_factor_Balsara_eps, fac_mu, a2_inv of the Gadget2
+   * entropy equation, ...) are not carried through: reject instead of computing
+   * silently wrong balsara / alpha values */
+  if (step->a != 1.0f || step->H != 0.0f)
+    return h->fail("cosmology is not supported: set a = 1, H = 0 (got a = %g, H = %g)", (double)step->a, (double)step->H);
   if (h->has_step && (h->step.ti_current != step->ti_current ||
                       h->step.max_active_bin != step->max_active_bin))
     h->lists_built = false; /* activity changed: the worklists depend on it */
@@ -1180,32 +1195,89 @@ static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
   return 0;
 }
 
+/* Which lists build_lists() (re)builds. LISTS_ALL starts from the uploaded cells
+ * (the gradient loop then shares the density list); the other two rebuild one
+ * list after the ghost changed a recursion predicate it depends on, with the
+ * h_max / h_max_active the device holds now. */
+enum { LISTS_ALL = 0, LISTS_FORCE = 1, LISTS_GRADIENT = 2 };
+
+static int pull_cell_hmax(H *h, std::vector<float> &hm, std::vector<float> &hma) {
+  hm.resize(h->ncells);
+  hma.resize(h->ncells);
+  float *d_tmp = h->d_hmax_tmp;
+  k_get_cell_hmax<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->ncells, d_tmp,
+                                                                  d_tmp + h->ncells);
+  h->stats.n_launches++;
+  CK(cudaMemcpyAsync(hm.data(), d_tmp, sizeof(float) * h->ncells, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(hma.data(), d_tmp + h->ncells, sizeof(float) * h->ncells, cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.n_host_syncs++;
+  return 0;
+}
+
 /* Builds worklists, the device cell table and the sort segments. */
-static int build_lists(H *h, bool force_only) {
+static int build_lists(H *h, int which) {
   if (!h->has_step) return h->fail("swiftgpu_set_step must be called before running a phase");
   if (h->cells.empty()) return h->fail("no cells uploaded");
   if (h->n <= 0) return h->fail("no particles uploaded");
   cudaSetDevice(h->cfg.device);
+  /* after the ghost: the recursion sees the h_max / h_max_active the device holds */
+  std::vector<float> hm, hma;
+  std::vector<swiftgpu_cell> saved;
+  if (which != LISTS_ALL) {
+    if (!h->d_cells) return h->fail("list rebuild before the first build");
+    if (pull_cell_hmax(h, hm, hma)) return 1;
+    saved = h->cells;
+    for (int c = 0; c < h->ncells; c++) {
+      h->cells[c].h_max = hm[c];
+      h->cells[c].h_max_active = hma[c];
+    }
+  }
   Flattener F(h->cells.data(), h->ncells, h->top.data(), (int)h->top.size(), h->cfg.dim,
               h->cfg.periodic, h->cfg.rank, h->step.ti_current);
-  WorkList Wd, Ws, Wf;
-  if (!force_only) {
+  WorkList Wd, Ws, Wf, Wg;
+  if (which == LISTS_ALL) {
     F.build_loop(0, Wd);
     std::vector<int32_t> aux;
     F.build_subset(Ws, aux);
     h->req_density = Wd.sort_requests;
     h->req_subset = Ws.sort_requests;
+    h->req_gradient.clear();
+    h->loop1_bits.resize(h->ncells);
+    for (int c = 0; c < h->ncells; c++)
+      h->loop1_bits[c] = (uint8_t)((Flattener::subpair1(h->cells[c]) ? 1 : 0) |
+                                   (Flattener::subself1(h->cells[c]) ? 2 : 0));
   }
-  F.build_loop(2, Wf);
-  h->force_bits.resize(h->ncells);
-  for (int c = 0; c < h->ncells; c++)
-    h->force_bits[c] = (uint8_t)((Flattener::subpair2(h->cells[c]) ? 1 : 0) |
-                                 (Flattener::subself2(h->cells[c]) ? 2 : 0));
+  if (which == LISTS_ALL || which == LISTS_FORCE) {
+    F.build_loop(2, Wf);
+    h->req_force = Wf.sort_requests;
+    h->force_bits.resize(h->ncells);
+    for (int c = 0; c < h->ncells; c++)
+      h->force_bits[c] = (uint8_t)((Flattener::subpair2(h->cells[c]) ? 1 : 0) |
+                                   (Flattener::subself2(h->cells[c]) ? 2 : 0));
+  }
+  if (which == LISTS_GRADIENT) {
+    F.build_loop(1, Wg);
+    h->req_gradient = Wg.sort_requests;
+    std::vector<uint8_t> gb(h->ncells);
+    for (int c = 0; c < h->ncells; c++)
+      gb[c] = (uint8_t)((Flattener::subpair1(h->cells[c]) ? 1 : 0) | (Flattener::subself1(h->cells[c]) ? 2 : 0));
+    CK(to_device(&h->d_grad_bits, gb));
+  }
+  /* the host copy keeps the uploaded (pre-ghost) values for the density and
+   * subset recursions of a later re-run */
+  if (which != LISTS_ALL)
+    for (int c = 0; c < h->ncells; c++) {
+      h->cells[c].h_max = saved[c].h_max;
+      h->cells[c].h_max_active = saved[c].h_max_active;
+    }
 
-  /* sort segments: union of the requests of the three lists */
+  /* sort segments: union of the requests of all lists */
   std::vector<uint64_t> req(h->req_density);
   req.insert(req.end(), h->req_subset.begin(), h->req_subset.end());
-  req.insert(req.end(), Wf.sort_requests.begin(), Wf.sort_requests.end());
+  req.insert(req.end(), h->req_gradient.begin(), h->req_gradient.end());
+  req.insert(req.end(), h->req_force.begin(), h->req_force.end());
   std::sort(req.begin(), req.end());
   req.erase(std::unique(req.begin(), req.end()), req.end());
 
@@ -1253,25 +1325,14 @@ static int build_lists(H *h, bool force_only) {
     off += dc[c].count;
     max_seg = std::max(max_seg, dc[c].count);
   }
-  /* If the force list was rebuilt after the ghost, keep the h_max the device
-   * already holds (it is newer than the host copy). */
-  if (force_only && h->d_cells) {
-    std::vector<float> hm(h->ncells), hma(h->ncells);
-    float *d_tmp = nullptr;
-    CK(cudaMalloc((void **)&d_tmp, 2 * sizeof(float) * h->ncells));
-    k_get_cell_hmax<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->ncells, d_tmp,
-                                                                    d_tmp + h->ncells);
-    CK(cudaMemcpyAsync(hm.data(), d_tmp, sizeof(float) * h->ncells, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(hma.data(), d_tmp + h->ncells, sizeof(float) * h->ncells,
-                       cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_tmp);
+  /* A list rebuilt after the ghost keeps the h_max the device already holds
+   * (it is newer than the host copy). */
+  if (which != LISTS_ALL)
     for (int c = 0; c < h->ncells; c++) {
       dc[c].h_max = hm[c];
       dc[c].h_max_active = hma[c];
     }
-  }
-  {
+  if (which == LISTS_ALL) {
     /* pristine table first (uploaded h_max), then the live one */
     std::vector<DevCell> dc0(dc);
     for (int c = 0; c < h->ncells; c++) {
@@ -1279,13 +1340,26 @@ static int build_lists(H *h, bool force_only) {
       dc0[c].h_max_active = h->cells_uploaded_hmax_active(c);
     }
     CK(to_device(&h->d_cells_init, dc0));
-    std::vector<float> dmin(h->ncells), dxp(h->ncells);
+    std::vector<float> dmin(h->ncells), dxp(h->ncells), dxpo(h->ncells);
     for (int c = 0; c < h->ncells; c++) {
       dmin[c] = h->cells[c].dmin;
       dxp[c] = h->cells[c].dx_max_part;
+      dxpo[c] = h->cells[c].dx_max_part_old;
     }
     CK(to_device(&h->d_dmin, dmin));
     CK(to_device(&h->d_dxp, dxp));
+    CK(to_device(&h->d_dxp_old, dxpo));
+    cudaFree(h->d_hmax_tmp);
+    h->d_hmax_tmp = nullptr;
+    CK(cudaMalloc((void **)&h->d_hmax_tmp, 2 * sizeof(float) * std::max(h->ncells, 1)));
+  } else {
+    /* the pristine table must know the new segments too (run_density copies it over the live one) */
+    std::vector<DevCell> dc0(dc);
+    for (int c = 0; c < h->ncells; c++) {
+      dc0[c].h_max = h->cells_uploaded_hmax(c);
+      dc0[c].h_max_active = h->cells_uploaded_hmax_active(c);
+    }
+    CK(to_device(&h->d_cells_init, dc0));
   }
   CK(to_device(&h->d_cells, dc));
   {
@@ -1297,12 +1371,13 @@ static int build_lists(H *h, bool force_only) {
       nb += (dc[c].count + 7) / 8;
     }
     if (nb > 0x7fffffffLL) return h->fail("too many octet boxes");
-    CK(to_device(&h->d_box_first, bf));
+    if (which == LISTS_ALL) CK(to_device(&h->d_box_first, bf));
     if (nb != h->nboxes || !h->boxes) {
       cudaFree(h->boxes);
       h->boxes = nullptr;
       CK(cudaMalloc((void **)&h->boxes, std::max<int64_t>(nb, 1) * 2 * sizeof(float4)));
       h->nboxes = nb;
+      h->sorted = false;
     }
   }
   CK(to_device(&h->d_segs, segs));
@@ -1323,14 +1398,24 @@ static int build_lists(H *h, bool force_only) {
   }
   if (max_seg > SORT_SMEM_MAX && !h->d_sort_keys)
     CK(cudaMalloc((void **)&h->d_sort_keys, std::max<int64_t>(off, 1) * sizeof(float)));
-  h->sorted = false;
+  h->ext_valid = false; /* the key extrema follow the segments */
+  if (which == LISTS_ALL) h->sorted = false;
 
-  if (!force_only) {
+  if (which == LISTS_ALL) {
     if (upload_list(h, Wd, h->L_density, false)) return 1;
     if (upload_list(h, Ws, h->L_subset, true)) return 1;
+    h->L_gradient.release();
+    h->gradient_own = false;
+    CK(to_device(&h->d_loop1_bits, h->loop1_bits));
   }
-  if (upload_list(h, Wf, h->L_force, false)) return 1;
-  CK(to_device(&h->d_force_bits, h->force_bits));
+  if (which == LISTS_ALL || which == LISTS_FORCE) {
+    if (upload_list(h, Wf, h->L_force, false)) return 1;
+    CK(to_device(&h->d_force_bits, h->force_bits));
+  }
+  if (which == LISTS_GRADIENT) {
+    if (upload_list(h, Wg, h->L_gradient, false)) return 1;
+    h->gradient_own = true;
+  }
   h->lists_built = true;
   return 0;
 }
@@ -1341,7 +1426,7 @@ static int ensure_lists(H *h) {
    * the AoS copy (the step restarts from the uploaded particle state) */
   if (h->perm_stale && h->d_aos && h->n > 0 && transpose_in(h)) return 1;
   if (h->lists_built) return 0;
-  return build_lists(h, false);
+  return build_lists(h, LISTS_ALL);
 }
 
 static int alloc_parts(H *h, int64_t n) {
@@ -1468,6 +1553,7 @@ static int phase_end(H *h, double *ms_out) {
 
 static bool use_cta_loops();
 static int loop_kind();
+static int launch_extrema(H *h);
 static float tile_maxdim(const H *h) {
   return (float)std::max(h->cfg.dim[0], std::max(h->cfg.dim[1], h->cfg.dim[2]));
 }
@@ -1487,14 +1573,19 @@ static int prep_tiles(H *h) {
 }
 /* full = the 13-axis sorted index arrays of runner_do_hydro_sort; the CTA
  * loops only consume the key extrema. */
-static int launch_sort(H *h, bool full) {
-  if (loop_kind() == 2 && prep_tiles(h)) return 1;
+static int launch_extrema(H *h) {
   if (h->n_ext_cells > 0) {
     k_extrema<<<(h->n_ext_cells * 32 + 127) / 128, 128, 0, h->stream>>>(h->d_ext_cells, h->n_ext_cells,
                                                                         h->d_cells, h->x, h->d_ext);
     h->stats.n_launches++;
     CK(cudaGetLastError());
   }
+  h->ext_valid = true;
+  return 0;
+}
+static int launch_sort(H *h, bool full) {
+  if (loop_kind() == 2 && prep_tiles(h)) return 1;
+  if (launch_extrema(h)) return 1;
   if (full && h->nsegs > 0) {
     k_sort<<<h->nsegs, 256, 0, h->stream>>>(h->d_segs, h->d_cells, h->x, h->sort_idx, h->d_sort_keys);
     h->stats.n_launches++;
@@ -1787,21 +1878,65 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
   return 0;
 }
 
+/* Has the ghost (or the rho halo) changed a recursion predicate the list was
+ * built with? Then rebuild it from the h_max / h_max_active the device holds. */
+static int revalidate_list(H *h, int which) {
+  CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int32_t), h->stream));
+  if (which == LISTS_FORCE)
+    k_pred_bits<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->d_dmin, h->d_dxp, h->d_force_bits,
+                                                                h->ncells, 0, h->d_flag);
+  else
+    k_pred_bits<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->d_dmin, h->d_dxp_old,
+                                                                h->d_loop1_bits, h->ncells, 1, h->d_flag);
+  h->stats.n_launches++;
+  int32_t flag = 0;
+  CK(cudaMemcpyAsync(&flag, h->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.n_host_syncs++;
+  if (which == LISTS_GRADIENT && h->gradient_own) {
+    /* an own gradient list exists: still valid if ITS bits match; dropped if the
+     * predicates are back to what the density list assumes */
+    if (!flag) {
+      h->L_gradient.release();
+      h->gradient_own = false;
+      return 0;
+    }
+    CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int32_t), h->stream));
+    k_pred_bits<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->d_dmin, h->d_dxp_old,
+                                                                h->d_grad_bits, h->ncells, 1, h->d_flag);
+    h->stats.n_launches++;
+    CK(cudaMemcpyAsync(&flag, h->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stats.n_host_syncs++;
+  }
+  if (!flag) return 0;
+  if (build_lists(h, which)) return 1;
+  if (which == LISTS_FORCE) h->stats.force_list_rebuilds++;
+  else h->stats.gradient_list_rebuilds++;
+  if (loop_kind() != 2) return launch_sort(h, !use_cta_loops());
+  /* new (cell, sid) segments may exist: their key extrema */
+  return launch_extrema(h);
+}
+
 extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   if (!h) return 1;
   if (h->cfg.scheme != SCH_SPHENIX) return 0;
   if (!(h->phases_done & SWIFTGPU_PHASE_GHOST)) return h->fail("run_gradient before run_ghost");
   if (phase_begin(h)) return 1;
+  /* DOSUB_PAIR1/SELF1 of the gradient task evaluate cell_can_recurse_in_subpair/
+   * subself_hydro_task (cell.h:951,992) on the h_max_active the ghost just set */
+  if (revalidate_list(h, LISTS_GRADIENT)) return 1;
+  DevList &L = h->gradient_own ? h->L_gradient : h->L_density;
   CK(cudaMemsetAsync(h->d_counters + 1, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
   bool sparse = false;
-  if (build_targets(h, h->L_density, &sparse)) return 1; /* depth_h changed in the ghost */
+  if (build_targets(h, L, &sparse)) return 1; /* depth_h changed in the ghost */
   if (loop_kind() == 2) {
     k_prep_gq<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->fq1, h->fq2, h->fq3, h->n, h->gq);
     h->stats.n_launches++;
   }
-  if (h->L_density.ntasks > 0) {
-    LoopArgs A = loop_args(h, h->L_density, h->ng, 1);
+  if (L.ntasks > 0) {
+    LoopArgs A = loop_args(h, L, h->ng, 1);
     CK((launch_loop1<LOOP_GRADIENT, false>(h, A, sparse)));
     h->stats.n_launches++;
   }
@@ -1846,45 +1981,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   const uint32_t need = h->cfg.scheme == SCH_SPHENIX ? SWIFTGPU_PHASE_EXTRA_GHOST : SWIFTGPU_PHASE_GHOST;
   if (!(h->phases_done & need)) return h->fail("run_force before the ghost phases");
   if (phase_begin(h)) return 1;
-  /* Has the ghost changed a recursion predicate the force list depends on? */
-  {
-    CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int32_t), h->stream));
-    k_force_bits<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->d_dmin, h->d_dxp,
-                                                                 h->d_force_bits, h->ncells, h->d_flag);
-    h->stats.n_launches++;
-    int32_t flag = 0;
-    CK(cudaMemcpyAsync(&flag, h->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (flag) {
-      /* pull the new h_max into the host cells and rebuild the force list */
-      std::vector<float> hm(h->ncells), hma(h->ncells);
-      float *d_tmp = nullptr;
-      CK(cudaMalloc((void **)&d_tmp, 2 * sizeof(float) * h->ncells));
-      k_get_cell_hmax<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->ncells, d_tmp,
-                                                                      d_tmp + h->ncells);
-      CK(cudaMemcpyAsync(hm.data(), d_tmp, sizeof(float) * h->ncells, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaMemcpyAsync(hma.data(), d_tmp + h->ncells, sizeof(float) * h->ncells,
-                         cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      cudaFree(d_tmp);
-      std::vector<swiftgpu_cell> saved(h->cells);
-      for (int c = 0; c < h->ncells; c++) {
-        h->cells[c].h_max = hm[c];
-        h->cells[c].h_max_active = hma[c];
-      }
-      const int rc = build_lists(h, true);
-      /* the host copy keeps the uploaded (pre-ghost) values for the density
-       * and subset recursions of a later re-run */
-      for (int c = 0; c < h->ncells; c++) {
-        h->cells[c].h_max = saved[c].h_max;
-        h->cells[c].h_max_active = saved[c].h_max_active;
-      }
-      if (rc) return 1;
-      /* new (cell, sid) segments may exist: sort again */
-      if (launch_sort(h, !use_cta_loops())) return 1;
-      h->sorted = true;
-    }
-  }
+  if (revalidate_list(h, LISTS_FORCE)) return 1;
   CK(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(unsigned long long), h->stream));
   bool sparse = false;
@@ -1931,6 +2028,10 @@ extern "C" int swiftgpu_halo_exchange(swiftgpu_t *h, int phase);
 extern "C" int swiftgpu_run_step(swiftgpu_t *h, uint32_t mask) {
   if (!h) return 1;
   const bool halo = h->cfg.nranks > 1 && h->halo_ready;
+  /* lists (and a pending re-transpose after new cells) first: the exchange
+   * writes into the SoA columns the transpose would overwrite */
+  cudaSetDevice(h->cfg.device);
+  if (ensure_lists(h)) return 1;
   if (halo && (mask & (SWIFTGPU_PHASE_SORT | SWIFTGPU_PHASE_DENSITY)) && swiftgpu_halo_exchange(h, 0))
     return 1;
   if ((mask & SWIFTGPU_PHASE_SORT) && swiftgpu_run_sort(h)) return 1;
@@ -1978,15 +2079,8 @@ extern "C" int swiftgpu_download_parts_device(swiftgpu_t *h, void *d_parts_aos, 
 extern "C" int swiftgpu_download_cells(swiftgpu_t *h, swiftgpu_cell *cells, int32_t ncells) {
   if (!h || !cells || ncells != h->ncells || !h->d_cells) return 1;
   cudaSetDevice(h->cfg.device);
-  std::vector<float> hm(ncells), hma(ncells);
-  float *d_tmp = nullptr;
-  CK(cudaMalloc((void **)&d_tmp, 2 * sizeof(float) * ncells));
-  k_get_cell_hmax<<<(ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, ncells, d_tmp, d_tmp + ncells);
-  h->stats.n_launches++;
-  CK(cudaMemcpyAsync(hm.data(), d_tmp, sizeof(float) * ncells, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(hma.data(), d_tmp + ncells, sizeof(float) * ncells, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_tmp);
+  std::vector<float> hm, hma;
+  if (pull_cell_hmax(h, hm, hma)) return 1;
   for (int c = 0; c < ncells; c++) {
     cells[c].h_max = hm[c];
     cells[c].h_max_active = hma[c];
@@ -2245,6 +2339,7 @@ extern "C" int swiftgpu_halo_exchange(swiftgpu_t *h, int phase) {
     h->stats.n_launches++;
   }
   CK(cudaGetLastError());
+  if (phase == 0) h->sorted = false; /* foreign x / h moved: tile records, octet boxes and key extrema are stale */
   h->halo_bytes[phase] = bytes;
   return 0;
 }

@@ -139,13 +139,25 @@ class Flattener {
     aux.swap(sorted_aux_);
   }
 
-  /* Bits of the h_max-dependent recursion predicates the force list used
-   * (cell.h:966 subpair2, :1007 subself2), for validation after the ghost. */
+  /* Bits of the h_max-dependent recursion predicates the lists were built with
+   * (force: cell.h:966 subpair2, :1007 subself2; density/gradient: :951
+   * subpair, :992 subself), for validation after the ghost. Only cells the
+   * recursion can descend from (split, at least space_recurse_size particles)
+   * ever evaluate them: all other cells report 0. */
+  static inline bool recursable(const swiftgpu_cell &c) {
+    return c.split && c.count >= kRecurseSizePair;
+  }
   static inline bool subpair2(const swiftgpu_cell &c) {
-    return (kKernelGammaF * c.h_max + c.dx_max_part) < 0.5f * c.dmin;
+    return recursable(c) && (kKernelGammaF * c.h_max + c.dx_max_part) < 0.5f * c.dmin;
   }
   static inline bool subself2(const swiftgpu_cell &c) {
-    return c.split && (kKernelGammaF * c.h_max < 0.5f * c.dmin);
+    return recursable(c) && (kKernelGammaF * c.h_max < 0.5f * c.dmin);
+  }
+  static inline bool subpair1(const swiftgpu_cell &c) {
+    return recursable(c) && (kKernelGammaF * c.h_max_active + c.dx_max_part_old) < 0.5f * c.dmin;
+  }
+  static inline bool subself1(const swiftgpu_cell &c) {
+    return recursable(c) && (kKernelGammaF * c.h_max_active < 0.5f * c.dmin);
   }
 
  private:
@@ -301,13 +313,14 @@ class Flattener {
       emit(MODE_PAIR_R, cj, ci, sid, shift, min_depth, max_depth, limit_max_h);
   }
 
+  /* only called on cells that are split and hold >= space_recurse_size particles */
   bool can_recurse_subpair(int loop, const swiftgpu_cell &c) const {
-    if (loop == 2) return subpair2(c); /* cell.h:966 */
-    return (kKernelGammaF * c.h_max_active + c.dx_max_part_old) < 0.5f * c.dmin; /* :951 */
+    if (loop == 2) return (kKernelGammaF * c.h_max + c.dx_max_part) < 0.5f * c.dmin; /* cell.h:966 */
+    return (kKernelGammaF * c.h_max_active + c.dx_max_part_old) < 0.5f * c.dmin;     /* :951 */
   }
   bool can_recurse_subself(int loop, const swiftgpu_cell &c) const {
-    if (loop == 2) return subself2(c); /* cell.h:1007 */
-    return (kKernelGammaF * c.h_max_active < 0.5f * c.dmin); /* :992 */
+    if (loop == 2) return c.split && (kKernelGammaF * c.h_max < 0.5f * c.dmin); /* cell.h:1007 */
+    return (kKernelGammaF * c.h_max_active < 0.5f * c.dmin);                    /* :992 */
   }
 
   void dosub_pair(int loop, int ci, int cj, int below) {

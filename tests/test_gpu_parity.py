@@ -23,23 +23,19 @@ def _check(c, g, mask=abi.PHASE_ALL, tol=TOL):
     got = g.download_parts()
     o, kind = util.run_oracle(c, mask)
     p = util.run_port(c, mask) if kind == "reference" else o
-    rep = util.parity_report(got, o.parts(), c.layout, c.scheme_name, c.cfg.h_tolerance)
-    print(c.scheme_name, kind, rep)
-    nd, ng, nf = g.download_counts()
-    pnd, png, pnf = p.counts()
+    rep = util.parity_report(got, o.parts(), c.layout, c.scheme_name, c.cfg.h_tolerance,
+                             time_base=c.step.time_base, alpha_max=c.cfg.viscosity_alpha_max,
+                             diffusion_beta=c.cfg.diffusion_beta)
+    print(c.scheme_name, kind, {k: v for k, v in rep.items() if k != "_clean"})
+    util.assert_parity(rep, tol, h_tolerance=c.cfg.h_tolerance)
+    # integer outputs: neighbour counts against the C restatement (== the reference's N_* counters,
+    # tests/test_oracle.py), exact wherever h is bit-identical and outside the dirty zone
     hp = host.field(p.parts(), c.layout, "h")
     hg = host.field(got, c.layout, "h")
-    same_h = np.array_equal(hp, hg)
-    if rep["flips"] == 0 and same_h:
-        # identical h everywhere -> identical neighbour sets, bit for bit
-        assert np.array_equal(nd, pnd), f"density counts differ on {(nd != pnd).sum()} particles"
-        assert np.array_equal(ng, png), f"gradient counts differ on {(ng != png).sum()} particles"
-        assert np.array_equal(nf, pnf), f"force counts differ on {(nf != pnf).sum()} particles"
-    else:
-        # last-bit h differences move a handful of kernel-edge neighbours
-        assert (nd != pnd).mean() < 5e-3 and (nf != pnf).mean() < 5e-3
-    util.assert_parity(rep, tol, h_tolerance=c.cfg.h_tolerance)
-    assert np.array_equal(host.field(got, c.layout, "depth_h"), host.field(o.parts(), c.layout, "depth_h")) or rep["flips"] > 0
+    rep_p = rep if p is o else util.parity_report(got, p.parts(), c.layout, c.scheme_name, c.cfg.h_tolerance)
+    util.assert_counts(rep_p, g.download_counts(), p.counts(), hg, hp)
+    dg, dr = host.field(got, c.layout, "depth_h"), host.field(o.parts(), c.layout, "depth_h")
+    assert np.array_equal(dg[rep["_clean"]], dr[rep["_clean"]]), "depth_h differs on clean particles"
     return rep
 
 
@@ -239,11 +235,7 @@ nd, ng, nf = g.download_counts()
 p = util.run_port(c)
 pnd, png, pnf = p.counts()
 rep = util.parity_report(got, p.parts(), c.layout, scheme, c.cfg.h_tolerance)
-same_h = np.array_equal(host.field(p.parts(), c.layout, "h"), host.field(got, c.layout, "h"))
-if rep["flips"] == 0 and same_h:
-    assert np.array_equal(nd, pnd) and np.array_equal(ng, png) and np.array_equal(nf, pnf), "counts differ"
-else:
-    assert (nd != pnd).mean() < 5e-3 and (nf != pnf).mean() < 5e-3
+util.assert_counts(rep, (nd, ng, nf), (pnd, png, pnf), host.field(got, c.layout, "h"), host.field(p.parts(), c.layout, "h"))
 util.assert_parity(rep, 1e-5, h_tolerance=c.cfg.h_tolerance)
 print("ALT_OK", rep["flips"])
 """
@@ -397,11 +389,17 @@ def test_full_size_properties_clustered128_sphenix():
     assert mom < 1e-4 * scale, (mom, scale)
     dt = g.download_timestep()
     assert np.all(dt > 0) and np.isfinite(dt).all()
-    g.upload_parts(c.parts)
-    g.run_step(abi.PHASE_ALL)
-    nd2, ng2, nf2 = g.download_counts()
-    assert np.array_equal(nd, nd2) and np.array_equal(ng, ng2) and np.array_equal(nf, nf2)
-    assert np.array_equal(host.field(g.download_parts(), lay, "h"), host.field(got, lay, "h"))
+    # determinism: a particle of a multi-level tree can be a target in several groups (atomic flush);
+    # five repetitions must reproduce counts, h and the accelerations bit for bit
+    a_hydro0 = host.field(got, lay, "a_hydro").copy()
+    for rep_i in range(5):
+        g.upload_parts(c.parts)
+        g.run_step(abi.PHASE_ALL)
+        nd2, ng2, nf2 = g.download_counts()
+        assert np.array_equal(nd, nd2) and np.array_equal(ng, ng2) and np.array_equal(nf, nf2), rep_i
+        again = g.download_parts()
+        assert np.array_equal(host.field(again, lay, "h"), host.field(got, lay, "h")), rep_i
+        assert np.array_equal(host.field(again, lay, "a_hydro"), a_hydro0), rep_i
     g.close()
 
 
@@ -526,4 +524,73 @@ def test_cutoff_on_lattice_distances(scheme, reach):
     p3 = util.run_port(c3)
     assert np.array_equal(host.field(p3.parts(), c3.layout, "h"), host.field(got, c3.layout, "h"))
     assert np.array_equal(nf, p3.counts()[2]), f"{(nf != p3.counts()[2]).sum()} force counts differ"
+    g.close()
+
+
+@pytest.mark.parametrize("scheme,with_velocity", (("gadget2", False), ("gadget2", True), ("sphenix", True)))
+def test_sedov64_vs_reference(scheme, with_velocity):
+    """BASELINE config 2's own initial conditions (bench.py's generator: Sedov blast
+    on a +-0.1 jittered lattice, E0 in the 15 central particles, P0 = 1e-6) at 64^3
+    against the unmodified reference: the blast centre has pressure contrasts of
+    1e11 and the h the ghost finds there. The pristine IC has v = 0 (viscosity,
+    u_dt, h_dt, div_v, rot_v identically zero), so the second variant adds the
+    radial velocity field of an expanding blast (v = 0.5 r_hat exp(-r^2 / 0.02)):
+    all viscous terms, the Balsara switch and (SPHENIX) the alpha evolution are
+    then exercised on the benchmarked workload too."""
+    ic = host.sedov_box(64, abi.SCHEMES[scheme])
+    if with_velocity:
+        d = ic["x"] - 0.5
+        r2 = (d * d).sum(axis=1)
+        ic["v"] = (0.5 * d / np.sqrt(np.maximum(r2, 1e-12))[:, None] * np.exp(-r2 / 0.02)[:, None]).astype(np.float32)
+    c = util.make_case(scheme, ic, host.default_top_grid(64))
+    g = util.run_gpu(c)
+    rep = _check(c, g)
+    assert rep["n"] == 64 ** 3
+    if with_velocity:
+        got = g.download_parts()
+        assert np.abs(host.field(got, c.layout, "h_dt")).max() > 0
+    g.close()
+
+
+def test_flip_rate_against_the_references_own():
+    """the flip allowance is tied to what the reference does
+    to ITSELF. Same 64^3 box: (a) the reference against the reference with the
+    particles permuted inside its leaves, (b) the GPU against the reference. The
+    GPU's flips must stay within twice the reference's own (+5 for Poisson noise
+    on counts of order ten), and both dirty zones are a few per cent of the box."""
+    from oracle import ref
+    scheme = "gadget2"
+    if not ref.available(scheme):
+        pytest.skip("oracle/_ref not present")
+    ic = host.jittered_box(64, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.03, seed=23)
+    c = util.make_case(scheme, ic, host.default_top_grid(64))
+    mask = abi.PHASE_SORT | abi.PHASE_DENSITY | abi.PHASE_GHOST
+    rep_ref = util.reference_self_flips(c, mask=mask, threads=4)
+    g = util.run_gpu(c, mask)
+    o, kind = util.run_oracle(c, mask)
+    rep_gpu = util.parity_report(g.download_parts(), o.parts(), c.layout, scheme)
+    print("reference self flips", rep_ref["flips"], "dirty", rep_ref["dirty_frac"], "| GPU flips", rep_gpu["flips"], "dirty",
+          rep_gpu["dirty_frac"])
+    assert rep_gpu["flips"] <= 2 * rep_ref["flips"] + 5, (rep_gpu["flips"], rep_ref["flips"])
+    assert rep_gpu["flip_max"] <= 2.5e-4 and rep_ref["flip_max"] <= 2.5e-4
+    assert rep_gpu["dirty_frac"] <= 0.1
+    g.close()
+
+
+def test_gradient_list_follows_the_ghost():
+    """the gradient loop's recursion evaluates
+    cell_can_recurse_in_subpair/subself_hydro_task (cell.h:951,992) on the
+    h_max_active the ghost just RAISED. Strongly clustered box whose initial h is 40 % too
+    small: the ghost grows h across the dmin/2 thresholds of the split cells, so
+    particles change depth_h and pairs move to coarser levels. The library must
+    notice (k_pred_bits), rebuild the gradient worklist, and reproduce the
+    reference's gradient neighbour counts and v_sig / laplace_u."""
+    ic = host.clustered_box(32, abi.SCHEME_SPHENIX, seed=2025, sigma=2.5)
+    ic["h"] = (ic["h"] * np.float32(0.6)).astype(np.float32)
+    c = util.make_case("sphenix", ic, (3, 3, 3))
+    assert c.tree.cells["split"].any()
+    g = util.run_gpu(c)
+    st = g.stats()
+    _check(c, g)
+    assert st.gradient_list_rebuilds >= 1, "the test did not move a recursion predicate: strengthen it"
     g.close()

@@ -23,7 +23,7 @@ def golden_layout(variant):
 def make_config(scheme, layout, rank=0, nranks=1, h_tolerance=1e-4, max_iter=30, h_max=1e10,
                 dim=(1.0, 1.0, 1.0)):
     cfg = abi.Config()
-    cfg.abi_version = 1
+    cfg.abi_version = abi.ABI_VERSION
     cfg.scheme = scheme
     cfg.device = 0
     cfg.periodic = 1
@@ -104,36 +104,60 @@ def compare_fields(got_u8, ref_u8, layout, names, rtol, report=None, floors=None
 #    (runner_ghost.c:1388). Two correct float summation orders can land on
 #    different sides of that test for a particle, which then stops one Newton
 #    step earlier or later ("flip": h differs by < h_tolerance, not by 1e-7).
-#    The reference itself is not reproducible across thread schedules in this
-#    respect. Flipped particles are counted (must be rare and within
-#    h_tolerance) and they and everything inside their kernel support are
-#    excluded from the 1e-5 comparisons.
-#  * a_hydro, u_dt, h_dt are sums of ~50 signed pair terms that cancel almost
-#    completely in near-uniform gas (|a| ~ 0.7 % of the sum of |terms|). The
-#    error is therefore measured against max(|ref|, 1e-2 * gross) where gross
-#    is the size of the un-cancelled pair sum, 48 m (P/rho^2) 2 / h^4 -- the
-#    "ignore-below" column of the reference's tests/difffloat.py.
+#    The reference ITSELF does this when only the order of the particles inside
+#    its leaf cells changes (tests/test_oracle.py::
+#    test_reference_flips_under_leaf_permutation measures its rate, ~5e-5 per
+#    particle). Flipped particles are counted, bounded against that rate, and
+#    they and everything inside their kernel support ("dirty zone") are taken
+#    out of the 1e-5 comparison; inside the dirty zone looser, finite bars hold
+#    (h within 2.5 h_tolerance, a_hydro within 5e-4 of the un-cancelled sum),
+#    the dirty fraction itself is bounded, and integer counts are compared
+#    exactly on every clean particle.
+#  * a_hydro, u_dt, h_dt, div_v, laplace_u, rho_dh are sums of ~50 signed pair
+#    terms that cancel almost completely in near-uniform gas (|a| ~ 0.7 % of the
+#    sum of |terms|). Their error is therefore measured against max(|ref|,
+#    1e-2 * gross) where gross is the size of the un-cancelled pair sum -- the
+#    "ignore-below" column of the reference's tests/difffloat.py; 1e-5 of
+#    1e-2 * gross is ~2 ulp of the un-cancelled sum. Quantities derived from
+#    such sums (balsara, f, div_v_dt, the SPHENIX alphas) get the floor of the
+#    underlying sum times their sensitivity to it.
 # ---------------------------------------------------------------------------
-def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None):
+KGAMMA = 1.825742
+
+
+def _box_of(x):
+    return np.maximum(np.ceil(x.max(axis=0) - 1e-9), 1.0)
+
+
+def dirty_zone(x, flip, reach):
+    """Particles within `reach` of a flipped one (periodic box of integer size)."""
+    from scipy.spatial import cKDTree
+    n = x.shape[0]
+    dirty = np.zeros(n, bool)
+    if flip.any():
+        box = _box_of(x)
+        xm = np.mod(x, box)
+        xm = np.where(xm >= box, 0.0, xm)
+        tree = cKDTree(xm, boxsize=box)
+        for i in np.nonzero(flip)[0]:
+            dirty[tree.query_ball_point(xm[i], reach)] = True
+    return dirty
+
+
+def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, time_base=1e-6,
+                  alpha_max=2.0, diffusion_beta=1.0):
     """only: boolean mask of the particles whose fields are compared (flips are
     detected on all of them: a flipped foreign neighbour dirties local ones)."""
-    from scipy.spatial import cKDTree
     f = lambda a, n: host.field(a, layout, n).astype(np.float64)  # noqa: E731
     hg, hr = f(got, "h"), f(ref, "h")
     herr = np.abs(hg - hr) / hr
     flip = herr > 2e-6
     x = host.field(ref, layout, "x")
     n = hr.size
-    dirty = np.zeros(n, bool)
-    if flip.any():
-        box = np.maximum(x.max(axis=0), 1.0)
-        tree = cKDTree(np.mod(x, 1.0), boxsize=1.0) if box.max() <= 1.0 else cKDTree(x)
-        reach = 2.0 * 1.825742 * max(hr.max(), hg.max())
-        for i in np.nonzero(flip)[0]:
-            dirty[tree.query_ball_point(np.mod(x[i], 1.0) if box.max() <= 1.0 else x[i], reach)] = True
-    clean = ~dirty
-    if only is not None:
-        clean = clean & np.asarray(only, bool)
+    dirty = dirty_zone(x, flip, 2.0 * KGAMMA * max(hr.max(), hg.max()))
+    sel = np.ones(n, bool) if only is None else np.asarray(only, bool)
+    clean = ~dirty & sel
+    dz = dirty & sel
     rep = {"n": n, "flips": int(flip.sum()), "flip_max": float(herr.max()), "dirty": int(dirty.sum())}
     rho = f(ref, "rho")
     m = f(ref, "mass")
@@ -143,10 +167,13 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None):
     gross = 48.0 * m * por2 * 2.0 / hr ** 4
     cs = f(ref, "soundspeed")
 
-    def rel(name, floor=None):
+    def err(name, floor=None):
         g, r = f(got, name), f(ref, name)
         den = np.abs(r) if floor is None else np.maximum(np.abs(r), floor)
-        e = np.abs(g - r) / np.maximum(den, 1e-300)
+        return np.abs(g - r) / np.maximum(den, 1e-300)
+
+    def rel(name, floor=None):
+        e = err(name, floor)
         return float(e[clean].max()) if clean.any() else 0.0
 
     rep["h"] = float(herr[clean].max()) if clean.any() else 0.0
@@ -168,6 +195,52 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None):
     vs = "v_sig"
     if has(layout, vs):
         rep[vs] = rel(vs)
+
+    # ---- the remaining outputs of the path (they persist into the next step) ----
+    # velocity / thermal gradient scales of the box: |dv| over a kernel ~ G h, so the un-cancelled
+    # sums behind div_v (laplace_u) are ~G (~Gu / h)
+    box = _box_of(x)
+    v = host.field(ref, layout, "v").astype(np.float64).reshape(-1, 3)
+    G = 2.0 * np.pi * float(np.sqrt(((v - v.mean(axis=0)) ** 2).sum(axis=1).mean())) / float(box.min())
+    tb = host.field(ref, layout, "time_bin").astype(np.int64)
+    dt_alpha = np.where(tb <= 0, 0.0, 2.0 ** (tb + 1) * time_base)
+    # Floors of the outputs derived from cancelling sums: FLOOR_FRAC x the un-cancelled scale, i.e. the
+    # 1e-5 bar is 5e-6 of that scale. Calibrated on the reference itself: with nothing changed but the
+    # order of the particles inside its leaves it moves these fields by up to 1.5e-6 of the scale
+    # (accumulated rounding of a ~50-term FP32 sum, worst particle of 1e4..1e5) and must pass this same
+    # metric at 5e-6 (tests/test_oracle.py::test_reference_flips_under_leaf_permutation).
+    FLOOR_FRAC = 0.5
+    floor_div = np.full(n, FLOOR_FRAC * G)
+    # balsara = |div| / (|div| + |curl| + 1e-4 c/h), a switch in [0, 1] whose sensitivity to the
+    # cancelling div_v is 1 / (|div| + |curl|), unbounded where the flow is locally uniform: absolute
+    rep["balsara"] = rel("balsara", 1.0)
+    # grad-h term: rho_dh, wcount_dh are sums of (3 W + u W') terms, ~3 rho / h un-cancelled
+    rep["f"] = rel("f", FLOOR_FRAC if scheme_name == "gadget2" else FLOOR_FRAC * m)
+    # limiter_data.min_ngb_time_bin: an integer (timestep_limiter_iact.h:41-55)
+    mg = host.field(got, layout, "min_ngb_time_bin")
+    mr = host.field(ref, layout, "min_ngb_time_bin")
+    rep["min_ngb_time_bin_mismatch"] = int((mg != mr)[clean].sum())
+    if scheme_name == "sphenix":
+        u = f(ref, "u")
+        Gu = 2.0 * np.pi * float(u.std()) / float(box.min())
+        floor_lap = 2.0 * FLOOR_FRAC * Gu / hr  # Gu (from the variance of u) underestimates |grad u| by ~2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            floor_div_dt = np.where(dt_alpha > 0, floor_div / dt_alpha, 0.0)
+        rep["div_v"] = rel("div_v", floor_div)
+        rep["div_v_previous_step"] = rel("div_v_previous_step", floor_div)
+        rep["div_v_dt"] = rel("div_v_dt", floor_div_dt)
+        rep["laplace_u"] = rel("laplace_u", floor_lap)
+        # alpha_loc = alpha_max S / (c^2 + S), S = (h gamma)^2 max(0, -div_v_dt): d alpha <= alpha_max (h gamma)^2 / c^2 d(div_v_dt)
+        rep["visc_alpha"] = rel("visc_alpha", 1e-3 + alpha_max * (hr * KGAMMA) ** 2 / np.maximum(cs, 1e-300) ** 2 * floor_div_dt)
+        # alpha_diff += dt (beta h gamma laplace_u / sqrt(u) - ...)
+        rep["diff_alpha"] = rel("diff_alpha", dt_alpha * diffusion_beta * hr * KGAMMA / np.sqrt(np.maximum(u, 1e-300)) * floor_lap)
+        rep["alpha_visc_max_ngb"] = rel("alpha_visc_max_ngb")
+    # ---- finite bars INSIDE the dirty zone ----
+    rep["dirty_frac"] = float(dz.sum()) / max(1, int(sel.sum()))
+    rep["dirty_h"] = float(herr[dz].max()) if dz.any() else 0.0
+    rep["dirty_a_hydro"] = float((da / np.maximum(np.maximum(na, gross), 1e-300))[dz].max()) if dz.any() else 0.0
+    rep["dirty_rho"] = float(err("rho")[dz].max()) if dz.any() else 0.0
+    rep["_clean"] = clean
     return rep
 
 
@@ -175,12 +248,48 @@ def has(layout, name):
     return host.has_field(layout, name)
 
 
-def assert_parity(rep, tol=1e-5, max_flip_frac=2e-3, h_tolerance=1e-4):
-    bad = {k: v for k, v in rep.items()
-           if k not in ("n", "flips", "flip_max", "dirty") and not (v <= tol)}
-    assert not bad, f"fields beyond {tol}: {bad} (report {rep})"
-    assert rep["flips"] <= max(2, int(max_flip_frac * rep["n"])), rep
-    assert rep["flip_max"] <= 2.5 * h_tolerance, rep
+_META = ("n", "flips", "flip_max", "dirty", "dirty_frac", "dirty_h", "dirty_a_hydro", "dirty_rho",
+         "min_ngb_time_bin_mismatch", "_clean")
+# the reference against itself with the particles permuted inside its leaves flips ~5e-5 of the particles
+# (test_reference_flips_under_leaf_permutation: 2 of 32 768, 3 of 110 592); the bound allows 4x that + 3
+REF_FLIP_RATE = 5e-5
+
+
+def assert_parity(rep, tol=1e-5, max_flip_frac=4 * REF_FLIP_RATE, h_tolerance=1e-4, max_dirty_frac=0.1):
+    bad = {k: v for k, v in rep.items() if k not in _META and not (v <= tol)}
+    assert not bad, f"fields beyond {tol}: {bad} (report { {k: v for k, v in rep.items() if k != '_clean'} })"
+    assert rep["min_ngb_time_bin_mismatch"] == 0, rep["min_ngb_time_bin_mismatch"]
+    assert rep["flips"] <= 3 + int(max_flip_frac * rep["n"]), (rep["flips"], rep["n"])
+    assert rep["flip_max"] <= 2.5 * h_tolerance, rep["flip_max"]
+    # the 1e-5 comparison must cover (almost) the whole box, and the excluded zone is bounded too
+    assert rep["dirty_frac"] <= max_dirty_frac, rep["dirty_frac"]
+    assert rep["dirty_h"] <= 2.5 * h_tolerance and rep["dirty_rho"] <= 10 * h_tolerance, (rep["dirty_h"], rep["dirty_rho"])
+    assert rep["dirty_a_hydro"] <= 5e-4, rep["dirty_a_hydro"]
+
+
+def assert_counts(rep, got_counts, want_counts, h_got, h_ref, names=("density", "gradient", "force")):
+    """Integer neighbour counts outside the dirty zone. Where the particle's own
+    h is bit-identical on both sides the density and gradient counts (relation
+    r < h_i gamma) must be EXACT. Where h differs in its last bits (< 2e-6
+    relative, not a flip) a neighbour sitting within that sliver of the kernel
+    edge legitimately moves: probability ~ 3 N_ngb dh/h ~ 1.5e-5 per particle,
+    so at most 3 + 1e-4 n such particles may differ (force, whose relation
+    r < max(h_i, h_j) gamma also sees the neighbours' last bits: 3 + 2e-4 n)."""
+    clean = rep["_clean"]
+    same = np.asarray(h_got) == np.asarray(h_ref)
+    n = clean.size
+    for nm, g, w in zip(names, got_counts, want_counts):
+        if g is None or w is None:
+            continue
+        diff = (g != w) & clean
+        if nm != "force":
+            bad = diff & same
+            assert not bad.any(), f"{nm} counts differ on {int(bad.sum())} clean particles with bit-identical h"
+            assert int(diff.sum()) <= 3 + int(1e-4 * n), f"{nm} counts differ on {int(diff.sum())} clean particles"
+        else:
+            if same.all():
+                assert not diff.any(), f"force counts differ on {int(diff.sum())} clean particles (h identical everywhere)"
+            assert int(diff.sum()) <= 3 + int(2e-4 * n), f"force counts differ on {int(diff.sum())} clean particles"
 
 
 def run_oracle(c, mask=None, threads=4, variant=None):
@@ -195,6 +304,45 @@ def run_oracle(c, mask=None, threads=4, variant=None):
     o = port.Port(c.scheme_name, c.cfg, c.step, c.tree.cells, c.tree.top, c.parts)
     o.run(mask)
     return o, "port"
+
+
+def permute_inside_leaves(c, seed=5):
+    """The same particles in a different (equally valid) memory order: shuffled
+    inside every leaf cell. Returns (parts, perm) with parts[k] = c.parts[perm[k]];
+    cell ranges are unchanged. Only the ORDER of the reference's sums changes."""
+    size = c.layout.size
+    rows = c.parts.reshape(-1, size)
+    cells = c.tree.cells
+    rng = np.random.default_rng(seed)
+    p = np.arange(rows.shape[0])
+    for leaf in np.nonzero(cells["split"] == 0)[0]:
+        f, n = int(cells["first_part"][leaf]), int(cells["count"][leaf])
+        p[f:f + n] = f + rng.permutation(n)
+    return np.ascontiguousarray(rows[p]).reshape(-1), p
+
+
+def unpermute(parts, perm, size):
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    return np.ascontiguousarray(parts.reshape(-1, size)[inv]).reshape(-1)
+
+
+def reference_self_flips(c, mask=None, threads=1):
+    """Runs the reference on c and on the leaf-permuted copy of c; returns the
+    parity report of one against the other (the reference's own irreproducibility
+    under a change of summation order)."""
+    from oracle import ref
+    mask = abi.PHASE_ALL if mask is None else mask
+    outs = []
+    parts2, perm = permute_inside_leaves(c)
+    for parts in (c.parts, parts2):
+        o = ref.Reference(c.scheme_name, c.cfg, c.step, c.tree.cells, c.tree.top, parts)
+        o.run(mask, threads=threads)
+        outs.append(o.parts().copy())
+        o.close()
+    b = unpermute(outs[1], perm, c.layout.size)
+    return parity_report(b, outs[0], c.layout, c.scheme_name, c.cfg.h_tolerance, time_base=c.step.time_base,
+                         alpha_max=c.cfg.viscosity_alpha_max, diffusion_beta=c.cfg.diffusion_beta)
 
 
 def run_port(c, mask=None):
