@@ -110,6 +110,9 @@ typedef struct port {
   float *alpha, *alpha_diff, *div_v_prev, *div_v_dt, *laplace_u, *alpha_max_ngb;
   signed char *time_bin, *depth_h, *min_ngb;
   int *nd, *ng, *nf;
+  /* un-cancelled sums (sum of |pair terms|) behind the cancelling outputs: the floors of the parity
+   * metric (tests/util.py), carried through the same finalising factors as the sums themselves */
+  float *g_a, *g_u, *g_hdt, *g_div, *g_rho_dh, *g_lap;
   int *leaf_of; /* leaf cell index of each particle */
   int ghost_iterations;
   int ghost_failed;
@@ -169,6 +172,8 @@ static inline void iact_density(port_t *s, float r2, const float dx[3], float hi
   dv[2] = s->v[3 * i + 2] - s->v[3 * j + 2];
   const float dvdr = dv[0] * dx[0] + dv[1] * dx[1] + dv[2] * dx[2];
   s->div_v[i] -= faci * dvdr;
+  s->g_div[i] += fabsf(faci * dvdr);
+  s->g_rho_dh[i] += fabsf(mj * (hydro_dimension * wi + ui * wi_dx));
   curlvr[0] = dv[1] * dx[2] - dv[2] * dx[1];
   curlvr[1] = dv[2] * dx[0] - dv[0] * dx[2];
   curlvr[2] = dv[0] * dx[1] - dv[1] * dx[0];
@@ -199,6 +204,7 @@ static inline void iact_gradient(port_t *s, float r2, const float dx[3], float h
   kernel_deval(ui, &wi, &wi_dx);
   const float delta_u_factor = (s->u[i] - s->u[j]) * r_inv;
   s->laplace_u[i] += s->m[j] * delta_u_factor * wi_dx / s->rho[j];
+  s->g_lap[i] += fabsf(s->m[j] * delta_u_factor * wi_dx / s->rho[j]);
   const float alpha_j = s->alpha[j];
   s->alpha_max_ngb[i] = pmax(s->alpha_max_ngb[i], alpha_j);
   s->ng[i]++;
@@ -259,6 +265,9 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
   s->u_dt[i] += du_dt_i * mj;
   s->h_dt[i] -= mj * dvdr * r_inv / rhoj * wi_dr * f_ij;
   s->v_sig[i] = pmax(s->v_sig[i], v_sig);
+  s->g_a[i] += fabsf(mj * acc) * r;
+  s->g_u[i] += (fabsf(sph_du_term_i) + fabsf(visc_du_term)) * mj;
+  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr * f_ij);
 #elif PORT_SCHEME == SCH_GADGET2
   const float f_i = s->f[i];
   const float f_j = s->f[j];
@@ -276,6 +285,11 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
   s->h_dt[i] -= mj * dvdr * r_inv / rhoj * wi_dr;
   s->v_sig[i] = pmax(s->v_sig[i], v_sig);
   s->u_dt[i] += mj * visc_term * dvdr_Hubble; /* entropy_dt */
+  s->g_a[i] += fabsf(mj * acc) * r;
+  /* entropy_dt only collects the viscous heating; the scale of the thermal energy equation it belongs
+   * to also holds the adiabatic term P/rho^2 dv.dx W'/r (x2: hydro_end_force halves the sum) */
+  s->g_u[i] += fabsf(mj * visc_term * dvdr_Hubble) + 2.f * fabsf(mj * f_i * P_over_rho2_i * dvdr * r_inv * wi_dr);
+  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr);
 #else /* SPHENIX */
   const float mi = s->m[i];
   const float pressurei = s->P[i];
@@ -306,6 +320,9 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
   const float du_dt_i = sph_du_term_i + visc_du_term + diff_du_term;
   s->u_dt[i] += du_dt_i * mj;
   s->h_dt[i] -= mj * dvdr * r_inv / rhoj * wi_dr;
+  s->g_a[i] += fabsf(mj * acc) * r;
+  s->g_u[i] += (fabsf(sph_du_term_i) + fabsf(visc_du_term) + fabsf(diff_du_term)) * mj;
+  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr);
 #endif
   /* runner_iact_nonsym_timebin */
   if (s->time_bin[j] > 0) s->min_ngb[i] = pmin(s->min_ngb[i], s->time_bin[j]);
@@ -687,6 +704,7 @@ static void init_part(port_t *s, long long p) {
   s->rho[p] = 0.f;
   s->rho_dh[p] = 0.f;
   s->div_v[p] = 0.f;
+  s->g_div[p] = s->g_rho_dh[p] = s->g_lap[p] = 0.f;
   s->rot_v[3 * p] = s->rot_v[3 * p + 1] = s->rot_v[3 * p + 2] = 0.f;
 #if PORT_SCHEME == SCH_SPHENIX
   s->laplace_u[p] = 0.f;
@@ -706,6 +724,7 @@ static void end_density(port_t *s, long long p) {
   s->wcount_dh[p] -= hydro_dimension * kernel_root;
   s->rho[p] *= h_inv_dim;
   s->rho_dh[p] *= h_inv_dim_plus_one;
+  s->g_rho_dh[p] = (s->g_rho_dh[p] + hydro_dimension * s->m[p] * kernel_root) * h_inv_dim_plus_one;
   s->wcount[p] *= h_inv_dim;
   s->wcount_dh[p] *= h_inv_dim_plus_one;
   const float rho_inv = 1.f / s->rho[p];
@@ -713,6 +732,7 @@ static void end_density(port_t *s, long long p) {
   s->rot_v[3 * p + 0] *= h_inv_dim_plus_one * a_inv2 * rho_inv;
   s->rot_v[3 * p + 1] *= h_inv_dim_plus_one * a_inv2 * rho_inv;
   s->rot_v[3 * p + 2] *= h_inv_dim_plus_one * a_inv2 * rho_inv;
+  s->g_div[p] *= h_inv_dim_plus_one * rho_inv * a_inv2;
 #if PORT_SCHEME == SCH_SPHENIX
   s->div_v[p] *= h_inv_dim_plus_one * rho_inv * a_inv2;
   s->div_v[p] += s->step.H * hydro_dimension;
@@ -731,6 +751,7 @@ static void has_no_neighbours(port_t *s, long long p) {
   s->rho_dh[p] = 0.f;
   s->wcount_dh[p] = 0.f;
   s->div_v[p] = 0.f;
+  s->g_div[p] = s->g_rho_dh[p] = s->g_lap[p] = 0.f;
   s->rot_v[3 * p] = s->rot_v[3 * p + 1] = s->rot_v[3 * p + 2] = 0.f;
 #if PORT_SCHEME == SCH_SPHENIX
   s->v_sig[p] = 0.f;
@@ -779,6 +800,7 @@ static void extra_ghost_part(port_t *s, long long p, float dt_alpha) {
   const float h_inv_dim = h_inv * h_inv * h_inv;
   const float h_inv_dim_plus_one = h_inv_dim * h_inv;
   s->laplace_u[p] *= 2.f * h_inv_dim_plus_one;
+  s->g_lap[p] *= 2.f * h_inv_dim_plus_one;
 
   const float a = s->step.a;
   const float kernel_support_physical = s->h[p] * a * kernel_gamma;
@@ -826,6 +848,7 @@ static void extra_ghost_part(port_t *s, long long p, float dt_alpha) {
   s->a[3 * p] = s->a[3 * p + 1] = s->a[3 * p + 2] = 0.f;
   s->u_dt[p] = 0.f;
   s->h_dt[p] = 0.f;
+  s->g_a[p] = s->g_u[p] = s->g_hdt[p] = 0.f;
   s->min_ngb[p] = num_time_bins + 1;
   s->nf[p] = 0;
 }
@@ -888,6 +911,7 @@ static void prepare_force(port_t *s, long long p) {
   s->a[3 * p] = s->a[3 * p + 1] = s->a[3 * p + 2] = 0.f;
   s->u_dt[p] = 0.f;
   s->h_dt[p] = 0.f;
+  s->g_a[p] = s->g_u[p] = s->g_hdt[p] = 0.f;
   s->v_sig[p] = 2.f * s->cs[p];
   s->nf[p] = 0;
 }
@@ -1209,6 +1233,8 @@ port_t *port_create(const swiftgpu_config *cfg, const swiftgpu_step *step,
   s->cs = falloc(n); s->balsara = falloc(n); s->v_sig = falloc(n); s->h_dt = falloc(n);
   s->alpha = falloc(n); s->alpha_diff = falloc(n); s->div_v_prev = falloc(n);
   s->div_v_dt = falloc(n); s->laplace_u = falloc(n); s->alpha_max_ngb = falloc(n);
+  s->g_a = falloc(n); s->g_u = falloc(n); s->g_hdt = falloc(n); s->g_div = falloc(n);
+  s->g_rho_dh = falloc(n); s->g_lap = falloc(n);
   s->time_bin = (signed char *)calloc(n, 1);
   s->depth_h = (signed char *)calloc(n, 1);
   s->min_ngb = (signed char *)calloc(n, 1);
@@ -1259,6 +1285,7 @@ void port_destroy(port_t *s) {
   free(s->rot_v); free(s->m); free(s->h); free(s->u); free(s->u_dt); free(s->rho);
   free(s->wcount); free(s->wcount_dh); free(s->rho_dh); free(s->div_v); free(s->f);
   free(s->P); free(s->cs); free(s->balsara); free(s->v_sig); free(s->h_dt);
+  free(s->g_a); free(s->g_u); free(s->g_hdt); free(s->g_div); free(s->g_rho_dh); free(s->g_lap);
   free(s->alpha); free(s->alpha_diff); free(s->div_v_prev); free(s->div_v_dt);
   free(s->laplace_u); free(s->alpha_max_ngb); free(s->time_bin); free(s->depth_h);
   free(s->min_ngb); free(s->nd); free(s->ng); free(s->nf);
@@ -1307,11 +1334,13 @@ int port_run(port_t *s, unsigned mask) {
         const long long p = c->first_part + k;
         if (!part_active(s, p)) continue;
         s->h_dt[p] *= s->h[p] * hydro_dimension_inv;
+        s->g_hdt[p] *= s->h[p] * hydro_dimension_inv;
 #if PORT_SCHEME == SCH_GADGET2
         /* 0.5 * gas_entropy_from_internal_energy(rho, entropy_dt) */
         const float cbrt_inv = 1.f / cbrtf(s->rho[p]);
         const float pow_mgm1 = cbrt_inv * cbrt_inv; /* rho^-(gamma-1) */
         s->u_dt[p] = 0.5f * (hydro_gamma_minus_one * s->u_dt[p] * pow_mgm1);
+        s->g_u[p] = 0.5f * (hydro_gamma_minus_one * s->g_u[p] * pow_mgm1);
 #endif
       }
     }
@@ -1377,3 +1406,16 @@ void port_get_counts(const port_t *s, int *nd, int *ng, int *nf) {
   if (nf) memcpy(nf, s->nf, sizeof(int) * s->n);
 }
 int port_ghost_iterations(const port_t *s) { return s->ghost_iterations; }
+/* The un-cancelled sums (sum over neighbours of |pair term|, finalised with the
+ * same factors as the sums) of a_hydro (norm), u_dt | entropy_dt, h_dt, div_v,
+ * rho_dh and laplace_u: what the parity metric floors its relative errors with. */
+void port_get_gross(const port_t *s, float *a, float *u, float *hdt, float *div, float *rho_dh,
+                    float *lap) {
+  const size_t b = sizeof(float) * (size_t)s->n;
+  if (a) memcpy(a, s->g_a, b);
+  if (u) memcpy(u, s->g_u, b);
+  if (hdt) memcpy(hdt, s->g_hdt, b);
+  if (div) memcpy(div, s->g_div, b);
+  if (rho_dh) memcpy(rho_dh, s->g_rho_dh, b);
+  if (lap) memcpy(lap, s->g_lap, b);
+}

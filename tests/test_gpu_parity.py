@@ -25,7 +25,7 @@ def _check(c, g, mask=abi.PHASE_ALL, tol=TOL):
     p = util.run_port(c, mask) if kind == "reference" else o
     rep = util.parity_report(got, o.parts(), c.layout, c.scheme_name, c.cfg.h_tolerance,
                              time_base=c.step.time_base, alpha_max=c.cfg.viscosity_alpha_max,
-                             diffusion_beta=c.cfg.diffusion_beta)
+                             diffusion_beta=c.cfg.diffusion_beta, gross=p.gross() if mask == abi.PHASE_ALL else None)
     print(c.scheme_name, kind, {k: v for k, v in rep.items() if k != "_clean"})
     util.assert_parity(rep, tol, h_tolerance=c.cfg.h_tolerance)
     # integer outputs: neighbour counts against the C restatement (== the reference's N_* counters,

@@ -92,7 +92,7 @@ def test_port_matches_reference_full_step(scheme):
     o, kind = util.run_oracle(c)
     assert kind == "reference"
     p = util.run_port(c)
-    rep = util.parity_report(p.parts(), o.parts(), c.layout, scheme)
+    rep = util.parity_report(p.parts(), o.parts(), c.layout, scheme, gross=p.gross())
     util.assert_parity(rep)
     assert np.array_equal(host.field(p.parts(), c.layout, "depth_h"), host.field(o.parts(), c.layout, "depth_h"))
     oc, pc = o.cells(), p.cells()
@@ -162,7 +162,7 @@ def test_port_matches_reference_active_subset(scheme):
     tb[:] = ic["time_bin"][c.tree.perm]
     o, _ = util.run_oracle(c)
     p = util.run_port(c)
-    rep = util.parity_report(p.parts(), o.parts(), c.layout, scheme)
+    rep = util.parity_report(p.parts(), o.parts(), c.layout, scheme, gross=p.gross())
     util.assert_parity(rep)
     inactive = tb > 1
     size = c.layout.size
@@ -177,7 +177,7 @@ def test_port_matches_reference_clustered_multilevel():
     assert c.tree.cells["split"].any()
     o, _ = util.run_oracle(c)
     p = util.run_port(c)
-    rep = util.parity_report(p.parts(), o.parts(), c.layout, "sphenix")
+    rep = util.parity_report(p.parts(), o.parts(), c.layout, "sphenix", gross=p.gross())
     util.assert_parity(rep)
 
 

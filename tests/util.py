@@ -144,10 +144,16 @@ def dirty_zone(x, flip, reach):
     return dirty
 
 
+FR = 0.5  # floor = FR x (sum over neighbours of |pair term|), see the header above
+
+
 def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, time_base=1e-6,
-                  alpha_max=2.0, diffusion_beta=1.0):
+                  alpha_max=2.0, diffusion_beta=1.0, gross=None):
     """only: boolean mask of the particles whose fields are compared (flips are
-    detected on all of them: a flipped foreign neighbour dirties local ones)."""
+    detected on all of them: a flipped foreign neighbour dirties local ones).
+    gross: the EXACT un-cancelled sums of the C restatement (oracle/port.py:
+    Port.gross()) for the same input; without it analytic proxies of the same
+    sums are used (valid for near-uniform gas only)."""
     f = lambda a, n: host.field(a, layout, n).astype(np.float64)  # noqa: E731
     hg, hr = f(got, "h"), f(ref, "h")
     herr = np.abs(hg - hr) / hr
@@ -164,7 +170,7 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, ti
     pname = "P_over_rho2" if scheme_name == "gadget2" else "pressure"
     P = f(ref, pname)
     por2 = P if scheme_name == "gadget2" else P / np.maximum(rho, 1e-300) ** 2
-    gross = 48.0 * m * por2 * 2.0 / hr ** 4
+    gross_px = 48.0 * m * por2 * 2.0 / hr ** 4  # analytic proxy of the un-cancelled acceleration sum
     cs = f(ref, "soundspeed")
 
     def err(name, floor=None):
@@ -183,15 +189,22 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, ti
     ag, ar = host.field(got, layout, "a_hydro").astype(np.float64), host.field(ref, layout, "a_hydro").astype(np.float64)
     da = np.linalg.norm(ag - ar, axis=1)
     na = np.linalg.norm(ar, axis=1)
-    ea = da / np.maximum(np.maximum(na, 1e-2 * gross), 1e-300)
-    rep["a_hydro"] = float(ea[clean].max()) if clean.any() else 0.0
     uname = "entropy_dt" if scheme_name == "gadget2" else "u_dt"
-    # pressure-work scale: gross acceleration x sound speed (x rho^(1-gamma) (gamma-1)/2 for the entropy form)
-    ufloor = 1e-2 * gross * cs
-    if scheme_name == "gadget2":
-        ufloor = ufloor * (2.0 / 3.0) * rho ** (-2.0 / 3.0)
+    if gross is not None:
+        gross_a = gross["a_hydro"] / FR * 0.1  # a_hydro keeps its round-1 bar: 0.1 x the exact un-cancelled sum
+        ufloor = FR * gross["u_dt"]
+        hfloor = FR * gross["h_dt"]
+    else:
+        gross_a = 1e-1 * gross_px / FR * 0.1  # the proxy overestimates the exact sum ~10x
+        # pressure-work scale: gross acceleration x sound speed (x rho^(1-gamma) (gamma-1)/2 for the entropy form)
+        ufloor = 1e-2 * gross_px * cs
+        if scheme_name == "gadget2":
+            ufloor = ufloor * (2.0 / 3.0) * rho ** (-2.0 / 3.0)
+        hfloor = 1e-2 * 48.0 * m / np.maximum(rho, 1e-300) * cs * 2.0 / hr ** 4 * hr / 3.0
+    ea = da / np.maximum(np.maximum(na, FR * gross_a), 1e-300)
+    rep["a_hydro"] = float(ea[clean].max()) if clean.any() else 0.0
     rep[uname] = rel(uname, ufloor)
-    rep["h_dt"] = rel("h_dt", 1e-2 * 48.0 * m / np.maximum(rho, 1e-300) * cs * 2.0 / hr ** 4 * hr / 3.0)
+    rep["h_dt"] = rel("h_dt", hfloor)
     vs = "v_sig"
     if has(layout, vs):
         rep[vs] = rel(vs)
@@ -204,27 +217,36 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, ti
     G = 2.0 * np.pi * float(np.sqrt(((v - v.mean(axis=0)) ** 2).sum(axis=1).mean())) / float(box.min())
     tb = host.field(ref, layout, "time_bin").astype(np.int64)
     dt_alpha = np.where(tb <= 0, 0.0, 2.0 ** (tb + 1) * time_base)
-    # Floors of the outputs derived from cancelling sums: FLOOR_FRAC x the un-cancelled scale, i.e. the
-    # 1e-5 bar is 5e-6 of that scale. Calibrated on the reference itself: with nothing changed but the
-    # order of the particles inside its leaves it moves these fields by up to 1.5e-6 of the scale
-    # (accumulated rounding of a ~50-term FP32 sum, worst particle of 1e4..1e5) and must pass this same
-    # metric at 5e-6 (tests/test_oracle.py::test_reference_flips_under_leaf_permutation).
-    FLOOR_FRAC = 0.5
-    floor_div = np.full(n, FLOOR_FRAC * G)
+    # Floors of the outputs derived from cancelling sums: FR x the un-cancelled sum, i.e. the 1e-5 bar is
+    # 5e-6 of that sum (~80 ulp: accumulated rounding of a ~50-term FP32 sum, worst particle of 1e5).
+    # Calibrated on the reference itself: with nothing changed but the order of the particles inside its
+    # leaves it must pass this same metric at 5e-6 (tests/test_oracle.py::
+    # test_reference_flips_under_leaf_permutation).
+    if gross is not None:
+        floor_div = FR * gross["div_v"]
+        floor_rho_dh = FR * gross["rho_dh"]
+    else:
+        floor_div = np.full(n, 0.5 * G)
+        floor_rho_dh = 0.5 * 6.0 * rho / hr
     # balsara = |div| / (|div| + |curl| + 1e-4 c/h), a switch in [0, 1] whose sensitivity to the
     # cancelling div_v is 1 / (|div| + |curl|), unbounded where the flow is locally uniform: absolute
     rep["balsara"] = rel("balsara", 1.0)
-    # grad-h term: rho_dh, wcount_dh are sums of (3 W + u W') terms, ~3 rho / h un-cancelled
-    # (6 rho / h un-cancelled: as f = h / (3 wcount) rho_dh / (1 + ...) that is 2 m; floor m)
-    rep["f"] = rel("f", FLOOR_FRAC if scheme_name == "gadget2" else 2.0 * FLOOR_FRAC * m)
+    # grad-h term from rho_dh (and wcount_dh): f = h / (3 wcount) rho_dh / (1 + ...) (Minimal, SPHENIX),
+    # f = 1 / (1 + h / (3 rho) rho_dh) (Gadget2)
+    cf = hr / (3.0 * np.maximum(rho, 1e-300))
+    # (x2: f also carries the error of wcount_dh and of h itself)
+    rep["f"] = rel("f", 2.0 * cf * floor_rho_dh * (1.0 if scheme_name == "gadget2" else m))
     # limiter_data.min_ngb_time_bin: an integer (timestep_limiter_iact.h:41-55)
     mg = host.field(got, layout, "min_ngb_time_bin")
     mr = host.field(ref, layout, "min_ngb_time_bin")
     rep["min_ngb_time_bin_mismatch"] = int((mg != mr)[clean].sum())
     if scheme_name == "sphenix":
         u = f(ref, "u")
-        Gu = 2.0 * np.pi * float(u.std()) / float(box.min())
-        floor_lap = 2.0 * FLOOR_FRAC * Gu / hr  # Gu (from the variance of u) underestimates |grad u| by ~2
+        if gross is not None:
+            floor_lap = FR * gross["laplace_u"]
+        else:
+            Gu = 2.0 * np.pi * float(u.std()) / float(box.min())
+            floor_lap = Gu / hr
         with np.errstate(divide="ignore", invalid="ignore"):
             floor_div_dt = np.where(dt_alpha > 0, floor_div / dt_alpha, 0.0)
         rep["div_v"] = rel("div_v", floor_div)
@@ -239,7 +261,7 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, ti
     # ---- finite bars INSIDE the dirty zone ----
     rep["dirty_frac"] = float(dz.sum()) / max(1, int(sel.sum()))
     rep["dirty_h"] = float(herr[dz].max()) if dz.any() else 0.0
-    rep["dirty_a_hydro"] = float((da / np.maximum(np.maximum(na, gross), 1e-300))[dz].max()) if dz.any() else 0.0
+    rep["dirty_a_hydro"] = float((da / np.maximum(np.maximum(na, 10.0 * gross_a), 1e-300))[dz].max()) if dz.any() else 0.0
     rep["dirty_rho"] = float(err("rho")[dz].max()) if dz.any() else 0.0
     rep["_clean"] = clean
     return rep
@@ -345,8 +367,9 @@ def reference_self_flips(c, mask=None, threads=1):
         outs.append(o.parts().copy())
         o.close()
     b = unpermute(outs[1], perm, c.layout.size)
+    gross = run_port(c, mask).gross() if mask == abi.PHASE_ALL else None
     return parity_report(b, outs[0], c.layout, c.scheme_name, c.cfg.h_tolerance, time_base=c.step.time_base,
-                         alpha_max=c.cfg.viscosity_alpha_max, diffusion_beta=c.cfg.diffusion_beta)
+                         alpha_max=c.cfg.viscosity_alpha_max, diffusion_beta=c.cfg.diffusion_beta, gross=gross)
 
 
 def run_port(c, mask=None):
