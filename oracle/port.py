@@ -27,7 +27,7 @@ def load(scheme_name):
         lib.port_get_cells.argtypes = [VP, VP]
         lib.port_get_counts.argtypes = [VP, VP, VP, VP]
         lib.port_ghost_iterations.argtypes = [VP]
-        lib.port_get_gross.argtypes = [VP] * 7
+        lib.port_get_gross.argtypes = [VP] * 10
         lib.port_kernel_deval.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.port_sub_pairs.argtypes = [C.c_int, VP, VP]
         _libs[scheme_name] = lib
@@ -68,8 +68,9 @@ class Port:
         return nd, ng, nf
 
     def gross(self):
-        """dict of the un-cancelled sums behind a_hydro, u_dt, h_dt, div_v, rho_dh, laplace_u."""
-        names = ("a_hydro", "u_dt", "h_dt", "div_v", "rho_dh", "laplace_u")
+        """dict of the un-cancelled sums behind a_hydro, u_dt, h_dt, div_v, rho_dh, laplace_u and the
+        squared kernel-noise sums of the first, second and last (swift_port.c: edge_weight)."""
+        names = ("a_hydro", "u_dt", "h_dt", "div_v", "rho_dh", "laplace_u", "a_hydro_sq", "u_dt_sq", "laplace_u_sq")
         arrs = [np.zeros(self.nparts, np.float32) for _ in names]
         self.lib.port_get_gross(self.h, *[a.ctypes.data for a in arrs])
         return dict(zip(names, (a.astype(np.float64) for a in arrs)))

@@ -113,6 +113,7 @@ typedef struct port {
   /* un-cancelled sums (sum of |pair terms|) behind the cancelling outputs: the floors of the parity
    * metric (tests/util.py), carried through the same finalising factors as the sums themselves */
   float *g_a, *g_u, *g_hdt, *g_div, *g_rho_dh, *g_lap;
+  float *g2_a, *g2_u, *g2_lap; /* squares: kernel-evaluation noise, see edge_weight() */
   int *leaf_of; /* leaf cell index of each particle */
   int ghost_iterations;
   int ghost_failed;
@@ -149,6 +150,21 @@ static inline void kernel_deval(float u, float *W, float *dW_dx) {
 void port_kernel_deval(float u, float *w, float *dw) { kernel_deval(u, w, dw); }
 
 /* ---------------- pair interactions (non-symmetric) ---------------- */
+
+/* Kernel-evaluation noise of a pair term, for the sums in which ONE neighbour can dominate (a_hydro,
+ * u_dt, laplace_u: weighted by the neighbour's pressure / energy). kernel_deval (kernel_hydro.h:257-285)
+ * evaluates the outer branch of the cubic spline, w' = -3 (1-x)^2, by Horner's rule on the EXPANDED
+ * coefficients {-1, 3, -3, 1} in FP32: the absolute error is ~4e-7 of the coefficient scale whatever x
+ * is, i.e. 1.3e-7 / (1-x)^2 RELATIVE to w' - 2e-4 at q = 0.97 - and it jumps with the last bit of h or r.
+ * These errors are independent between pairs, so they are accumulated in quadrature: g2 = sum (|term| /
+ * (1-q)^2)^2. For ordinary neighbourhoods sqrt(g2) stays below the plain un-cancelled sum; a neighbour
+ * at the kernel edge that is orders of magnitude hotter (the shell around a Sedov blast) dominates both
+ * the sum and g2 and carries its 1e-4 into them - in the reference exactly as here. */
+static inline float edge_weight(float r, float h) {
+  const float q = r / (h * kernel_gamma);
+  const float e = 1.f - q;
+  return e > 1.e-3f ? 1.f / (e * e) : 1.e6f;
+}
 
 /* runner_iact_nonsym_density: Minimal hydro_iact.h:137, Gadget2 :158,
  * SPHENIX :141 (identical arithmetic; div_v lives in viscosity.div_v there) */
@@ -204,7 +220,11 @@ static inline void iact_gradient(port_t *s, float r2, const float dx[3], float h
   kernel_deval(ui, &wi, &wi_dx);
   const float delta_u_factor = (s->u[i] - s->u[j]) * r_inv;
   s->laplace_u[i] += s->m[j] * delta_u_factor * wi_dx / s->rho[j];
-  s->g_lap[i] += fabsf(s->m[j] * delta_u_factor * wi_dx / s->rho[j]);
+  {
+    const float t = fabsf(s->m[j] * delta_u_factor * wi_dx / s->rho[j]);
+    s->g_lap[i] += t;
+    s->g2_lap[i] += (t * edge_weight(r, hi)) * (t * edge_weight(r, hi));
+  }
   const float alpha_j = s->alpha[j];
   s->alpha_max_ngb[i] = pmax(s->alpha_max_ngb[i], alpha_j);
   s->ng[i]++;
@@ -241,6 +261,7 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
   const float omega_ij = pmin(dvdr_Hubble, 0.f);
   const float mu_ij = fac_mu * r_inv * omega_ij;
   const float v_sig = s->cs[i] + s->cs[j] - const_viscosity_beta * mu_ij;
+  const float ew = fmaxf(wi_dx != 0.f ? edge_weight(r, hi) : 1.f, wj_dx != 0.f ? edge_weight(r, hj) : 1.f);
   const float balsara_i = s->balsara[i];
   const float balsara_j = s->balsara[j];
 #if PORT_SCHEME == SCH_MINIMAL
@@ -266,8 +287,13 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
   s->h_dt[i] -= mj * dvdr * r_inv / rhoj * wi_dr * f_ij;
   s->v_sig[i] = pmax(s->v_sig[i], v_sig);
   s->g_a[i] += fabsf(mj * acc) * r;
-  s->g_u[i] += (fabsf(sph_du_term_i) + fabsf(visc_du_term)) * mj;
-  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr * f_ij);
+  s->g2_a[i] += (fabsf(mj * acc) * r * ew) * (fabsf(mj * acc) * r * ew);
+  {
+    const float t = (fabsf(sph_du_term_i) + fabsf(visc_du_term)) * mj;
+    s->g_u[i] += t;
+    s->g2_u[i] += (t * ew) * (t * ew);
+  }
+  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr * f_ij) ;
 #elif PORT_SCHEME == SCH_GADGET2
   const float f_i = s->f[i];
   const float f_j = s->f[j];
@@ -286,10 +312,15 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
   s->v_sig[i] = pmax(s->v_sig[i], v_sig);
   s->u_dt[i] += mj * visc_term * dvdr_Hubble; /* entropy_dt */
   s->g_a[i] += fabsf(mj * acc) * r;
+  s->g2_a[i] += (fabsf(mj * acc) * r * ew) * (fabsf(mj * acc) * r * ew);
   /* entropy_dt only collects the viscous heating; the scale of the thermal energy equation it belongs
    * to also holds the adiabatic term P/rho^2 dv.dx W'/r (x2: hydro_end_force halves the sum) */
-  s->g_u[i] += fabsf(mj * visc_term * dvdr_Hubble) + 2.f * fabsf(mj * f_i * P_over_rho2_i * dvdr * r_inv * wi_dr);
-  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr);
+  {
+    const float t = fabsf(mj * visc_term * dvdr_Hubble) + 2.f * fabsf(mj * f_i * P_over_rho2_i * dvdr * r_inv * wi_dr);
+    s->g_u[i] += t;
+    s->g2_u[i] += (t * ew) * (t * ew);
+  }
+  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr) ;
 #else /* SPHENIX */
   const float mi = s->m[i];
   const float pressurei = s->P[i];
@@ -321,8 +352,13 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
   s->u_dt[i] += du_dt_i * mj;
   s->h_dt[i] -= mj * dvdr * r_inv / rhoj * wi_dr;
   s->g_a[i] += fabsf(mj * acc) * r;
-  s->g_u[i] += (fabsf(sph_du_term_i) + fabsf(visc_du_term) + fabsf(diff_du_term)) * mj;
-  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr);
+  s->g2_a[i] += (fabsf(mj * acc) * r * ew) * (fabsf(mj * acc) * r * ew);
+  {
+    const float t = (fabsf(sph_du_term_i) + fabsf(visc_du_term) + fabsf(diff_du_term)) * mj;
+    s->g_u[i] += t;
+    s->g2_u[i] += (t * ew) * (t * ew);
+  }
+  s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr) ;
 #endif
   /* runner_iact_nonsym_timebin */
   if (s->time_bin[j] > 0) s->min_ngb[i] = pmin(s->min_ngb[i], s->time_bin[j]);
@@ -705,6 +741,7 @@ static void init_part(port_t *s, long long p) {
   s->rho_dh[p] = 0.f;
   s->div_v[p] = 0.f;
   s->g_div[p] = s->g_rho_dh[p] = s->g_lap[p] = 0.f;
+  s->g2_lap[p] = 0.f;
   s->rot_v[3 * p] = s->rot_v[3 * p + 1] = s->rot_v[3 * p + 2] = 0.f;
 #if PORT_SCHEME == SCH_SPHENIX
   s->laplace_u[p] = 0.f;
@@ -752,6 +789,7 @@ static void has_no_neighbours(port_t *s, long long p) {
   s->wcount_dh[p] = 0.f;
   s->div_v[p] = 0.f;
   s->g_div[p] = s->g_rho_dh[p] = s->g_lap[p] = 0.f;
+  s->g2_lap[p] = 0.f;
   s->rot_v[3 * p] = s->rot_v[3 * p + 1] = s->rot_v[3 * p + 2] = 0.f;
 #if PORT_SCHEME == SCH_SPHENIX
   s->v_sig[p] = 0.f;
@@ -801,6 +839,7 @@ static void extra_ghost_part(port_t *s, long long p, float dt_alpha) {
   const float h_inv_dim_plus_one = h_inv_dim * h_inv;
   s->laplace_u[p] *= 2.f * h_inv_dim_plus_one;
   s->g_lap[p] *= 2.f * h_inv_dim_plus_one;
+  s->g2_lap[p] *= (2.f * h_inv_dim_plus_one) * (2.f * h_inv_dim_plus_one);
 
   const float a = s->step.a;
   const float kernel_support_physical = s->h[p] * a * kernel_gamma;
@@ -849,6 +888,7 @@ static void extra_ghost_part(port_t *s, long long p, float dt_alpha) {
   s->u_dt[p] = 0.f;
   s->h_dt[p] = 0.f;
   s->g_a[p] = s->g_u[p] = s->g_hdt[p] = 0.f;
+  s->g2_a[p] = s->g2_u[p] = 0.f;
   s->min_ngb[p] = num_time_bins + 1;
   s->nf[p] = 0;
 }
@@ -912,6 +952,7 @@ static void prepare_force(port_t *s, long long p) {
   s->u_dt[p] = 0.f;
   s->h_dt[p] = 0.f;
   s->g_a[p] = s->g_u[p] = s->g_hdt[p] = 0.f;
+  s->g2_a[p] = s->g2_u[p] = 0.f;
   s->v_sig[p] = 2.f * s->cs[p];
   s->nf[p] = 0;
 }
@@ -1235,6 +1276,7 @@ port_t *port_create(const swiftgpu_config *cfg, const swiftgpu_step *step,
   s->div_v_dt = falloc(n); s->laplace_u = falloc(n); s->alpha_max_ngb = falloc(n);
   s->g_a = falloc(n); s->g_u = falloc(n); s->g_hdt = falloc(n); s->g_div = falloc(n);
   s->g_rho_dh = falloc(n); s->g_lap = falloc(n);
+  s->g2_a = falloc(n); s->g2_u = falloc(n); s->g2_lap = falloc(n);
   s->time_bin = (signed char *)calloc(n, 1);
   s->depth_h = (signed char *)calloc(n, 1);
   s->min_ngb = (signed char *)calloc(n, 1);
@@ -1285,6 +1327,7 @@ void port_destroy(port_t *s) {
   free(s->rot_v); free(s->m); free(s->h); free(s->u); free(s->u_dt); free(s->rho);
   free(s->wcount); free(s->wcount_dh); free(s->rho_dh); free(s->div_v); free(s->f);
   free(s->P); free(s->cs); free(s->balsara); free(s->v_sig); free(s->h_dt);
+  free(s->g2_a); free(s->g2_u); free(s->g2_lap);
   free(s->g_a); free(s->g_u); free(s->g_hdt); free(s->g_div); free(s->g_rho_dh); free(s->g_lap);
   free(s->alpha); free(s->alpha_diff); free(s->div_v_prev); free(s->div_v_dt);
   free(s->laplace_u); free(s->alpha_max_ngb); free(s->time_bin); free(s->depth_h);
@@ -1341,6 +1384,7 @@ int port_run(port_t *s, unsigned mask) {
         const float pow_mgm1 = cbrt_inv * cbrt_inv; /* rho^-(gamma-1) */
         s->u_dt[p] = 0.5f * (hydro_gamma_minus_one * s->u_dt[p] * pow_mgm1);
         s->g_u[p] = 0.5f * (hydro_gamma_minus_one * s->g_u[p] * pow_mgm1);
+        s->g2_u[p] *= (0.5f * hydro_gamma_minus_one * pow_mgm1) * (0.5f * hydro_gamma_minus_one * pow_mgm1);
 #endif
       }
     }
@@ -1410,7 +1454,7 @@ int port_ghost_iterations(const port_t *s) { return s->ghost_iterations; }
  * same factors as the sums) of a_hydro (norm), u_dt | entropy_dt, h_dt, div_v,
  * rho_dh and laplace_u: what the parity metric floors its relative errors with. */
 void port_get_gross(const port_t *s, float *a, float *u, float *hdt, float *div, float *rho_dh,
-                    float *lap) {
+                    float *lap, float *a2, float *u2, float *lap2) {
   const size_t b = sizeof(float) * (size_t)s->n;
   if (a) memcpy(a, s->g_a, b);
   if (u) memcpy(u, s->g_u, b);
@@ -1418,4 +1462,7 @@ void port_get_gross(const port_t *s, float *a, float *u, float *hdt, float *div,
   if (div) memcpy(div, s->g_div, b);
   if (rho_dh) memcpy(rho_dh, s->g_rho_dh, b);
   if (lap) memcpy(lap, s->g_lap, b);
+  if (a2) memcpy(a2, s->g2_a, b);
+  if (u2) memcpy(u2, s->g2_u, b);
+  if (lap2) memcpy(lap2, s->g2_lap, b);
 }

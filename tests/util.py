@@ -145,6 +145,7 @@ def dirty_zone(x, flip, reach):
 
 
 FR = 0.5  # floor = FR x (sum over neighbours of |pair term|), see the header above
+FRE = 0.05  # ... + FRE x sqrt(sum (|pair term| / (1 - q)^2)^2): FP32 Horner noise of kernel_deval, oracle/swift_port.c
 
 
 def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, time_base=1e-6,
@@ -191,8 +192,9 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, ti
     na = np.linalg.norm(ar, axis=1)
     uname = "entropy_dt" if scheme_name == "gadget2" else "u_dt"
     if gross is not None:
-        gross_a = gross["a_hydro"] / FR * 0.1  # a_hydro keeps its round-1 bar: 0.1 x the exact un-cancelled sum
-        ufloor = FR * gross["u_dt"]
+        # a_hydro keeps its round-1 bar (0.1 x the plain un-cancelled sum); + the kernel-evaluation noise
+        gross_a = (0.1 * gross["a_hydro"] + FRE * np.sqrt(gross["a_hydro_sq"])) / FR
+        ufloor = FR * gross["u_dt"] + FRE * np.sqrt(gross["u_dt_sq"])
         hfloor = FR * gross["h_dt"]
     else:
         gross_a = 1e-1 * gross_px / FR * 0.1  # the proxy overestimates the exact sum ~10x
@@ -243,7 +245,7 @@ def parity_report(got, ref, layout, scheme_name, h_tolerance=1e-4, only=None, ti
     if scheme_name == "sphenix":
         u = f(ref, "u")
         if gross is not None:
-            floor_lap = FR * gross["laplace_u"]
+            floor_lap = FR * gross["laplace_u"] + FRE * np.sqrt(gross["laplace_u_sq"])
         else:
             Gu = 2.0 * np.pi * float(u.std()) / float(box.min())
             floor_lap = Gu / hr
