@@ -77,6 +77,7 @@ __device__ __forceinline__ int64_t sort_offset(const DevCell &c, int sid) {
   return c.sort_base + (int64_t)__popc((unsigned)c.sort_mask & ((1u << sid) - 1u)) * c.count;
 }
 
+struct TaskRec;
 struct LoopArgs {
   const DevCell *cells;
   const Item *items;
@@ -109,6 +110,10 @@ struct LoopArgs {
   float margin; /* absolute widening of the float prefilter */
   int hold;     /* stages a consumer warp holds before it drains (<= NS - 1) */
   unsigned int *task_counter; /* persistent CTAs draw their tasks from here (zeroed per launch) */
+  /* frame pipeline (loops_pipe.cuh) */
+  const float4 *frames;            /* per-(cell, origin) arrays of (float)(x - origin) */
+  const struct TaskRec *task_recs; /* compacted tasks of this launch (k_task_recs) */
+  const unsigned int *ntask_dev;   /* their number */
   /* outputs */
   float4 *dA;      /* (rho, rho_dh, wcount, wcount_dh) */
   float4 *dB;      /* (div_v, rot_v) */

@@ -85,14 +85,15 @@ struct __align__(16) PipeItem {
   double sh[3]; /* double modes: dx = (float)((x_t - sh) - x_s) */
   float d[3];   /* cull: target own-frame float - d = position in the source cell's own frame */
   float rsrc;   /* force: h_max gamma of the source cell (also the source-side cap) */
+  float relq, padd; /* (8-byte aligned) force test: r2 < fma(max(hig2, hjg2), relq, padd); (1, 0) in the frame modes */
   float hcap;   /* target-side cap of h gamma under which the key conditions are implied */
-  float relq, padd; /* force test: r2 < fma(max(hig2, hjg2), relq, padd); (1, 0) in the frame modes */
   int32_t item;     /* global item index (slow path) */
   int32_t gi_base;  /* global particle index = gi_base + slot-in-stage */
   int16_t dofs;     /* slot -> index in the staged double columns */
   int8_t mode, sid, min_depth, max_depth, dbl, nokey;
 };
 static_assert(sizeof(PipeItem) == 96, "PipeItem");
+static_assert(offsetof(PipeItem, relq) % 8 == 0, "relq/padd are read as one float2");
 
 template <int NP, int NS, int QCAP, int CW, int DS>
 struct PipeSmem {
@@ -164,9 +165,23 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
     const int ntask = (int)*A.ntask_dev;
 
     /* ---- one window of 32 items of a task: derive the constants, cull, write (lane = item) ---- */
+    struct CellLite { /* what the item constants need of a cell */
+      double loc[3];
+      float h_max, h_max_active, h_max_allowed, width, dx_max_part;
+      int32_t first, count;
+    };
+    auto load_cell = [&](int c) {
+      const DevCell &C = A.cells[c];
+      CellLite L;
+      L.loc[0] = C.loc[0]; L.loc[1] = C.loc[1]; L.loc[2] = C.loc[2];
+      L.h_max = C.h_max; L.h_max_active = C.h_max_active; L.h_max_allowed = C.h_max_allowed;
+      L.width = C.width; L.dx_max_part = C.dx_max_part;
+      L.first = C.first; L.count = C.count;
+      return L;
+    };
     struct WinLoad { /* registers in flight between the steps of the prefetch */
       Item I;
-      DevCell sc;
+      CellLite sc;
       int bfirst;
       bool valid;
     };
@@ -176,87 +191,93 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
     };
     auto win_load_cells = [&](WinLoad &W) {
       if (W.valid) {
-        W.sc = A.cells[W.I.scell];
+        W.sc = load_cell(W.I.scell);
         W.bfirst = A.cell_box_first[W.I.scell];
       }
     };
-    auto win_finish = [&](const TaskRec &T, const DevCell &tcell, int win_base, const WinLoad &W, int buf) -> unsigned {
+    auto win_finish = [&](const TaskRec &T, const CellLite &tcell, int win_base, const WinLoad &W, int buf) -> unsigned {
       bool keep = false;
       if (W.valid) {
         const Item &I = W.I;
-        const DevCell &sc = W.sc;
+        const CellLite &sc = W.sc;
         const int mode = I.mode;
         const double shx = I.shift[0] * A.dim[0], shy = I.shift[1] * A.dim[1], shz = I.shift[2] * A.dim[2];
-        PipeItem p;
-        p.mode = (int8_t)mode;
-        p.sid = (int8_t)I.sid;
-        p.min_depth = I.min_depth;
-        p.max_depth = I.max_depth;
-        p.dbl = 0;
-        p.nokey = 0;
-        p.dofs = 0;
-        p.item = T.item_first + win_base + lane;
-        p.gi_base = 0;
-        p.rsrc = FORCE ? __fmul_rn(sc.h_max, KERNEL_GAMMA) : 0.f;
-        p.hcap = 3.402823466e+38f;
-        p.relq = 1.f;
-        p.padd = 0.f;
-        p.sh[0] = p.sh[1] = p.sh[2] = 0.;
+        /* written in place (a local PipeItem would live in local memory) */
+        PipeItem *const wp = &sWin[buf * 32 + lane];
+        wp->mode = (int8_t)mode;
+        wp->sid = (int8_t)I.sid;
+        wp->min_depth = I.min_depth;
+        wp->max_depth = I.max_depth;
+        wp->dofs = 0;
+        wp->item = T.item_first + win_base + lane;
+        wp->gi_base = 0;
+        const float rsrc = FORCE ? __fmul_rn(sc.h_max, KERNEL_GAMMA) : 0.f;
+        wp->rsrc = rsrc;
+        float hcap = 3.402823466e+38f, relq = 1.f, padd = 0.f;
+        int dbl = 0, nokey = 0;
+        double o0, o1, o2, s0 = 0., s1 = 0., s2 = 0.;
         /* displacement target - source = (t_own + T.loc) - (s_own + S.loc) - sh_eff */
         double ex = 0., ey = 0., ez = 0.; /* sh_eff */
         if (mode == MODE_PAIR_L || mode == MODE_PAIR_R) {
-          const DevCell &ci = (mode == MODE_PAIR_L) ? tcell : sc;
-          const DevCell &cj = (mode == MODE_PAIR_L) ? sc : tcell;
-          if (mode == MODE_PAIR_L) { /* pix = x - (cj->loc + shift), targets are the pi */
-            p.ot[0] = __dadd_rn(cj.loc[0], shx);
-            p.ot[1] = __dadd_rn(cj.loc[1], shy);
-            p.ot[2] = __dadd_rn(cj.loc[2], shz);
+          if (mode == MODE_PAIR_L) { /* pix = x - (cj->loc + shift), targets are the pi, cj = source cell */
+            o0 = __dadd_rn(sc.loc[0], shx);
+            o1 = __dadd_rn(sc.loc[1], shy);
+            o2 = __dadd_rn(sc.loc[2], shz);
             ex = shx; ey = shy; ez = shz;
-          } else { /* pjx = x - cj->loc, targets are the pj */
-            p.ot[0] = cj.loc[0];
-            p.ot[1] = cj.loc[1];
-            p.ot[2] = cj.loc[2];
+          } else { /* pjx = x - cj->loc, targets are the pj, cj = target cell */
+            o0 = tcell.loc[0];
+            o1 = tcell.loc[1];
+            o2 = tcell.loc[2];
             ex = -shx; ey = -shy; ez = -shz;
           }
           if (FORCE) {
-            p.hcap = __fmul_rn(tcell.h_max, KERNEL_GAMMA);
+            hcap = __fmul_rn(tcell.h_max, KERNEL_GAMMA);
           } else {
-            const float h_max_lim = (I.flags & 1) ? ci.h_max_allowed : 3.402823466e+38f;
-            p.hcap = __fmul_rn(fminf(h_max_lim, tcell.h_max_active), KERNEL_GAMMA);
+            const float ci_hma = (mode == MODE_PAIR_L) ? tcell.h_max_allowed : sc.h_max_allowed;
+            const float h_max_lim = (I.flags & 1) ? ci_hma : 3.402823466e+38f;
+            hcap = __fmul_rn(fminf(h_max_lim, tcell.h_max_active), KERNEL_GAMMA);
           }
         } else if (mode == MODE_SUB_SELF) { /* floats relative to c->loc, :1108 */
-          p.ot[0] = sc.loc[0];
-          p.ot[1] = sc.loc[1];
-          p.ot[2] = sc.loc[2];
-          p.nokey = 1;
+          o0 = sc.loc[0];
+          o1 = sc.loc[1];
+          o2 = sc.loc[2];
+          nokey = 1;
         } else {
           /* double modes: prefilter in the source cell's own frame, exact in the drain */
-          p.dbl = 1;
+          dbl = 1;
           if (mode != MODE_SELF) {
-            p.sh[0] = shx; p.sh[1] = shy; p.sh[2] = shz;
+            s0 = shx; s1 = shy; s2 = shz;
             ex = shx; ey = shy; ez = shz;
           } else {
-            p.nokey = 1;
+            nokey = 1;
           }
-          p.ot[0] = __dadd_rn(sc.loc[0], p.sh[0]);
-          p.ot[1] = __dadd_rn(sc.loc[1], p.sh[1]);
-          p.ot[2] = __dadd_rn(sc.loc[2], p.sh[2]);
+          o0 = __dadd_rn(sc.loc[0], s0);
+          o1 = __dadd_rn(sc.loc[1], s1);
+          o2 = __dadd_rn(sc.loc[2], s2);
           /* limit r^2 of a prefilter radius (R (1 + 1e-5) + margin)^2 <= R^2 PRE_REL2 + padd for R <= Rmax */
-          const float Rmax = fmaxf(T.rmax, p.rsrc);
-          p.relq = PL_PRE_REL2;
-          p.padd = fmaf(2.f * Rmax, A.margin, A.margin * A.margin) * 1.001f;
+          const float Rmax = fmaxf(T.rmax, rsrc);
+          relq = PL_PRE_REL2;
+          padd = fmaf(2.f * Rmax, A.margin, A.margin * A.margin) * 1.001f;
         }
-        p.d[0] = (float)__dsub_rn(__dadd_rn(sc.loc[0], ex), tcell.loc[0]);
-        p.d[1] = (float)__dsub_rn(__dadd_rn(sc.loc[1], ey), tcell.loc[1]);
-        p.d[2] = (float)__dsub_rn(__dadd_rn(sc.loc[2], ez), tcell.loc[2]);
-        sWin[buf * 32 + lane] = p;
+        wp->ot[0] = o0; wp->ot[1] = o1; wp->ot[2] = o2;
+        wp->sh[0] = s0; wp->sh[1] = s1; wp->sh[2] = s2;
+        wp->hcap = hcap;
+        wp->relq = relq;
+        wp->padd = padd;
+        wp->dbl = (int8_t)dbl;
+        wp->nokey = (int8_t)nokey;
+        const float d0 = (float)__dsub_rn(__dadd_rn(sc.loc[0], ex), tcell.loc[0]);
+        const float d1 = (float)__dsub_rn(__dadd_rn(sc.loc[1], ey), tcell.loc[1]);
+        const float d2 = (float)__dsub_rn(__dadd_rn(sc.loc[2], ez), tcell.loc[2]);
+        wp->d[0] = d0; wp->d[1] = d1; wp->d[2] = d2;
         sWinAux[buf * 32 + lane] = make_int4(sc.first, sc.count, (int)I.sframe, W.bfirst);
         /* item-level cull: the source cell's box [0, width] (+ drift) against the task's target box */
-        const float r = fmaf(fmaxf(T.rmax, p.rsrc), PREFILTER_REL, A.margin) + sc.dx_max_part;
+        const float r = fmaf(fmaxf(T.rmax, rsrc), PREFILTER_REL, A.margin) + sc.dx_max_part;
+        const float dd[3] = {d0, d1, d2};
         float q2 = 0.f;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          const float a = 0.f - (T.hi[k] - p.d[k]), b = (T.lo[k] - p.d[k]) - sc.width;
+          const float a = 0.f - (T.hi[k] - dd[k]), b = (T.lo[k] - dd[k]) - sc.width;
           const float gk = fmaxf(0.f, fmaxf(a, b));
           q2 = fmaf(gk, gk, q2);
         }
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
     };
 
     TaskRec cur, nxt;
-    DevCell cur_cell, nxt_cell;
+    CellLite cur_cell, nxt_cell;
     unsigned cur_km = 0, nxt_km = 0;
     int cur_buf = 0;
     bool cur_valid = false, nxt_valid = false;
@@ -282,7 +303,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
       const int t = draw();
       if (t < ntask) {
         cur = A.task_recs[t];
-        cur_cell = A.cells[cur.tcell];
+        cur_cell = load_cell(cur.tcell);
         WinLoad W;
         win_load_items(cur, 0, W);
         win_load_cells(W);
@@ -315,7 +336,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
             break;
           }
           case 2:
-            nxt_cell = A.cells[nxt.tcell];
+            nxt_cell = load_cell(nxt.tcell);
             win_load_items(nxt, 0, PW);
             pstate = 3;
             break;
@@ -335,80 +356,35 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
 
       const TaskRec &T = cur;
       bool first_stage = true; /* the first published stage of the task carries the task's targets */
-      int win_base = 0;
-      unsigned km = cur_km; /* kept items of the window */
-      int j = 0;            /* next position in the window */
-      int off = 0;          /* source offset inside the current item */
-      bool exhausted = false;
-      for (;; it++) {
+      unsigned km = cur_km;    /* kept items of the window */
+
+      /* ---- publish one stage: lanes with `has` copy their fragment (lane-parallel), lane 0 arrives ---- */
+      auto publish = [&](bool has, int myfrag, int nfr, int used, int my_w, int my_off, int my_n, int my_pool,
+                         int my_dbase, int gap_from, int gap_to) {
         const int s = it % NS;
         const uint32_t ph = (uint32_t)((it / NS) & 1);
-        /* ---- assemble the fragments of this stage (warp-uniform) ---- */
-        int used = 0, nfr = 0, dused = 0;
-        int my_w = 0, my_off = 0, my_n = 0, my_pool = 0, my_dbase = 0;
-        while (!exhausted && nfr < PL_FRAGS && used < PL_SLOTS) {
-          const unsigned mm = j >= 32 ? 0u : (km >> j) << j;
-          if (!mm) {
-            if (nfr > 0) break; /* the window table is still referenced by this stage's fragments */
-            win_base += 32;
-            if (win_base >= T.item_count) {
-              exhausted = true;
-              break;
-            }
-            /* a further window of a long item list (multi-level trees): loaded in place */
-            WinLoad W;
-            win_load_items(T, win_base, W);
-            win_load_cells(W);
-            km = win_finish(T, cur_cell, win_base, W, cur_buf);
-            j = 0;
-            continue;
-          }
-          const int jj = __ffs(mm) - 1;
-          const int4 aux = sWinAux[cur_buf * 32 + jj];
-          const bool dbl = sWin[cur_buf * 32 + jj].dbl != 0;
-          const int left = aux.y - off, room = PL_SLOTS - used;
-          int take = left <= room ? left : (room & ~7);
-          if (dbl) {
-            const int droom = (DS - dused) & ~7;
-            if (take > droom) take = droom;
-          }
-          if (take <= 0) break;
-          if (lane == nfr) {
-            my_w = jj;
-            my_off = off;
-            my_n = take;
-            my_pool = used;
-            my_dbase = dused;
-          }
-          used += (take + 7) & ~7;
-          if (dbl) dused += ((take + 7) & ~7) + 2;
-          nfr++;
-          if (take == left) {
-            j = jj + 1;
-            off = 0;
-          } else {
-            off += take;
-            if (!dbl || used >= PL_SLOTS) break;
-            break;
-          }
-        }
         char *const st = smem + s * SM::kStageBytes;
         int32_t *const meta = (int32_t *)(st + SM::kStageMeta);
-        if (nfr == 0) break; /* the task's items are exhausted */
         mbar_wait(sEmpty + s, ph ^ 1u);
         uint32_t bytes = 0;
-        if (lane < nfr) {
-          PipeItem p = sWin[cur_buf * 32 + my_w];
+        if (has) {
           const int4 aux = sWinAux[cur_buf * 32 + my_w];
           const int first = aux.x + my_off;
           const int dpar = first & 1; /* the double columns are copied from an even index */
-          p.gi_base = first - my_pool;
-          p.dofs = (int16_t)(my_dbase + dpar - my_pool);
-          ((PipeItem *)(st + SM::kStageIT))[lane] = p;
-          /* octet -> fragment map, sentinel records of the padding slots */
+          const bool pdbl = sWin[cur_buf * 32 + my_w].dbl != 0;
+          {
+            const int4 *const src4 = (const int4 *)&sWin[cur_buf * 32 + my_w];
+            int4 *const dst4 = (int4 *)&((PipeItem *)(st + SM::kStageIT))[myfrag];
+#pragma unroll
+            for (int q = 0; q < (int)sizeof(PipeItem) / 16; q++) dst4[q] = src4[q];
+            PipeItem *const dp = (PipeItem *)dst4;
+            dp->gi_base = first - my_pool;
+            dp->dofs = (int16_t)(my_dbase + dpar - my_pool);
+          }
+          /* octet -> fragment map, sentinel records of the padding slots, sentinel boxes of a gap */
           const int o0 = my_pool >> 3, o1 = (my_pool + my_n + 7) >> 3;
           uint8_t *o2f = (uint8_t *)(st + SM::kStageO2F);
-          for (int o = o0; o < o1; o++) o2f[o] = (uint8_t)lane;
+          for (int o = o0; o < o1; o++) o2f[o] = (uint8_t)myfrag;
           float4 *F = (float4 *)(st + SM::kStageF);
           for (int k = my_pool + my_n; k < o1 * 8; k++)
             F[k] = make_float4(-3.0e30f, -3.0e30f, -3.0e30f, 0.f);
@@ -431,7 +407,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
               bytes += n16;
             }
           }
-          if (p.dbl) {
+          if (pdbl) {
             const uint32_t n8 = (uint32_t)((my_n + dpar + 1) & ~1) * 8u;
             double *D = (double *)(st + SM::kStageD) + my_dbase;
             tma_load(D, A.xs0 + (first - dpar), n8, sFull + s);
@@ -444,8 +420,14 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
                    sFull + s);
           bytes += nb32;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(FULL_MASK, bytes, o);
+        /* octets no fragment owns (an item's padding to the minimum size, possibly carried over from the
+         * previous stage): boxes no cull accepts */
+        for (int o = gap_from >> 3; o < (gap_to >> 3); o++) {
+          ((uint8_t *)(st + SM::kStageO2F))[o] = 0;
+          ((float4 *)(st + SM::kStageOB))[2 * o] = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 0.f);
+          ((float4 *)(st + SM::kStageOB))[2 * o + 1] = make_float4(-3.0e30f, -3.0e30f, -3.0e30f, 0.f);
+        }
+        bytes = __reduce_add_sync(FULL_MASK, bytes);
         __syncwarp();
         if (lane == 0) {
           meta[PM_NFR] = nfr;
@@ -461,7 +443,102 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
           mbar_arrive_tx(sFull + s, bytes);
         }
         first_stage = false;
-        prefetch_step(); /* one dependent load of the next task per stage */
+        it++;
+        if (!(A.hold & 1)) prefetch_step(); /* one dependent load of the next task per stage */
+      };
+
+      for (int win_base = 0;; win_base += 32) {
+        if (win_base > 0) {
+          /* a further window of a long item list (multi-level trees): loaded in place */
+          WinLoad W;
+          win_load_items(T, win_base, W);
+          win_load_cells(W);
+          km = win_finish(T, cur_cell, win_base, W, cur_buf);
+        }
+        /* ---- layout of the window's kept items in a virtual source array cut into stages of
+         * PL_SLOTS (lane = item): exclusive prefix sum of the padded sizes. An item takes at least
+         * 40 slots, so a stage holds at most 2 partial + 6 whole items = PL_FRAGS fragments. ---- */
+        const int4 myaux = sWinAux[cur_buf * 32 + lane];
+        const bool kept = (km >> lane) & 1u;
+        const bool mydbl = kept && sWin[cur_buf * 32 + lane].dbl != 0;
+        const int n = kept ? myaux.y : 0;
+        const int pn = (n + 7) & ~7;
+        /* a double-mode item larger than the stage's double columns: serial fallback below */
+        /* (... or, in the main loops whose double columns hold one small item, a second double-mode item) */
+        const bool big = (A.hold & 2) || __any_sync(FULL_MASK, mydbl && pn > (DS & ~7)) ||
+                         (DS < PL_SLOTS && __popc(__ballot_sync(FULL_MASK, mydbl)) > 1);
+        if (!big) {
+          const int v = kept ? max(pn, 40) : 0;
+          int V = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, V, o);
+            if (lane >= o) V += t;
+          }
+          const int vstart = V - v;
+          const int total = __shfl_sync(FULL_MASK, V, 31);
+          const int nstages = (total + PL_SLOTS - 1) / PL_SLOTS;
+          for (int k = 0; k < nstages; k++) {
+            const int lo = k * PL_SLOTS, hi = lo + PL_SLOTS;
+            const int a0 = max(vstart, lo), b0 = min(vstart + pn, hi);
+            const bool has = kept && a0 < b0;
+            const int my_off = a0 - vstart;
+            const int my_n = min(n - my_off, b0 - a0);
+            const int my_pool = a0 - lo;
+            const unsigned fmask = __ballot_sync(FULL_MASK, has);
+            const int nfr = __popc(fmask);
+            const int myfrag = __popc(fmask & ((1u << lane) - 1u));
+            const int used = __reduce_max_sync(FULL_MASK, has ? my_pool + ((my_n + 7) & ~7) : 0);
+            /* my padding (to the minimum size) inside this stage, below the last real slot: it must not
+             * look like sources */
+            const int gap_from = kept ? min(max(vstart + pn, lo), hi) - lo : 0;
+            const int gap_to = kept ? min(min(max(vstart + v, lo), hi) - lo, used) : 0;
+            publish(has, myfrag, nfr, used, lane, my_off, my_n, my_pool, DS >= PL_SLOTS ? my_pool + 2 * myfrag : 0,
+                    gap_from, gap_to);
+          }
+        } else {
+          /* ---- serial assembly (stage by stage, warp-uniform) ---- */
+          int j = 0;   /* next position in the window */
+          int off = 0; /* source offset inside the current item */
+          for (;;) {
+            int used = 0, nfr = 0, dused = 0;
+            int my_w = 0, my_off = 0, my_n = 0, my_pool = 0, my_dbase = 0;
+            while (nfr < PL_FRAGS && used < PL_SLOTS) {
+              const unsigned mm = j >= 32 ? 0u : (km >> j) << j;
+              if (!mm) break;
+              const int jj = __ffs(mm) - 1;
+              const int4 aux = sWinAux[cur_buf * 32 + jj];
+              const bool dbl = sWin[cur_buf * 32 + jj].dbl != 0;
+              const int left = aux.y - off, room = PL_SLOTS - used;
+              int take = left <= room ? left : (room & ~7);
+              if (dbl) {
+                const int droom = (DS - dused) & ~7;
+                if (take > droom) take = droom;
+              }
+              if (take <= 0) break;
+              if (lane == nfr) {
+                my_w = jj;
+                my_off = off;
+                my_n = take;
+                my_pool = used;
+                my_dbase = dused;
+              }
+              used += (take + 7) & ~7;
+              if (dbl) dused += ((take + 7) & ~7) + 2;
+              nfr++;
+              if (take == left) {
+                j = jj + 1;
+                off = 0;
+              } else {
+                off += take;
+                break;
+              }
+            }
+            if (nfr == 0) break; /* the window's items are exhausted */
+            publish(lane < nfr, lane, nfr, used, my_w, my_off, my_n, my_pool, my_dbase, 0, 0);
+          }
+        }
+        if (win_base + 32 >= T.item_count) break;
       }
       while (pstate != 5) prefetch_step();
       cur_valid = nxt_valid;

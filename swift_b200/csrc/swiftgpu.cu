@@ -27,6 +27,7 @@
 #include "../../include/swiftgpu.h"
 #include "loops_cta.cuh"
 #include "loops_tile.cuh"
+#include "loops_pipe.cuh"
 
 using namespace swiftgpu;
 
@@ -47,12 +48,14 @@ struct DevList {
   Group *groups = nullptr;
   int32_t *task_group = nullptr, *task_chunk = nullptr;
   int32_t *tgt_first = nullptr, *tgt_count = nullptr, *tgt_list = nullptr;
+  TaskRec *task_recs = nullptr; /* compacted per launch by k_task_recs */
   int ngroups = 0, ntasks = 0;
   size_t nitems = 0;
   int64_t tgt_total = 0;
   void release() {
     cudaFree(items); cudaFree(groups); cudaFree(task_group); cudaFree(task_chunk);
-    cudaFree(tgt_first); cudaFree(tgt_count); cudaFree(tgt_list);
+    cudaFree(tgt_first); cudaFree(tgt_count); cudaFree(tgt_list); cudaFree(task_recs);
+    task_recs = nullptr;
     items = nullptr; groups = nullptr; task_group = task_chunk = nullptr;
     tgt_first = tgt_count = tgt_list = nullptr;
     ngroups = ntasks = 0; nitems = 0; tgt_total = 0;
@@ -118,6 +121,20 @@ struct swiftgpu_handle {
   int nleaves = 0;
   bool leaves_valid = false;
   bool perm_stale = false; /* cells changed after the particles were transposed */
+  /* frame arrays (loops_pipe.cuh): one per (cell, origin) the items of the lists read */
+  struct FrameRec {
+    int32_t first, count;
+    double o[3];
+    uint32_t off;
+    uint32_t pad;
+  };
+  std::vector<FrameRec> frames_host;
+  std::vector<int32_t> frame_idx; /* [cell * 14 + slot] -> index into frames_host (slot 0: own frame, 1 + sid: ci frames) */
+  float4 *d_frames = nullptr;
+  FrameRec *d_frame_recs = nullptr;
+  uint64_t frames_total = 0, frames_cap = 0;
+  size_t frame_recs_uploaded = 0;
+  bool frames_valid = false; /* d_frames holds the frames of the current positions */
   /* tile pipeline records (loops_tile.cuh) */
   float4 *xf = nullptr, *gq = nullptr, *boxes = nullptr;
   double *xs = nullptr; /* 3 columns of n + 4 doubles */
@@ -289,7 +306,10 @@ __global__ void k_aos_to_soa(const char *aos, DevLayout D, Soa S, int64_t n, con
    * particle was active in: they are what inactive neighbours contribute. */
   const float P = rd<float>(b, D.scheme == SCH_GADGET2 ? L.P_over_rho2 : L.pressure);
   S.fq1[p] = make_float4(rho, P, rd<float>(b, L.f), rd<float>(b, L.soundspeed));
-  S.fq2[p] = make_float4(rd<float>(b, L.balsara), h, u, __int_as_float((int)tb));
+  /* the force loop's test reads the exact h^2 gamma^2 of a source from the spare lane of its payload:
+   * fq2.z (Minimal, Gadget2: u is not read by their force interaction) or fq3.z (SPHENIX) */
+  S.fq2[p] = make_float4(rd<float>(b, L.balsara), h, D.scheme == SCH_SPHENIX ? u : hg2_exact(h),
+                         __int_as_float((int)tb));
   S.f_hdt[p] = rd<float>(b, L.h_dt);
   S.f_vsig[p] = rd<float>(b, L.v_sig);
   S.f_minngb[p] = rd<int8_t>(b, L.min_ngb_time_bin);
@@ -300,7 +320,7 @@ __global__ void k_aos_to_soa(const char *aos, DevLayout D, Soa S, int64_t n, con
     const float al = rd<float>(b, L.visc_alpha), ad = rd<float>(b, L.diff_alpha);
     S.alpha[p] = al;
     S.alpha_diff[p] = ad;
-    S.fq3[p] = make_float4(al, ad, 0.f, 0.f);
+    S.fq3[p] = make_float4(al, ad, hg2_exact(h), 0.f);
     S.div_v_prev[p] = rd<float>(b, L.div_v_previous_step);
     S.div_v_dt[p] = rd<float>(b, L.div_v_dt);
     S.div_v[p] = rd<float>(b, L.div_v);
@@ -508,6 +528,102 @@ __global__ void __launch_bounds__(128)
 }
 
 /* ======================================================================== */
+/* Kernels of the frame pipeline (loops_pipe.cuh)                            */
+/* ======================================================================== */
+/* One warp per frame: F[k] = (float)(x_k - origin) for the particles of the
+ * frame's cell - the reference's pix / pjx of functions_hydro.h:1327-1338,
+ * evaluated once per step instead of once per candidate pair. */
+__global__ void __launch_bounds__(128)
+    k_frames(const swiftgpu_handle::FrameRec *recs, int64_t nframes, const double *xs0, const double *xs1,
+             const double *xs2, float4 *frames) {
+  const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (f >= nframes) return;
+  const swiftgpu_handle::FrameRec R = recs[f];
+  float4 *out = frames + R.off;
+  for (int k = lane; k < R.count; k += 32) {
+    const size_t p = (size_t)R.first + k;
+    out[k] = make_float4(dsubf(xs0[p], R.o[0]), dsubf(xs1[p], R.o[1]), dsubf(xs2[p], R.o[2]), 0.f);
+  }
+}
+/* Octet boxes in the cell's OWN frame (float)(x - loc): what the culls of the
+ * frame pipeline compare, shifted by the per-item float offset `d`. */
+__global__ void __launch_bounds__(128)
+    k_octet_boxes_own(const DevCell *cells, int ncells, const int32_t *box_first, const double *xs0,
+                      const double *xs1, const double *xs2, float4 *boxes) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= ncells) return;
+  const DevCell C = cells[c];
+  const int first = C.first, count = C.count;
+  const int noct = (count + 7) >> 3;
+  float4 *out = boxes + 2 * (size_t)box_first[c];
+  for (int o = lane; o < noct; o += 32) {
+    float lo0 = 3.0e30f, lo1 = 3.0e30f, lo2 = 3.0e30f, hi0 = -3.0e30f, hi1 = -3.0e30f, hi2 = -3.0e30f;
+    const int k1 = min(count, 8 * o + 8);
+    for (int k = 8 * o; k < k1; k++) {
+      const size_t p = (size_t)first + k;
+      const float fx = dsubf(xs0[p], C.loc[0]), fy = dsubf(xs1[p], C.loc[1]), fz = dsubf(xs2[p], C.loc[2]);
+      lo0 = fminf(lo0, fx); lo1 = fminf(lo1, fy); lo2 = fminf(lo2, fz);
+      hi0 = fmaxf(hi0, fx); hi1 = fmaxf(hi1, fy); hi2 = fmaxf(hi2, fz);
+    }
+    out[2 * o] = make_float4(lo0, lo1, lo2, 0.f);
+    out[2 * o + 1] = make_float4(hi0, hi1, hi2, 0.f);
+  }
+}
+/* One warp per (group, 64-target chunk) of the host task list: the TaskRec of
+ * every NON-EMPTY task, compacted (the order of the heaviest-first list is kept
+ * up to the scheduling of the warps). */
+__global__ void __launch_bounds__(128)
+    k_task_recs(const int32_t *task_group, const int32_t *task_chunk, int ntasks, const Group *groups,
+                const DevCell *cells, const int32_t *tgt_first, const int32_t *tgt_count,
+                const int32_t *tgt_list, const double *xs0, const double *xs1, const double *xs2,
+                const float *h, TaskRec *recs, unsigned int *ntask_dev) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= ntasks) return;
+  const int g = task_group[w];
+  const int nt = tgt_count[g];
+  const int t0 = task_chunk[w] * PL_TARGETS;
+  if (t0 >= nt) return;
+  const int n = min(PL_TARGETS, nt - t0);
+  const Group G = groups[g];
+  const DevCell C = cells[G.tcell];
+  const int off = tgt_first[g] + t0;
+  float lo[3] = {3.0e30f, 3.0e30f, 3.0e30f}, hi[3] = {-3.0e30f, -3.0e30f, -3.0e30f}, rmax = 0.f;
+  for (int k = lane; k < n; k += 32) {
+    const int ti = tgt_list[off + k];
+    const float f[3] = {dsubf(xs0[ti], C.loc[0]), dsubf(xs1[ti], C.loc[1]), dsubf(xs2[ti], C.loc[2])};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      lo[a] = fminf(lo[a], f[a]);
+      hi[a] = fmaxf(hi[a], f[a]);
+    }
+    rmax = fmaxf(rmax, __fmul_rn(h[ti], KERNEL_GAMMA));
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    lo[a] = warp_min(lo[a]);
+    hi[a] = warp_max(hi[a]);
+  }
+  rmax = warp_max(rmax);
+  if (lane == 0) {
+    TaskRec R;
+    R.item_first = G.item_first;
+    R.item_count = G.item_count;
+    R.tgt_off = off;
+    R.ntgt = n;
+    R.tcell = G.tcell;
+    for (int a = 0; a < 3; a++) {
+      R.lo[a] = lo[a];
+      R.hi[a] = hi[a];
+    }
+    R.rmax = rmax;
+    recs[atomicAdd(ntask_dev, 1u)] = R;
+  }
+}
+
+/* ======================================================================== */
 /* Kernel: target lists (active particles of each group's cell)              */
 /* ======================================================================== */
 __global__ void k_build_targets(const Group *groups, int ngroups, const DevCell *cells,
@@ -637,10 +753,10 @@ __device__ __forceinline__ void ghost_finalise(const GhostArgs &G, int p, float 
   }
   S.rho[p] = rho;
   S.fq1[p] = make_float4(rho, P, f, cs);
-  S.fq2[p] = make_float4(balsara, h, u, __int_as_float(tb));
+  S.fq2[p] = make_float4(balsara, h, SCHEME == SCH_SPHENIX ? u : hg2_exact(h), __int_as_float(tb));
   if (SCHEME == SCH_SPHENIX) {
     const float al = S.alpha[p];
-    S.fq3[p] = make_float4(al, S.alpha_diff[p], 0.f, 0.f);
+    S.fq3[p] = make_float4(al, S.alpha_diff[p], hg2_exact(h), 0.f);
     S.div_v[p] = div_v;
     S.g_vsig[p] = 2.f * cs; /* hydro_reset_gradient */
     S.g_amax[p] = al;
@@ -877,7 +993,7 @@ __global__ void __launch_bounds__(128) k_extra_ghost(const ExtraArgs E) {
     new_ad = fminf(new_ad, viscous_diffusion_limit);
     S.alpha_diff[p] = new_ad;
     S.g_lap[p] = laplace_u;
-    S.fq3[p] = make_float4(alpha, new_ad, 0.f, 0.f);
+    S.fq3[p] = make_float4(alpha, new_ad, hg2_exact(h), 0.f);
     /* hydro_reset_acceleration + timestep_limiter_prepare_force */
     S.fo1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     S.f_hdt[p] = 0.f;
@@ -1095,6 +1211,7 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   cudaFree(h->d_flag); cudaFree(h->d_force_bits); cudaFree(h->d_loop1_bits); cudaFree(h->d_grad_bits);
   cudaFree(h->d_dxp_old); cudaFree(h->d_hmax_tmp);
   cudaFree(h->boxes); cudaFree(h->d_box_first); cudaFree(h->d_leaves);
+  cudaFree(h->d_frames); cudaFree(h->d_frame_recs);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1157,6 +1274,47 @@ static cudaError_t to_device(T **dst, const std::vector<T> &v) {
   return e;
 }
 
+/* The frame array an item reads: the source cell's particles relative to the
+ * origin of the reference's leaf-level call (functions_hydro.h:1327-1338).
+ * slot 0 = the cell's own frame (x - loc): sources of DOPAIR when the cell is
+ * the right cell cj, DOSELF_SUBSET, and the prefilter frame of the double
+ * modes; slot 1 + sid = x - (cj->loc + shift) when the cell is the left cell ci
+ * of a pair of orientation sid. Frames are shared by all lists. */
+static uint32_t frame_of(H *h, const Item &it) {
+  const int slot = it.mode == MODE_PAIR_R ? 1 + it.sid : 0;
+  const swiftgpu_cell &sc = h->cells[it.scell];
+  double o[3];
+  for (int k = 0; k < 3; k++) {
+    if (slot == 0)
+      o[k] = sc.loc[k];
+    else /* the targets' cell is cj: origin cj->loc + shift, as the device derives it */
+      o[k] = h->cells[it.tcell].loc[k] + (double)it.shift[k] * h->cfg.dim[k];
+  }
+  int32_t &idx = h->frame_idx[(size_t)it.scell * 14 + slot];
+  if (idx >= 0) {
+    const H::FrameRec &F = h->frames_host[idx];
+    if (F.o[0] == o[0] && F.o[1] == o[1] && F.o[2] == o[2]) return F.off;
+    /* same (cell, orientation) with another origin (tiny periodic grids): look for it, else append */
+    for (size_t k = 0; k < h->frames_host.size(); k++) {
+      const H::FrameRec &E = h->frames_host[k];
+      if (E.first == (int32_t)sc.first_part && E.count == sc.count && E.o[0] == o[0] && E.o[1] == o[1] &&
+          E.o[2] == o[2])
+        return E.off;
+    }
+  }
+  H::FrameRec F;
+  F.first = (int32_t)sc.first_part;
+  F.count = sc.count;
+  for (int k = 0; k < 3; k++) F.o[k] = o[k];
+  F.off = (uint32_t)h->frames_total;
+  F.pad = 0;
+  h->frames_total += (uint64_t)sc.count;
+  if (idx < 0) idx = (int32_t)h->frames_host.size();
+  h->frames_host.push_back(F);
+  h->frames_valid = false;
+  return F.off;
+}
+
 static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
   D.release();
   D.ngroups = (int)W.groups.size();
@@ -1184,7 +1342,10 @@ static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
   }
   D.ntasks = (int)tg.size();
   D.tgt_total = subset ? h->n : tot;
-  CK(to_device(&D.items, W.items));
+  std::vector<Item> items(W.items);
+  for (Item &it : items) it.sframe = frame_of(h, it);
+  if (h->frames_total > 0xfffffff0ull) return h->fail("frame arrays exceed 2^32 entries");
+  CK(to_device(&D.items, items));
   CK(to_device(&D.groups, W.groups));
   CK(to_device(&D.task_group, tg));
   CK(to_device(&D.task_chunk, tc));
@@ -1192,6 +1353,7 @@ static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
   CK(cudaMalloc((void **)&D.tgt_count, std::max(D.ngroups, 1) * sizeof(int32_t)));
   CK(cudaMemset(D.tgt_count, 0, std::max(D.ngroups, 1) * sizeof(int32_t)));
   CK(cudaMalloc((void **)&D.tgt_list, std::max<int64_t>(D.tgt_total, 1) * sizeof(int32_t)));
+  CK(cudaMalloc((void **)&D.task_recs, std::max(D.ntasks, 1) * sizeof(TaskRec)));
   return 0;
 }
 
@@ -1238,6 +1400,10 @@ static int build_lists(H *h, int which) {
               h->cfg.periodic, h->cfg.rank, h->step.ti_current);
   WorkList Wd, Ws, Wf, Wg;
   if (which == LISTS_ALL) {
+    h->frames_host.clear();
+    h->frame_idx.assign((size_t)h->ncells * 14, -1);
+    h->frames_total = 0;
+    h->frames_valid = false;
     F.build_loop(0, Wd);
     std::vector<int32_t> aux;
     F.build_subset(Ws, aux);
@@ -1561,13 +1727,46 @@ static float tile_maxdim(const H *h) {
 static float tile_margin(const H *h) { return 1.0e-6f * tile_maxdim(h); }
 /* r-margin under which the sorted-axis conditions are implied (key rounding < 5e-7 * dim) */
 static float tile_keyE(const H *h) { return 2.0e-6f * tile_maxdim(h); }
+/* (Re)computes the frame arrays of the current positions (all of them: positions moved, or the
+ * frame table grew with a rebuilt list). */
+static int ensure_frames(H *h) {
+  if (h->frames_valid) return 0;
+  if (h->frames_total > h->frames_cap || !h->d_frames) {
+    cudaFree(h->d_frames);
+    h->d_frames = nullptr;
+    h->frames_cap = h->frames_total + h->frames_total / 16 + 64;
+    CK(cudaMalloc((void **)&h->d_frames, sizeof(float4) * (size_t)h->frames_cap));
+  }
+  if (h->frame_recs_uploaded != h->frames_host.size() || !h->d_frame_recs) {
+    CK(to_device(&h->d_frame_recs, h->frames_host));
+    h->frame_recs_uploaded = h->frames_host.size();
+  }
+  const int64_t nf = (int64_t)h->frames_host.size();
+  if (nf > 0) {
+    k_frames<<<(unsigned)((nf * 32 + 127) / 128), 128, 0, h->stream>>>(h->d_frame_recs, nf, h->xs, h->xs + (h->n + 4),
+                                                                     h->xs + 2 * (h->n + 4), h->d_frames);
+    h->stats.n_launches++;
+    CK(cudaGetLastError());
+  }
+  h->frames_valid = true;
+  return 0;
+}
 static int prep_tiles(H *h) {
   const int64_t n = h->n;
   k_prep_tiles<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->x, h->hh, n, tile_margin(h), h->xf,
                                                                   h->xs);
-  k_octet_boxes<<<(h->ncells * 32 + 127) / 128, 128, 0, h->stream>>>(h->d_cells, h->ncells,
-                                                                     h->d_box_first, h->xf, h->boxes);
-  h->stats.n_launches += 2;
+  h->stats.n_launches++;
+  if (loop_kind() == 3) {
+    k_octet_boxes_own<<<(h->ncells * 32 + 127) / 128, 128, 0, h->stream>>>(
+        h->d_cells, h->ncells, h->d_box_first, h->xs, h->xs + (n + 4), h->xs + 2 * (n + 4), h->boxes);
+    h->stats.n_launches++;
+    h->frames_valid = false;
+    if (ensure_frames(h)) return 1;
+  } else {
+    k_octet_boxes<<<(h->ncells * 32 + 127) / 128, 128, 0, h->stream>>>(h->d_cells, h->ncells,
+                                                                       h->d_box_first, h->xf, h->boxes);
+    h->stats.n_launches++;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1584,7 +1783,7 @@ static int launch_extrema(H *h) {
   return 0;
 }
 static int launch_sort(H *h, bool full) {
-  if (loop_kind() == 2 && prep_tiles(h)) return 1;
+  if (loop_kind() >= 2 && prep_tiles(h)) return 1;
   if (launch_extrema(h)) return 1;
   if (full && h->nsegs > 0) {
     k_sort<<<h->nsegs, 256, 0, h->stream>>>(h->d_segs, h->d_cells, h->x, h->sort_idx, h->d_sort_keys);
@@ -1625,11 +1824,14 @@ static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
   A.keyE = tile_keyE(h);
   A.margin = tile_margin(h);
   A.task_counter = (unsigned int *)(h->d_counters + 14);
+  A.frames = h->d_frames;
+  A.task_recs = D.task_recs;
+  A.ntask_dev = (const unsigned int *)(h->d_counters + 15);
   {
     static int hold = -1;
     if (hold < 0) {
       const char *e = getenv("SWIFTGPU_HOLD");
-      hold = e ? atoi(e) : 2; /* 2 of the 3-4 ring stages held, the rest in flight */
+      hold = e ? atoi(e) : (loop_kind() == 3 ? 0 : 2); /* tile: stages held before a drain; pipe: debug bits */
     }
     A.hold = hold;
   }
@@ -1666,8 +1868,23 @@ static int build_targets(H *h, DevList &D, bool *sparse_out = nullptr) {
     unsigned long long t[2] = {0, 0};
     CK(cudaMemcpyAsync(t, h->d_counters + 12, sizeof(t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->stats.n_host_syncs++;
     *sparse_out = t[1] > 0 && t[0] < (unsigned long long)sparse_threshold() * t[1];
   }
+  return 0;
+}
+
+/* The compacted TaskRecs of one launch of the frame pipeline, from the target lists as they are NOW
+ * (no host round trip: the kernel reads the number of tasks from device memory). */
+static int build_task_recs(H *h, const DevList &D) {
+  CK(cudaMemsetAsync(h->d_counters + 15, 0, sizeof(unsigned long long), h->stream));
+  if (D.ntasks == 0) return 0;
+  const int64_t n = h->n;
+  k_task_recs<<<(unsigned)(((int64_t)D.ntasks * 32 + 127) / 128), 128, 0, h->stream>>>(
+      D.task_group, D.task_chunk, D.ntasks, D.groups, h->d_cells, D.tgt_first, D.tgt_count, D.tgt_list, h->xs,
+      h->xs + (n + 4), h->xs + 2 * (n + 4), h->hh, D.task_recs, (unsigned int *)(h->d_counters + 15));
+  h->stats.n_launches++;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -1681,14 +1898,15 @@ static int read_counter(H *h, int k, int64_t *out) {
 
 /* CTA-cooperative type-1 loops (loops_cta.cuh); SWIFTGPU_WARP_LOOPS=1 selects the
  * warp-private kernels of loops.cuh instead (kept for A/B measurements). */
-/* SWIFTGPU_LOOPS=tile (default: TMA pipeline, loops_tile.cuh) | cta (loops_cta.cuh) |
- * warp (loops.cuh); the older kernels are kept for A/B measurements. */
+/* SWIFTGPU_LOOPS=pipe (default: frame pipeline, loops_pipe.cuh) | tile (loops_tile.cuh) | cta
+ * (loops_cta.cuh) | warp (loops.cuh); the older kernels are kept for A/B measurements. */
 static int loop_kind() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("SWIFTGPU_LOOPS");
     const char *w = getenv("SWIFTGPU_WARP_LOOPS");
-    v = 2;
+    v = 3;
+    if (e && !strcmp(e, "tile")) v = 2;
     if (e && !strcmp(e, "cta")) v = 1;
     if (e && !strcmp(e, "warp")) v = 0;
     if (w && w[0] == '1') v = 0;
@@ -1737,6 +1955,56 @@ static cudaError_t launch_tile(H *h, const LoopArgs &A, bool sparse = false) {
   if (sparse) return launch_tile_cw<LOOP, SCHEME, 4>(h, A);
   return launch_tile_cw<LOOP, SCHEME, 8>(h, A);
 }
+/* frame pipeline (loops_pipe.cuh): DS = double-column slots per stage (64: only the self item of a
+ * main loop is evaluated on doubles; 256: the ghost re-runs, where every pair item is) */
+template <int LOOP, int SCHEME, int NS, int DS>
+static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
+  constexpr bool FORCE = (LOOP == LOOP_FORCE);
+  constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
+  constexpr int CW = 8;
+  constexpr int bytes = PipeSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1), CW, DS>::kBytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_pipe<LOOP, SCHEME, NS, CW, DS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  static int resident = 0;
+  if (!resident) {
+    int per_sm = 0, sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipe<LOOP, SCHEME, NS, CW, DS>,
+                                                                  32 * (CW + 1), bytes);
+    if (e != cudaSuccess) return e;
+    resident = std::max(1, per_sm) * std::max(1, sms);
+    if (getenv("SWIFTGPU_VERBOSE"))
+      fprintf(stderr, "k_pipe<%d,%d,NS=%d,DS=%d>: %d B smem, %d CTAs/SM\n", LOOP, SCHEME, NS, DS, bytes, per_sm);
+  }
+  const int grid = (int)std::min<long long>(A.ntasks, resident);
+  if (grid <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(A.task_counter, 0, sizeof(unsigned int), h->stream);
+  if (e != cudaSuccess) return e;
+  k_pipe<LOOP, SCHEME, NS, CW, DS><<<grid, 32 * (CW + 1), bytes, h->stream>>>(A);
+  return cudaGetLastError();
+}
+#ifndef PL_NS_DENSITY
+#define PL_NS_DENSITY 4
+#define PL_NS_SUBSET 3
+#define PL_NS_GRADIENT 3
+#define PL_NS_FORCE 4
+#define PL_NS_FORCE_SPHENIX 3
+#endif
+template <int LOOP, bool SUBSET, int SCHEME>
+static cudaError_t launch_pipe(H *h, const LoopArgs &A) {
+  if (LOOP == LOOP_FORCE)
+    return launch_pipe_ns<LOOP_FORCE, SCHEME, (SCHEME == SCH_SPHENIX ? PL_NS_FORCE_SPHENIX : PL_NS_FORCE), 64>(h, A);
+  if (LOOP == LOOP_GRADIENT) return launch_pipe_ns<LOOP_GRADIENT, 0, PL_NS_GRADIENT, 64>(h, A);
+  if (SUBSET) return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SUBSET, 256>(h, A);
+  return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_DENSITY, 64>(h, A);
+}
+
 template <int LOOP, bool SUBSET, int SCHEME>
 static cudaError_t launch_cta(H *h, const LoopArgs &A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
@@ -1754,6 +2022,7 @@ static cudaError_t launch_cta(H *h, const LoopArgs &A) {
 }
 template <int LOOP, bool SUBSET>
 static cudaError_t launch_loop1(H *h, const LoopArgs &A, bool sparse = false) {
+  if (loop_kind() == 3) return launch_pipe<LOOP, SUBSET, 0>(h, A);
   if (loop_kind() == 2) return launch_tile<LOOP, 0>(h, A, sparse);
   if (use_cta_loops()) return launch_cta<LOOP, SUBSET, 0>(h, A);
   k_loop1<LOOP, SUBSET><<<A.ntasks, 32, Tile1<LOOP, SUBSET>::kBytes, h->stream>>>(A);
@@ -1761,6 +2030,7 @@ static cudaError_t launch_loop1(H *h, const LoopArgs &A, bool sparse = false) {
 }
 template <int SCHEME>
 static cudaError_t launch_loop2(H *h, const LoopArgs &A, bool sparse = false) {
+  if (loop_kind() == 3) return launch_pipe<LOOP_FORCE, false, SCHEME>(h, A);
   if (loop_kind() == 2) return launch_tile<LOOP_FORCE, SCHEME>(h, A, sparse);
   if (use_cta_loops()) return launch_cta<LOOP_FORCE, false, SCHEME>(h, A);
   k_loop2<SCHEME><<<A.ntasks, 32, Tile2<SCHEME>::kBytes, h->stream>>>(A);
@@ -1783,6 +2053,7 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 8, 0, sizeof(unsigned long long), h->stream));
   bool sparse = false;
   if (build_targets(h, h->L_density, &sparse)) return 1;
+  if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, h->L_density))) return 1;
   if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->nd, 0);
     CK((launch_loop1<LOOP_DENSITY, false>(h, A, sparse)));
@@ -1858,6 +2129,7 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
       /* re-run the density loop for the unconverged particles
        * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
       CK(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long), h->stream));
+      if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, D))) return 1;
       LoopArgs A = loop_args(h, D, h->nd, 4);
       /* few unconverged particles per leaf: smaller CTAs, more of them per SM */
       const bool sparse = redo < (int64_t)sparse_threshold() * D.ngroups;
@@ -1931,7 +2203,8 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
   bool sparse = false;
   if (build_targets(h, L, &sparse)) return 1; /* depth_h changed in the ghost */
-  if (loop_kind() == 2) {
+  if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, L))) return 1;
+  if (loop_kind() >= 2) {
     k_prep_gq<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->fq1, h->fq2, h->fq3, h->n, h->gq);
     h->stats.n_launches++;
   }
@@ -1986,6 +2259,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(unsigned long long), h->stream));
   bool sparse = false;
   if (build_targets(h, h->L_force, &sparse)) return 1;
+  if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, h->L_force))) return 1;
   if (loop_kind() == 2) { /* h changed in the ghost (and the rho halo): source reach of the prefilter */
     k_refresh_reach<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->hh, h->n, tile_margin(h),
                                                                           h->xf);

@@ -62,7 +62,7 @@ enum ItemMode : int {
   MODE_SUB_PAIR_F = 5   /* DOPAIR_SUBSET, flipped: sources descending */
 };
 
-/* 16-byte directed item. `tcell` holds the targets, `scell` the sources.
+/* 24-byte directed item. `tcell` holds the targets, `scell` the sources.
  * For the PAIR modes ci/cj (after space_getsid_and_swap_cells) are
  * (tcell,scell) for MODE_PAIR_L and (scell,tcell) for MODE_PAIR_R. */
 struct Item {
@@ -74,8 +74,10 @@ struct Item {
   int8_t max_depth;
   int8_t shift[3]; /* periodic shift in units of dim[k] (of the ORIENTED pair) */
   uint8_t flags;   /* bit0: limit_max_h (h_max clamp = ci->h_max_allowed) */
+  uint32_t sframe; /* offset (float4 units) of the source cell's frame array this item reads (loops_pipe.cuh) */
+  uint32_t pad_;
 };
-static_assert(sizeof(Item) == 16, "Item must be 16 bytes");
+static_assert(sizeof(Item) == 24, "Item must be 24 bytes");
 
 /* A group = all items sharing a target cell, contiguous in the item array. */
 struct Group {
@@ -291,6 +293,8 @@ class Flattener {
     r.it.max_depth = (int8_t)max_depth;
     for (int k = 0; k < 3; k++) r.it.shift[k] = shift ? shift[k] : 0;
     r.it.flags = (uint8_t)(limit_max_h ? 1 : 0);
+    r.it.sframe = 0;
+    r.it.pad_ = 0;
     r.aux = aux;
     raw_.push_back(r);
   }
