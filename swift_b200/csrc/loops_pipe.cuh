@@ -112,8 +112,7 @@ struct PipeSmem {
   static constexpr int kBox = kBar + 2 * NS * 8;
   static constexpr int kWin = kBox + (CW + 1) * 32; /* producer: 2 windows of 32 items */
   static constexpr int kWinAux = kWin + 2 * 32 * (int)sizeof(PipeItem);
-  static constexpr int kTX = kWinAux + 2 * 32 * 16; /* target doubles: 3 columns of PL_TARGETS */
-  static constexpr int kBytes = kTX + 3 * PL_TARGETS * 8;
+  static constexpr int kBytes = kWinAux + 2 * 32 * 16;
 };
 
 /* stage meta: 16 words */
@@ -122,10 +121,10 @@ enum { PM_NFR = 0, PM_NOCT = 1, PM_FLAG = 2, PM_TASK = 3, PM_TGT_OFF = 4, PM_NTG
 /* force payload lane of the exact hj^2 gamma^2 of the source (k_ghost / k_aos_to_soa keep it there) */
 #define PL_HG2_COL(SCHEME) ((SCHEME) == SCH_SPHENIX ? 3 : 2)
 
-#define PL_MIN_BLOCKS(LOOP) ((LOOP) == LOOP_FORCE ? 2 : 3)
+#define PL_MIN_BLOCKS(LOOP) 2
 
 template <int LOOP, int SCHEME, int NS, int CW, int DS>
-__global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(const LoopArgs A) {
+__global__ void __launch_bounds__(32 * (CW + 1), 2) k_pipe(const LoopArgs A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
   constexpr int QCAP = FORCE ? TL_SUBCAP2 : TL_SUBCAP1;
@@ -587,7 +586,6 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
   float th = 1.f, tvx = 0.f, tvy = 0.f, tvz = 0.f, tu = 0.f, tcs = 0.f;
   float thg2 = 0.f, th_inv = 1.f, thg = 0.f, tsure2 = 0.f, r2e = 0.f;
   ForceQ tq;
-  double *const sTX = (double *)(smem + SM::kTX) + warp * 8 + t8;
   float4 *const sTP = (float4 *)(smem + SM::kTP) + warp * (2 * PL_FRAGS * 8); /* [par][frag][t8] */
 
   DensityAcc dacc;
@@ -770,12 +768,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP)) k_pipe(con
       tox = dsubf(tx, l0);
       toy = dsubf(ty, l1);
       toz = dsubf(tz, l2);
-      __syncwarp(); /* the previous task's drains are done with sTX / sBox / sTP */
-      if (s4 == 0) {
-        sTX[0] = tx;
-        sTX[PL_TARGETS] = ty;
-        sTX[2 * PL_TARGETS] = tz;
-      }
+      __syncwarp(); /* the previous task's drains are done with sBox / sTP */
       /* the warp's target box (own-frame floats of the target cell) and its reach */
       float blo[3], bhi[3], rmax;
       blo[0] = tvalid ? tox : 3.0e30f;

@@ -167,6 +167,15 @@ __device__ __forceinline__ void iact_density(DensityAcc &a, float r2, float dx, 
   a.rot[2] += faci * (dvx * dy - dvy * dx);
 }
 
+/* The same for a candidate that may be masked out (evaluated unconditionally, discarded if !ok). */
+__device__ __forceinline__ void iact_density_masked(DensityAcc &a, float r2, float dx, float dy, float dz,
+                                                    float hi_inv, float vix, float viy, float viz, float mj,
+                                                    float vjx, float vjy, float vjz, bool ok) {
+  const DensityAcc old = a;
+  iact_density(a, r2, dx, dy, dz, hi_inv, vix, viy, viz, mj, vjx, vjy, vjz);
+  if (!ok) a = old;
+}
+
 struct GradientAcc {
   float v_sig, laplace_u, alpha_max;
 };
@@ -296,6 +305,16 @@ __device__ __forceinline__ void iact_force(ForceAcc &a, float r2, float dx, floa
     a.h_dt -= mj * dvdr * r_inv * rhoj_inv * wi_dr;
   }
   if (pj.time_bin > 0) a.min_ngb = min(a.min_ngb, pj.time_bin);
+}
+
+/* iact_force for a candidate that may be masked out: evaluated unconditionally (so that two
+ * candidates interleave in one basic block), the accumulators keep their old values if !ok. */
+template <int SCHEME>
+__device__ __forceinline__ void iact_force_masked(ForceAcc &a, float r2, float dx, float dy, float dz,
+                                                  const ForceQ &pi, const ForceQ &pj, float a2_Hubble, bool ok) {
+  const ForceAcc old = a;
+  iact_force<SCHEME>(a, r2, dx, dy, dz, pi, pj, a2_Hubble);
+  if (!ok) a = old;
 }
 
 }  // namespace swiftgpu

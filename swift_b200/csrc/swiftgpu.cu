@@ -28,6 +28,7 @@
 #include "loops_cta.cuh"
 #include "loops_tile.cuh"
 #include "loops_pipe.cuh"
+#include "loops_direct.cuh"
 
 using namespace swiftgpu;
 
@@ -131,6 +132,7 @@ struct swiftgpu_handle {
   std::vector<FrameRec> frames_host;
   std::vector<int32_t> frame_idx; /* [cell * 14 + slot] -> index into frames_host (slot 0: own frame, 1 + sid: ci frames) */
   float4 *d_frames = nullptr;
+  int2 *d_flat_tgt = nullptr; /* (target, group) list of a sparse launch (loops_direct.cuh) */
   FrameRec *d_frame_recs = nullptr;
   uint64_t frames_total = 0, frames_cap = 0;
   size_t frame_recs_uploaded = 0;
@@ -1181,6 +1183,8 @@ static void free_parts(H *h) {
   cudaFree(h->xf); cudaFree(h->xs); cudaFree(h->gq);
   cudaFree(h->d_d2h); cudaFree(h->d_h2d); cudaFree(h->d_cnt_tmp); cudaFree(h->dt_cfl);
   h->d_d2h = h->d_h2d = h->d_cnt_tmp = nullptr;
+  cudaFree(h->d_flat_tgt);
+  h->d_flat_tgt = nullptr;
   h->dt_cfl = nullptr;
   h->xf = h->gq = nullptr; h->xs = nullptr;
   h->d_aos = nullptr; h->x = nullptr;
@@ -1211,7 +1215,7 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   cudaFree(h->d_flag); cudaFree(h->d_force_bits); cudaFree(h->d_loop1_bits); cudaFree(h->d_grad_bits);
   cudaFree(h->d_dxp_old); cudaFree(h->d_hmax_tmp);
   cudaFree(h->boxes); cudaFree(h->d_box_first); cudaFree(h->d_leaves);
-  cudaFree(h->d_frames); cudaFree(h->d_frame_recs);
+  cudaFree(h->d_frames); cudaFree(h->d_frame_recs); cudaFree(h->d_flat_tgt);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1955,6 +1959,26 @@ static cudaError_t launch_tile(H *h, const LoopArgs &A, bool sparse = false) {
   if (sparse) return launch_tile_cw<LOOP, SCHEME, 4>(h, A);
   return launch_tile_cw<LOOP, SCHEME, 8>(h, A);
 }
+/* sparse target sets (late ghost iterations): one warp per target, loops_direct.cuh */
+static int launch_direct_density(H *h, const DevList &D, const LoopArgs &A) {
+  if (!h->d_flat_tgt) CK(cudaMalloc((void **)&h->d_flat_tgt, sizeof(int2) * (size_t)std::max<int64_t>(h->n, 1)));
+  unsigned int *nflat = (unsigned int *)(h->d_counters + 15);
+  CK(cudaMemsetAsync(nflat, 0, sizeof(unsigned long long), h->stream));
+  if (D.ngroups == 0) return 0;
+  k_flat_targets<<<(D.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(D.groups, D.ngroups, D.tgt_first, D.tgt_count,
+                                                                     D.tgt_list, h->d_flat_tgt, nflat);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  k_direct<LOOP_DENSITY><<<sms * 8, 256, 0, h->stream>>>(A, h->d_flat_tgt, nflat);
+  h->stats.n_launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 /* frame pipeline (loops_pipe.cuh): DS = double-column slots per stage (64: only the self item of a
  * main loop is evaluated on doubles; 256: the ghost re-runs, where every pair item is) */
 template <int LOOP, int SCHEME, int NS, int DS>
@@ -1990,9 +2014,12 @@ static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
   return cudaGetLastError();
 }
 #ifndef PL_NS_DENSITY
-#define PL_NS_DENSITY 4
-#define PL_NS_SUBSET 3
-#define PL_NS_GRADIENT 3
+/* ring depth = what fits 2 CTAs per SM: the consumer warps of a CTA need different stages (each
+ * culls against its own 8 targets), so the fastest runs ahead of the slowest by up to the ring depth;
+ * a deeper ring is what removes the full-barrier waits (ncu: 17-27 % of the samples at 4 stages) */
+#define PL_NS_DENSITY 7
+#define PL_NS_SUBSET 5
+#define PL_NS_GRADIENT 5
 #define PL_NS_FORCE 4
 #define PL_NS_FORCE_SPHENIX 3
 #endif
@@ -2129,12 +2156,25 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
       /* re-run the density loop for the unconverged particles
        * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
       CK(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long), h->stream));
-      if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, D))) return 1;
-      LoopArgs A = loop_args(h, D, h->nd, 4);
-      /* few unconverged particles per leaf: smaller CTAs, more of them per SM */
+      /* few unconverged particles per leaf: (pipe) one warp per target straight from L2, (tile)
+       * smaller CTAs, more of them per SM */
       const bool sparse = redo < (int64_t)sparse_threshold() * D.ngroups;
-      CK((launch_loop1<LOOP_DENSITY, true>(h, A, sparse)));
-      h->stats.n_launches++;
+      static int direct_thr = -1;
+      if (direct_thr < 0) {
+        const char *e = getenv("SWIFTGPU_DIRECT");
+        direct_thr = e ? atoi(e) : 4; /* unconverged particles per leaf below which the per-target kernel wins */
+      }
+      if (getenv("SWIFTGPU_VERBOSE")) fprintf(stderr, "ghost iteration %d: %lld to redo in %d leaves\n", iter, (long long)redo, D.ngroups);
+      if (loop_kind() == 3 && redo < (int64_t)direct_thr * D.ngroups) {
+        if (ensure_frames(h)) return 1;
+        LoopArgs A = loop_args(h, D, h->nd, 4);
+        if (launch_direct_density(h, D, A)) return 1;
+      } else {
+        if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, D))) return 1;
+        LoopArgs A = loop_args(h, D, h->nd, 4);
+        CK((launch_loop1<LOOP_DENSITY, true>(h, A, sparse)));
+        h->stats.n_launches++;
+      }
       int64_t nn = 0;
       if (read_counter(h, 4, &nn)) return 1;
       extra_density += nn;
