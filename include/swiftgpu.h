@@ -205,6 +205,14 @@ int swiftgpu_upload_parts(swiftgpu_t *h, const void *parts_aos, int64_t nparts);
 int swiftgpu_upload_parts_device(swiftgpu_t *h, const void *d_parts_aos,
                                  int64_t nparts);
 
+/* Multi-rank: only the rank's OWN particles cross the host boundary. The host's array holds them in
+ * [0, nlocal) and the proxies of the foreign cells behind them (the layout of space->parts /
+ * space->nr_parts in the reference); the proxies' slots [nlocal, ntotal) are filled on the device by
+ * the xv halo exchange - the reference fills them with recv tasks (scheduler.c:1088-1112) - never by
+ * the host. The matching download returns the local particles only. */
+int swiftgpu_upload_parts_local(swiftgpu_t *h, const void *parts_aos, int64_t nlocal, int64_t ntotal);
+int swiftgpu_download_parts_local(swiftgpu_t *h, void *parts_aos, int64_t nlocal);
+
 int swiftgpu_set_step(swiftgpu_t *h, const swiftgpu_step *step);
 
 /* Run all further work of this handle on the caller's CUDA stream

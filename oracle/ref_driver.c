@@ -563,6 +563,13 @@ static double run_kind(swiftref_t *s, enum ref_kind kind, int nthreads) {
     ws[t].next = &next;
     ws[t].runner.e = &s->engine;
     ws[t].runner.id = t;
+#ifdef WITH_VECTORIZATION
+    /* engine_config.c:1038-1043: the particle caches of the hand-vectorised loops */
+    ws[t].runner.ci_cache.count = 0;
+    ws[t].runner.cj_cache.count = 0;
+    cache_init(&ws[t].runner.ci_cache, 512);
+    cache_init(&ws[t].runner.cj_cache, 512);
+#endif
     if (nthreads > 1) pthread_create(&ws[t].th, NULL, worker_main, &ws[t]);
   }
   if (nthreads == 1)
@@ -570,6 +577,12 @@ static double run_kind(swiftref_t *s, enum ref_kind kind, int nthreads) {
   else
     for (int t = 0; t < nthreads; t++) pthread_join(ws[t].th, NULL);
   const double dt = now_s() - t0;
+#ifdef WITH_VECTORIZATION
+  for (int t = 0; t < nthreads; t++) {
+    cache_clean(&ws[t].runner.ci_cache);
+    cache_clean(&ws[t].runner.cj_cache);
+  }
+#endif
   free(ws);
   return dt;
 }

@@ -122,6 +122,8 @@ EXPORTS = [
     ("swiftgpu_upload_cells", C.c_int, [VP, VP, I32, VP, I32]),
     ("swiftgpu_upload_parts", C.c_int, [VP, VP, I64]),
     ("swiftgpu_upload_parts_device", C.c_int, [VP, VP, I64]),
+    ("swiftgpu_upload_parts_local", C.c_int, [VP, VP, I64, I64]),
+    ("swiftgpu_download_parts_local", C.c_int, [VP, VP, I64]),
     ("swiftgpu_set_step", C.c_int, [VP, C.POINTER(Step)]),
     ("swiftgpu_set_stream", C.c_int, [VP, VP]),
     ("swiftgpu_run_sort", C.c_int, [VP]),

@@ -166,12 +166,12 @@ __host__ __device__ __forceinline__ size_t halo_field_offset(const HaloFields &F
   return off;
 }
 
-/* idx holds HOST-order particle indices (identical lists on both ranks);
- * h2d maps them to this rank's device order. */
+/* idx holds particle indices; h2d (may be null: idx are device indices already) maps host-order
+ * indices to this rank's device order. */
 __global__ void k_halo_pack(HaloFields F, const int32_t *idx, const int32_t *h2d, int64_t n, char *buf) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  const size_t p = (size_t)h2d[idx[s]];
+  const size_t p = h2d ? (size_t)h2d[idx[s]] : (size_t)idx[s];
   for (int f = 0; f < F.n; f++) {
     const size_t off = halo_field_offset(F, f, n);
     halo_copy(buf + off + (size_t)F.esz[f] * s, (const char *)F.ptr[f] + (size_t)F.esz[f] * p, F.esz[f]);
@@ -180,7 +180,7 @@ __global__ void k_halo_pack(HaloFields F, const int32_t *idx, const int32_t *h2d
 __global__ void k_halo_unpack(HaloFields F, const int32_t *idx, const int32_t *h2d, int64_t n, const char *buf) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  const size_t p = (size_t)h2d[idx[s]];
+  const size_t p = h2d ? (size_t)h2d[idx[s]] : (size_t)idx[s];
   for (int f = 0; f < F.n; f++) {
     const size_t off = halo_field_offset(F, f, n);
     halo_copy((char *)F.ptr[f] + (size_t)F.esz[f] * p, buf + off + (size_t)F.esz[f] * s, F.esz[f]);

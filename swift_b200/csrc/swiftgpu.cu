@@ -89,6 +89,7 @@ struct swiftgpu_handle {
   std::vector<uint8_t> force_bits; /* recursion predicate bits the force list was built with */
   std::vector<uint8_t> loop1_bits; /* ... and the density list (cell.h:951,992), revalidated for the gradient loop */
   int64_t n = 0;
+  int64_t n_host = 0; /* particles that cross the host boundary: [0, n_host) (all, or the local ones) */
   int ncells = 0;
 
   /* device */
@@ -1191,12 +1192,12 @@ static void free_parts(H *h) {
   h->n = 0;
 }
 
-static void halo_release(H *h) {
+static void halo_release(H *h, bool keep_comm = false) {
   for (HaloPeer &P : h->halo) {
     cudaFree(P.d_send_idx); cudaFree(P.d_recv_idx); cudaFree(P.d_sendbuf); cudaFree(P.d_recvbuf);
   }
   h->halo.clear();
-  if (h->comm) {
+  if (h->comm && !keep_comm) {
     std::string e;
     NcclApi *N = nccl_api(e);
     if (N) N->CommDestroy(h->comm);
@@ -1644,6 +1645,9 @@ static int build_device_order(H *h) {
     for (const swiftgpu_cell &c : h->cells) {
       if (c.split || c.count <= 1) continue;
       if (c.first_part < 0 || c.first_part + c.count > n) return h->fail("cell range outside the particle array");
+      /* proxies keep the order they arrive in: the halo exchange ships every cell in the SENDER's
+       * device order (its Morton order), the same in all three phases */
+      if (h->cfg.nranks > 1 && c.nodeID != h->cfg.rank) continue;
       LeafRec R;
       for (int k = 0; k < 3; k++) {
         R.loc[k] = c.loc[k];
@@ -1679,7 +1683,8 @@ static int transpose_in(H *h) {
   CK(cudaMemsetAsync(h->dA, 0, sizeof(float4) * n, h->stream));
   CK(cudaMemsetAsync(h->dB, 0, sizeof(float4) * n, h->stream));
   CK(cudaMemsetAsync(h->fq3, 0, sizeof(float4) * n, h->stream));
-  k_aos_to_soa<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_aos, D, soa_of(h), n, h->d_d2h);
+  const int64_t nh = h->n_host > 0 ? h->n_host : n;
+  k_aos_to_soa<<<(unsigned)((nh + 255) / 256), 256, 0, h->stream>>>(h->d_aos, D, soa_of(h), nh, h->d_d2h);
   h->stats.n_launches++;
   CK(cudaGetLastError());
   h->phases_done = 0;
@@ -1693,7 +1698,25 @@ extern "C" int swiftgpu_upload_parts(swiftgpu_t *h, const void *parts_aos, int64
   if (!h || !parts_aos || nparts <= 0) return 1;
   cudaSetDevice(h->cfg.device);
   if (alloc_parts(h, nparts)) return 1;
+  h->n_host = nparts;
   CK(cudaMemcpyAsync(h->d_aos, parts_aos, h->aos_bytes, cudaMemcpyHostToDevice, h->stream));
+  return transpose_in(h);
+}
+
+/* Only the rank's OWN particles cross the host boundary: space->parts holds them in [0, nlocal) and
+ * the proxies of foreign cells behind them; the proxies' slots are filled by the xv halo exchange
+ * (the reference fills them with recv tasks, scheduler.c:1088-1112), never by the host. */
+extern "C" int swiftgpu_upload_parts_local(swiftgpu_t *h, const void *parts_aos, int64_t nlocal, int64_t ntotal) {
+  if (!h || !parts_aos || nlocal <= 0 || ntotal < nlocal) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (ntotal > nlocal && h->cfg.nranks <= 1) return h->fail("upload_parts_local: proxies without ranks");
+  for (const swiftgpu_cell &c : h->cells)
+    if (c.depth == 0 && c.count > 0 && (c.nodeID == h->cfg.rank) != (c.first_part + c.count <= nlocal))
+      return h->fail("upload_parts_local: the local top-level cells must own exactly the range [0, nlocal)");
+  if (alloc_parts(h, ntotal)) return 1;
+  h->n_host = nlocal;
+  CK(cudaMemcpyAsync(h->d_aos, parts_aos, (size_t)h->cfg.layout.size * (size_t)nlocal, cudaMemcpyHostToDevice,
+                     h->stream));
   return transpose_in(h);
 }
 
@@ -2365,8 +2388,9 @@ static int transpose_out(H *h) {
   D.L = h->cfg.layout;
   D.scheme = h->cfg.scheme;
   const int density_only = (h->phases_done & SWIFTGPU_PHASE_GHOST) ? 0 : 1;
-  k_soa_to_aos<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(
-      h->d_aos, D, soa_of(h), h->n, h->step.max_active_bin, density_only, h->d_d2h);
+  const int64_t nh = h->n_host > 0 ? h->n_host : h->n;
+  k_soa_to_aos<<<(unsigned)((nh + 255) / 256), 256, 0, h->stream>>>(
+      h->d_aos, D, soa_of(h), nh, h->step.max_active_bin, density_only, h->d_d2h);
   h->stats.n_launches++;
   CK(cudaGetLastError());
   return 0;
@@ -2378,6 +2402,17 @@ extern "C" int swiftgpu_download_parts(swiftgpu_t *h, void *parts_aos, int64_t n
   if (transpose_out(h)) return 1;
   CK(cudaMemcpyAsync(parts_aos, h->d_aos, h->aos_bytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int swiftgpu_download_parts_local(swiftgpu_t *h, void *parts_aos, int64_t nlocal) {
+  if (!h || !parts_aos || nlocal <= 0 || nlocal != h->n_host) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (transpose_out(h)) return 1;
+  CK(cudaMemcpyAsync(parts_aos, h->d_aos, (size_t)h->cfg.layout.size * (size_t)nlocal, cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.n_host_syncs++;
   return 0;
 }
 
@@ -2563,11 +2598,15 @@ extern "C" int swiftgpu_halo_setup(swiftgpu_t *h, const void *id128) {
   std::string e;
   NcclApi *N = nccl_api(e);
   if (!N) return h->fail("%s", e.c_str());
-  halo_release(h);
-  sg_ncclUniqueId id;
-  memcpy(&id, id128, sizeof(id));
-  int rc = N->CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank);
-  if (rc != 0) return h->fail("ncclCommInitRank: %s", N->GetErrorString(rc));
+  /* new cells: new send / receive lists; the communicator (one per handle, an NCCL id can be used
+   * once) is kept */
+  halo_release(h, /*keep_comm=*/true);
+  if (!h->comm) {
+    sg_ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    int rc = N->CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank);
+    if (rc != 0) return h->fail("ncclCommInitRank: %s", N->GetErrorString(rc));
+  }
 
   std::map<int, HaloPlan> plans;
   build_halo_plans(h->cells.data(), h->top.data(), (int)h->top.size(), h->cfg.dim, h->cfg.periodic,
@@ -2588,6 +2627,9 @@ extern "C" int swiftgpu_halo_setup(swiftgpu_t *h, const void *id128) {
     std::vector<int32_t> si, ri;
     si.reserve(P.nsend);
     ri.reserve(P.nrecv);
+    /* DEVICE indices: a cell is the same contiguous range on the host and on the device, and its
+     * particles travel in the sender's device order (Morton order inside its leaves), which the
+     * receiver adopts for its proxy of the cell */
     for (int32_t c : kv.second.send_cells)
       for (int k = 0; k < h->cells[c].count; k++) si.push_back((int32_t)h->cells[c].first_part + k);
     for (int32_t c : kv.second.recv_cells)
@@ -2617,7 +2659,7 @@ extern "C" int swiftgpu_halo_exchange(swiftgpu_t *h, int phase) {
   int64_t bytes = 0;
   for (HaloPeer &P : h->halo) {
     if (P.nsend > 0) {
-      k_halo_pack<<<(unsigned)((P.nsend + 255) / 256), 256, 0, h->stream>>>(F, P.d_send_idx, h->d_h2d, P.nsend,
+      k_halo_pack<<<(unsigned)((P.nsend + 255) / 256), 256, 0, h->stream>>>(F, P.d_send_idx, nullptr, P.nsend,
                                                                           P.d_sendbuf);
       h->stats.n_launches++;
     }
@@ -2641,7 +2683,7 @@ extern "C" int swiftgpu_halo_exchange(swiftgpu_t *h, int phase) {
   if (rc != 0) return h->fail("ncclGroupEnd: %s", N->GetErrorString(rc));
   for (HaloPeer &P : h->halo) {
     if (P.nrecv > 0) {
-      k_halo_unpack<<<(unsigned)((P.nrecv + 255) / 256), 256, 0, h->stream>>>(F, P.d_recv_idx, h->d_h2d, P.nrecv,
+      k_halo_unpack<<<(unsigned)((P.nrecv + 255) / 256), 256, 0, h->stream>>>(F, P.d_recv_idx, nullptr, P.nrecv,
                                                                             P.d_recvbuf);
       h->stats.n_launches++;
     }

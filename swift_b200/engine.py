@@ -55,6 +55,15 @@ class SwiftGPU:
         self.nparts = nparts
         self._ck(self.lib.swiftgpu_upload_parts(self.h, host_ptr, nparts), "upload_parts")
 
+    def upload_parts_local(self, host_ptr, nlocal, ntotal):
+        """Only the rank's own particles ([0, nlocal) of the host array); the proxies arrive by the halo exchange."""
+        self.nparts = ntotal
+        self.nlocal = nlocal
+        self._ck(self.lib.swiftgpu_upload_parts_local(self.h, host_ptr, nlocal, ntotal), "upload_parts_local")
+
+    def download_parts_local(self, host_ptr):
+        self._ck(self.lib.swiftgpu_download_parts_local(self.h, host_ptr, self.nlocal), "download_parts_local")
+
     def upload_parts_device(self, dev_ptr, nparts):
         self.nparts = nparts
         self._ck(self.lib.swiftgpu_upload_parts_device(self.h, dev_ptr, nparts), "upload_parts_device")

@@ -219,6 +219,69 @@ def clustered_box(L=256, scheme=abi.SCHEME_SPHENIX, seed=2025, sigma=1.5, eta=1.
     return _finish(ic, scheme, n)
 
 
+def _hash_uniform(idx, seed, stream):
+    """Counter-based uniforms in [0, 1): splitmix64 of (global lattice index, seed, stream). The same
+    particle gets the same numbers whichever rank generates it."""
+    with np.errstate(over="ignore"):
+        z = idx.astype(np.uint64) * np.uint64(3) + np.uint64(stream) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def brick_box(L, scheme, grid=(1, 1, 1), rank=0, top=None, jitter=0.2, seed=42, eta=1.2348, rho=1.0, u0=1.0,
+              vamp=0.05, active_fraction=1.0):
+    """The rank's part of ONE periodic unit box of L^3 jittered-lattice particles split over
+    grid[0] x grid[1] x grid[2] ranks (partition_uniform_grid, src/partition.c:104-121): the rank's own
+    top-level cells plus one top-level cell of halo on every side (the foreign cells it holds proxies
+    of). Jitter comes from a counter-based hash of the global lattice index, so every rank generates
+    identical particles for the cells it shares with its neighbours and the union over the ranks is the
+    same box whatever the grid is (grid (1,1,1): the whole box). Returns the ic dict; ic["id"] is the
+    global lattice index + 1."""
+    top = top if top is not None else default_top_grid(L)[0]
+    assert L % top == 0 and all(top % g == 0 for g in grid)
+    per = L // top  # lattice points per top-level cell and axis
+    r3 = (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
+    axes = []
+    for a in range(3):
+        if grid[a] == 1:
+            axes.append(np.arange(L, dtype=np.int64))
+        else:
+            lo = r3[a] * (top // grid[a]) * per - per
+            hi = (r3[a] + 1) * (top // grid[a]) * per + per
+            axes.append(np.mod(np.arange(lo, hi, dtype=np.int64), L))
+    I, J, K = np.meshgrid(*axes, indexing="ij")
+    I, J, K = I.reshape(-1), J.reshape(-1), K.reshape(-1)
+    gidx = (I * L + J) * L + K
+    n = gidx.shape[0]
+    x = np.empty((n, 3), np.float64)
+    for a, ia in enumerate((I, J, K)):
+        x[:, a] = (ia + 0.5 + (2.0 * _hash_uniform(gidx, seed, a) - 1.0) * jitter) / L
+    del I, J, K
+    k = 2 * np.pi
+    v = np.empty((n, 3), np.float32)
+    v[:, 0] = (np.sin(k * x[:, 1]) + 0.5 * np.cos(2 * k * x[:, 2])) * vamp
+    v[:, 1] = (np.sin(k * x[:, 2]) + 0.5 * np.cos(2 * k * x[:, 0])) * vamp
+    v[:, 2] = (np.sin(k * x[:, 0]) + 0.5 * np.cos(2 * k * x[:, 1])) * vamp
+    u = (u0 * (1.0 + 0.1 * np.sin(k * x[:, 0]) * np.cos(k * x[:, 1]))).astype(np.float32)
+    ic = {"x": x, "v": v, "mass": np.full(n, rho / L ** 3, np.float32),
+          "h": np.full(n, eta / L, np.float32), "u": u, "_rho0": rho}
+    tb = None
+    if active_fraction < 1.0:
+        # active region clustered in space: where a smooth field exceeds the level that holds the
+        # requested fraction of the volume (|sin sin sin| > t; the fraction is measured on this sample)
+        f = np.sin(k * x[:, 0]) * np.sin(k * x[:, 1]) * np.sin(k * x[:, 2])
+        ref = np.sin(k * np.linspace(0, 1, 64, endpoint=False) + 0.01)
+        fr = (ref[:, None, None] * ref[None, :, None] * ref[None, None, :]).reshape(-1)
+        thr = np.quantile(fr, 1.0 - active_fraction)
+        tb = np.where(f >= thr, 1, 3)
+    ic = _finish(ic, scheme, n, tb)
+    ic["id"] = gidx + 1
+    return ic
+
+
 def default_top_grid(L, max_top=32):
     """Top-level grid: cells at least 2*gamma*h*space_stretch wide
     (space_regrid.c:50-127) and at least 3 per axis; prefer ~4096 parts/cell."""
@@ -240,11 +303,14 @@ def step_scalars(max_active_bin=56):
 # touches one of them (src/engine_proxy.c; a pair task exists iff at least one
 # side is local, engine_maketasks.c:3562-3569).
 # ---------------------------------------------------------------------------
-def extract_rank(tree, parts_u8, layout, rank, periodic=True):
+def extract_rank(tree, parts_u8, layout, rank, periodic=True, local_first=False):
     # parts_u8 may be None: pack the returned sub-tree with pack_parts() instead
     """Sub-tree + particles of `rank`: local top-level cells and their foreign
     neighbours. Returns (Tree, parts_u8, sel, is_local) where sel[k] is the
-    index in the global (cell-ordered) particle array of local particle k."""
+    index in the global (cell-ordered) particle array of local particle k.
+    local_first: the rank's own top-level cells (and hence its own particles)
+    come first, the proxies after them - how SWIFT lays out space->parts - so
+    that only [0, n_local) has to cross the host boundary."""
     cells, top = tree.cells, np.asarray(tree.top)
     ntop = top.shape[0]
     tc = cells[top]
@@ -273,12 +339,15 @@ def extract_rank(tree, parts_u8, layout, rank, periodic=True):
     new_index = np.cumsum(cell_keep) - 1
     new_index[~cell_keep] = -1
     sub = cells[cell_keep].copy()
-    # particle ranges of the kept top-level cells, in `top` order
+    # particle ranges of the kept top-level cells, in `top` order (local ones first if asked)
     kept_top = top[keep]
+    if local_first:
+        kl = local[keep]
+        kept_top = np.concatenate([kept_top[kl], kept_top[~kl]])
     counts = cells["count"][kept_top].astype(np.int64)
     offs = np.concatenate([[0], np.cumsum(counts)[:-1]])
     top_off = np.zeros(ntop, dtype=np.int64)
-    top_off[keep] = offs
+    top_off[pos[kept_top]] = offs
     top_first = cells["first_part"][top]
     tpos = pos[sub["top"]]
     sub["first_part"] = top_off[tpos] + (sub["first_part"] - top_first[tpos])
@@ -287,7 +356,7 @@ def extract_rank(tree, parts_u8, layout, rank, periodic=True):
         sub[name] = np.where(v >= 0, new_index[np.maximum(v, 0)], -1)
     pr = sub["progeny"]
     sub["progeny"] = np.where(pr >= 0, new_index[np.maximum(pr, 0)], -1)
-    sel = np.concatenate([np.arange(f, f + c) for f, c in zip(top_first[keep], counts)]) if len(counts) else np.zeros(0, np.int64)
+    sel = np.concatenate([np.arange(f, f + c) for f, c in zip(cells["first_part"][kept_top], counts)]) if len(counts) else np.zeros(0, np.int64)
     size = layout.size
     sub_parts = None
     if parts_u8 is not None:

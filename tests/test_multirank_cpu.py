@@ -118,3 +118,49 @@ def test_halo_plan_two_processes_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"RANK_OK {r}" in o, o
+
+
+def test_brick_generator_is_the_same_box_on_every_grid():
+    """bench.py's strong-scaling workload: every rank generates only its brick + one top-level cell of
+    halo (host.brick_box), yet the union over the ranks is the single-GPU box bit for bit, whatever the
+    grid; the rank's own particles come first in its array (what swiftgpu_upload_parts_local needs)
+    and every halo cell holds the same particles as its owner's copy (same count - the exchange ships
+    cells in the sender's device order, so only the SET has to agree)."""
+    L, top = 64, 4
+    scheme = abi.SCHEME_SPHENIX
+    whole = host.brick_box(L, scheme, top=top)
+    by_id = np.argsort(whole["id"])
+    for grid in ((2, 1, 1), (2, 2, 1), (2, 2, 2)):
+        world = grid[0] * grid[1] * grid[2]
+        seen = np.zeros(L ** 3 + 1, np.int32)
+        per_rank = []
+        for rank in range(world):
+            ic = host.brick_box(L, scheme, grid=grid, rank=rank, top=top)
+            pos = by_id[np.searchsorted(whole["id"][by_id], ic["id"])]
+            assert np.array_equal(whole["x"][pos], ic["x"]) and np.array_equal(whole["u"][pos], ic["u"])
+            c = util.make_case("sphenix", ic, (top,) * 3, rank_grid=grid, rank=rank, pack=False)
+            sub, _, sel, is_local = host.extract_rank(c.tree, None, c.layout, rank, local_first=True)
+            nl = int(is_local.sum())
+            assert is_local[:nl].all() and not is_local[nl:].any()
+            ids = np.asarray(ic["id"])[sub.perm]
+            seen[ids[:nl]] += 1
+            per_rank.append((sub, ids))
+            # local top-level cells own exactly [0, nl)
+            tops = sub.cells[sub.top]
+            loc = tops["nodeID"] == rank
+            assert (tops["first_part"][loc] + tops["count"][loc]).max() == nl
+            assert tops["first_part"][~loc].min() >= nl
+        assert (seen[1:] == 1).all(), "every particle is local on exactly one rank"
+        # a proxy cell holds the same particle set as the owner's cell at the same location
+        def cell_sets(sub, ids):
+            out = {}
+            for t in sub.top:
+                cc = sub.cells[t]
+                f, n = int(cc["first_part"]), int(cc["count"])
+                out[tuple(np.round(cc["loc"] * top).astype(int))] = (int(cc["nodeID"]), frozenset(ids[f:f + n].tolist()))
+            return out
+        sets = [cell_sets(s, i) for s, i in per_rank]
+        for r, cs in enumerate(sets):
+            for loc, (owner, members) in cs.items():
+                if owner != r:
+                    assert sets[owner][loc][1] == members
