@@ -114,6 +114,9 @@ typedef struct port {
    * metric (tests/util.py), carried through the same finalising factors as the sums themselves */
   float *g_a, *g_u, *g_hdt, *g_div, *g_rho_dh, *g_lap;
   float *g2_a, *g2_u, *g2_lap; /* squares: kernel-evaluation noise, see edge_weight() */
+  /* absolute noise of the inputs that are themselves ratios of cancelling sums: the Balsara switch and
+   * (SPHENIX) the diffusion alpha, at the size the metric allows them (1e-5 of their floors) */
+  float *nz_B, *nz_ad, *nz_al;
   int *leaf_of; /* leaf cell index of each particle */
   int ghost_iterations;
   int ghost_failed;
@@ -293,6 +296,12 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
     s->g_u[i] += t;
     s->g2_u[i] += (t * ew) * (t * ew);
   }
+  {
+    /* viscous terms carry the noise of the two Balsara switches */
+    const float wb = 2.e6f * (s->nz_B[i] + s->nz_B[j]) / fmaxf(balsara_i + balsara_j, 1.e-30f);
+    s->g2_a[i] += (fabsf(mj * visc_acc_term) * r * wb) * (fabsf(mj * visc_acc_term) * r * wb);
+    s->g2_u[i] += (fabsf(mj * visc_du_term) * wb) * (fabsf(mj * visc_du_term) * wb);
+  }
   s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr * f_ij) ;
 #elif PORT_SCHEME == SCH_GADGET2
   const float f_i = s->f[i];
@@ -319,6 +328,11 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
     const float t = fabsf(mj * visc_term * dvdr_Hubble) + 2.f * fabsf(mj * f_i * P_over_rho2_i * dvdr * r_inv * wi_dr);
     s->g_u[i] += t;
     s->g2_u[i] += (t * ew) * (t * ew);
+  }
+  {
+    const float wb = 2.e6f * (s->nz_B[i] + s->nz_B[j]) / fmaxf(balsara_i + balsara_j, 1.e-30f);
+    s->g2_a[i] += (fabsf(mj * visc_term) * r * wb) * (fabsf(mj * visc_term) * r * wb);
+    s->g2_u[i] += (fabsf(mj * visc_term * dvdr_Hubble) * wb) * (fabsf(mj * visc_term * dvdr_Hubble) * wb);
   }
   s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr) ;
 #else /* SPHENIX */
@@ -357,6 +371,18 @@ static inline void iact_force(port_t *s, float r2, const float dx[3], float hi,
     const float t = (fabsf(sph_du_term_i) + fabsf(visc_du_term) + fabsf(diff_du_term)) * mj;
     s->g_u[i] += t;
     s->g2_u[i] += (t * ew) * (t * ew);
+  }
+  {
+    const float wb = 2.e6f * (s->nz_B[i] + s->nz_B[j]) / fmaxf(balsara_i + balsara_j, 1.e-30f);
+    s->g2_a[i] += (fabsf(mj * visc_acc_term) * r * wb) * (fabsf(mj * visc_acc_term) * r * wb);
+    s->g2_u[i] += (fabsf(mj * visc_du_term) * wb) * (fabsf(mj * visc_du_term) * wb);
+    /* ... of the two viscosity alphas (alpha_loc = alpha_max S / (c^2 + S) is all noise in cold gas) */
+    const float wa = 2.e6f * (s->nz_al[i] + s->nz_al[j]) / fmaxf(alpha, 1.e-30f);
+    s->g2_a[i] += (fabsf(mj * visc_acc_term) * r * wa) * (fabsf(mj * visc_acc_term) * r * wa);
+    s->g2_u[i] += (fabsf(mj * visc_du_term) * wa) * (fabsf(mj * visc_du_term) * wa);
+    /* ... and the diffusion term that of the diffusion alphas */
+    const float wd = 2.e6f * fmaxf(s->nz_ad[i], s->nz_ad[j]);
+    s->g2_u[i] += (fabsf(mj * diff_du_term) * wd) * (fabsf(mj * diff_du_term) * wd);
   }
   s->g_hdt[i] += fabsf(mj * dvdr * r_inv / rhoj * wi_dr) ;
 #endif
@@ -824,6 +850,8 @@ static void prepare_gradient(port_t *s, long long p) {
   s->P[p] = pressure;
   s->cs[p] = soundspeed;
   s->balsara[p] = balsara;
+  /* d balsara = d(div_v) / (|div| + |curl| + eps), d(div_v) = 1e-5 x 0.5 x (un-cancelled sum) */
+  s->nz_B[p] = 5.e-6f * s->g_div[p] / (abs_div_v + curl_v + 0.0001f * soundspeed * fac_B / s->h[p]);
   /* reset_gradient */
   s->v_sig[p] = 2.f * s->cs[p];
   s->alpha_max_ngb[p] = s->alpha[p];
@@ -840,6 +868,9 @@ static void extra_ghost_part(port_t *s, long long p, float dt_alpha) {
   s->laplace_u[p] *= 2.f * h_inv_dim_plus_one;
   s->g_lap[p] *= 2.f * h_inv_dim_plus_one;
   s->g2_lap[p] *= (2.f * h_inv_dim_plus_one) * (2.f * h_inv_dim_plus_one);
+  /* relative noise of the diffusion alpha this laplace_u produces (it starts from alpha_diff ~ 0) */
+  s->nz_ad[p] = fminf(1.f, 1.e-5f * (0.5f * s->g_lap[p] + 0.05f * sqrtf(s->g2_lap[p])) /
+                               fmaxf(fabsf(s->laplace_u[p]), 1.e-30f));
 
   const float a = s->step.a;
   const float kernel_support_physical = s->h[p] * a * kernel_gamma;
@@ -857,6 +888,11 @@ static void extra_ghost_part(port_t *s, long long p, float dt_alpha) {
                       : 0.f;
   const float soundspeed_square = soundspeed_physical * soundspeed_physical;
   const float alpha_loc = s->cfg.viscosity_alpha_max * S / (soundspeed_square + S);
+  /* absolute noise of the viscosity alpha: d alpha <= alpha_max (h gamma)^2 / c^2 d(div_v) / dt, capped */
+  s->nz_al[p] = dt_alpha == 0.f ? 0.f
+                                : fminf(s->cfg.viscosity_alpha_max,
+                                        s->cfg.viscosity_alpha_max * kernel_support_physical * kernel_support_physical /
+                                            soundspeed_square * 5.e-6f * s->g_div[p] / dt_alpha);
   if (alpha_loc > s->alpha[p]) {
     s->alpha[p] = alpha_loc;
   } else {
@@ -924,6 +960,8 @@ static void prepare_force(port_t *s, long long p) {
   s->P[p] = pressure;
   s->cs[p] = soundspeed;
   s->balsara[p] = balsara;
+  s->nz_B[p] = s->cfg.viscosity_alpha * 5.e-6f * s->g_div[p] /
+               (abs_div_physical_v + curl_v + 0.0001f * fac_Balsara_eps * soundspeed * h_inv);
 #else /* Gadget2 */
   const float rho_inv = 1.f / s->rho[p];
   /* gas_pressure_from_entropy = entropy * pow_gamma(rho); pow_gamma = cbrt^2*x */
@@ -946,6 +984,8 @@ static void prepare_force(port_t *s, long long p) {
   s->P[p] = P_over_rho2;
   s->cs[p] = soundspeed;
   s->balsara[p] = balsara;
+  s->nz_B[p] = s->cfg.viscosity_alpha * 5.e-6f * s->g_div[p] /
+               (abs_div_physical_v + curl_v + 0.0001f * fac_Balsara_eps * soundspeed * h_inv);
 #endif
   s->min_ngb[p] = num_time_bins + 1; /* timestep_limiter_prepare_force */
   s->a[3 * p] = s->a[3 * p + 1] = s->a[3 * p + 2] = 0.f;
@@ -1277,6 +1317,7 @@ port_t *port_create(const swiftgpu_config *cfg, const swiftgpu_step *step,
   s->g_a = falloc(n); s->g_u = falloc(n); s->g_hdt = falloc(n); s->g_div = falloc(n);
   s->g_rho_dh = falloc(n); s->g_lap = falloc(n);
   s->g2_a = falloc(n); s->g2_u = falloc(n); s->g2_lap = falloc(n);
+  s->nz_B = falloc(n); s->nz_ad = falloc(n); s->nz_al = falloc(n);
   s->time_bin = (signed char *)calloc(n, 1);
   s->depth_h = (signed char *)calloc(n, 1);
   s->min_ngb = (signed char *)calloc(n, 1);
@@ -1327,7 +1368,7 @@ void port_destroy(port_t *s) {
   free(s->rot_v); free(s->m); free(s->h); free(s->u); free(s->u_dt); free(s->rho);
   free(s->wcount); free(s->wcount_dh); free(s->rho_dh); free(s->div_v); free(s->f);
   free(s->P); free(s->cs); free(s->balsara); free(s->v_sig); free(s->h_dt);
-  free(s->g2_a); free(s->g2_u); free(s->g2_lap);
+  free(s->g2_a); free(s->g2_u); free(s->g2_lap); free(s->nz_B); free(s->nz_ad); free(s->nz_al);
   free(s->g_a); free(s->g_u); free(s->g_hdt); free(s->g_div); free(s->g_rho_dh); free(s->g_lap);
   free(s->alpha); free(s->alpha_diff); free(s->div_v_prev); free(s->div_v_dt);
   free(s->laplace_u); free(s->alpha_max_ngb); free(s->time_bin); free(s->depth_h);

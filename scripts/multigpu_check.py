@@ -46,6 +46,15 @@ def main():
         # oracle: the whole box on one rank
         c1 = util.make_case(scheme, ic, (4, 4, 4))
         o, kind = util.run_oracle(c1)
+        # proxies arrive (and stay) in the SENDER's device order, so only a rank's local rows of its
+        # AoS array are meaningful: assemble the whole box from every rank's local rows
+        size = c.layout.size
+        full = torch.zeros(c.n * size, dtype=torch.uint8, device="cuda").reshape(-1, size)
+        rows = torch.from_numpy(got.reshape(-1, size)[is_local]).cuda()
+        full[torch.from_numpy(sel[is_local]).cuda()] = rows
+        full32 = full.to(torch.int32)
+        dist.all_reduce(full32, op=dist.ReduceOp.SUM)
+        got = full32.to(torch.uint8).cpu().numpy().reshape(-1)[np.repeat(sel, size) * size + np.tile(np.arange(size), sel.shape[0])]
         want = o.parts().reshape(-1, c.layout.size)[sel].reshape(-1)
         rep = util.parity_report(got, want, c.layout, scheme, only=is_local)
         p1 = util.run_port(c1)
