@@ -26,10 +26,12 @@ namespace swiftgpu {
 /* flat list of the targets of a launch: (particle, group), compacted by k_flat_targets */
 __global__ void __launch_bounds__(128)
     k_flat_targets(const Group *groups, int ngroups, const int32_t *tgt_first, const int32_t *tgt_count,
-                   const int32_t *tgt_list, int2 *flat, unsigned int *nflat) {
+                   const int32_t *tgt_list, int2 *flat, unsigned int *nflat, const unsigned long long *gate,
+                   unsigned long long gate_hi) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (g >= ngroups) return;
+  if (gate && *gate >= gate_hi) return; /* too many targets for this kernel: the pipeline takes the pass */
   const int nt = tgt_count[g];
   if (nt <= 0) return;
   unsigned base = 0;

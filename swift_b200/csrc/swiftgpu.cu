@@ -170,6 +170,10 @@ struct swiftgpu_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t pev[7][2] = {}; /* per phase: begin / end of its last run */
+  uint32_t pev_pending = 0;   /* phases whose time has not been read back yet */
+  int cur_phase = -1;
+  bool counters_pending = false;
   swiftgpu_stats stats;
 
   int fail(const char *fmt, ...) {
@@ -581,10 +585,14 @@ __global__ void __launch_bounds__(128)
     k_task_recs(const int32_t *task_group, const int32_t *task_chunk, int ntasks, const Group *groups,
                 const DevCell *cells, const int32_t *tgt_first, const int32_t *tgt_count,
                 const int32_t *tgt_list, const double *xs0, const double *xs1, const double *xs2,
-                const float *h, TaskRec *recs, unsigned int *ntask_dev) {
+                const float *h, TaskRec *recs, unsigned int *ntask_dev, const unsigned long long *gate,
+                unsigned long long gate_lo, unsigned long long gate_hi) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= ntasks) return;
+  /* ghost re-runs: this launch only if the number of unconverged particles (a device counter the
+   * host never reads in between) is in [gate_lo, gate_hi) - else the other kernel takes the pass */
+  if (gate && (*gate < gate_lo || *gate >= gate_hi)) return;
   const int g = task_group[w];
   const int nt = tgt_count[g];
   const int t0 = task_chunk[w] * PL_TARGETS;
@@ -1217,6 +1225,9 @@ extern "C" void swiftgpu_destroy(swiftgpu_t *h) {
   cudaFree(h->d_dxp_old); cudaFree(h->d_hmax_tmp);
   cudaFree(h->boxes); cudaFree(h->d_box_first); cudaFree(h->d_leaves);
   cudaFree(h->d_frames); cudaFree(h->d_frame_recs); cudaFree(h->d_flat_tgt);
+  for (int ph = 0; ph < 7; ph++)
+    for (int k = 0; k < 2; k++)
+      if (h->pev[ph][k]) cudaEventDestroy(h->pev[ph][k]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1728,19 +1739,54 @@ extern "C" int swiftgpu_upload_parts_device(swiftgpu_t *h, const void *d_parts_a
   return transpose_in(h);
 }
 
-static int phase_begin(H *h) {
+/* Phase timing without a host round trip: the begin / end events of every phase are recorded on the
+ * stream and read back lazily by swiftgpu_get_stats (sync_stats), together with the interaction
+ * counters, which live on the device until then. */
+enum { PH_SORT = 0, PH_DENSITY, PH_GHOST, PH_GRADIENT, PH_EXTRA_GHOST, PH_FORCE, PH_END_FORCE };
+static int phase_begin(H *h, int ph = -1) {
   cudaSetDevice(h->cfg.device);
   if (ensure_lists(h)) return 1;
-  CK(cudaEventRecord(h->ev0, h->stream));
+  h->cur_phase = ph;
+  if (ph >= 0) {
+    for (int k = 0; k < 2; k++)
+      if (!h->pev[ph][k]) CK(cudaEventCreate(&h->pev[ph][k]));
+    CK(cudaEventRecord(h->pev[ph][0], h->stream));
+  }
   return 0;
 }
-static int phase_end(H *h, double *ms_out) {
-  CK(cudaEventRecord(h->ev1, h->stream));
-  CK(cudaEventSynchronize(h->ev1));
-  float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  *ms_out = ms;
+static int phase_end(H *h, double *) {
+  const int ph = h->cur_phase;
+  if (ph >= 0) {
+    CK(cudaEventRecord(h->pev[ph][1], h->stream));
+    h->pev_pending |= 1u << ph;
+  }
+  h->cur_phase = -1;
+  h->counters_pending = true;
   CK(cudaGetLastError());
+  return 0;
+}
+static int sync_stats(H *h) {
+  if (!h->pev_pending && !h->counters_pending) return 0;
+  unsigned long long c[16];
+  CK(cudaMemcpyAsync(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.n_host_syncs++;
+  double *ms[7] = {&h->stats.ms_sort, &h->stats.ms_density, &h->stats.ms_ghost, &h->stats.ms_gradient,
+                   &h->stats.ms_extra_ghost, &h->stats.ms_force, &h->stats.ms_end_force};
+  for (int ph = 0; ph < 7; ph++)
+    if ((h->pev_pending >> ph) & 1u) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, h->pev[ph][0], h->pev[ph][1]) == cudaSuccess) *ms[ph] = t;
+    }
+  h->pev_pending = 0;
+  h->counters_pending = false;
+  h->stats.n_density = (int64_t)(c[0] + c[4]); /* + the ghost's re-runs */
+  h->stats.n_gradient = (int64_t)c[1];
+  h->stats.n_force = (int64_t)c[2];
+  h->stats.t_density = (int64_t)c[8];
+  h->stats.t_gradient = (int64_t)c[9];
+  h->stats.t_force = (int64_t)c[10];
+  h->stats.ghost_iterations = (int32_t)c[5];
   return 0;
 }
 
@@ -1823,7 +1869,7 @@ static int launch_sort(H *h, bool full) {
 
 extern "C" int swiftgpu_run_sort(swiftgpu_t *h) {
   if (!h) return 1;
-  if (phase_begin(h)) return 1;
+  if (phase_begin(h, PH_SORT)) return 1;
   h->full_sorted = false;
   if (launch_sort(h, !use_cta_loops())) return 1;
   h->sorted = true;
@@ -1903,13 +1949,15 @@ static int build_targets(H *h, DevList &D, bool *sparse_out = nullptr) {
 
 /* The compacted TaskRecs of one launch of the frame pipeline, from the target lists as they are NOW
  * (no host round trip: the kernel reads the number of tasks from device memory). */
-static int build_task_recs(H *h, const DevList &D) {
+static int build_task_recs(H *h, const DevList &D, const unsigned long long *gate = nullptr,
+                           unsigned long long gate_lo = 0, unsigned long long gate_hi = ~0ull) {
   CK(cudaMemsetAsync(h->d_counters + 15, 0, sizeof(unsigned long long), h->stream));
   if (D.ntasks == 0) return 0;
   const int64_t n = h->n;
   k_task_recs<<<(unsigned)(((int64_t)D.ntasks * 32 + 127) / 128), 128, 0, h->stream>>>(
       D.task_group, D.task_chunk, D.ntasks, D.groups, h->d_cells, D.tgt_first, D.tgt_count, D.tgt_list, h->xs,
-      h->xs + (n + 4), h->xs + 2 * (n + 4), h->hh, D.task_recs, (unsigned int *)(h->d_counters + 15));
+      h->xs + (n + 4), h->xs + 2 * (n + 4), h->hh, D.task_recs, (unsigned int *)(h->d_counters + 15), gate, gate_lo,
+      gate_hi);
   h->stats.n_launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1983,13 +2031,14 @@ static cudaError_t launch_tile(H *h, const LoopArgs &A, bool sparse = false) {
   return launch_tile_cw<LOOP, SCHEME, 8>(h, A);
 }
 /* sparse target sets (late ghost iterations): one warp per target, loops_direct.cuh */
-static int launch_direct_density(H *h, const DevList &D, const LoopArgs &A) {
+static int launch_direct_density(H *h, const DevList &D, const LoopArgs &A, const unsigned long long *gate = nullptr,
+                                 unsigned long long gate_hi = ~0ull) {
   if (!h->d_flat_tgt) CK(cudaMalloc((void **)&h->d_flat_tgt, sizeof(int2) * (size_t)std::max<int64_t>(h->n, 1)));
-  unsigned int *nflat = (unsigned int *)(h->d_counters + 15);
+  unsigned int *nflat = (unsigned int *)(h->d_counters + 13);
   CK(cudaMemsetAsync(nflat, 0, sizeof(unsigned long long), h->stream));
   if (D.ngroups == 0) return 0;
   k_flat_targets<<<(D.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(D.groups, D.ngroups, D.tgt_first, D.tgt_count,
-                                                                     D.tgt_list, h->d_flat_tgt, nflat);
+                                                                     D.tgt_list, h->d_flat_tgt, nflat, gate, gate_hi);
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -2091,7 +2140,7 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   if (!h) return 1;
   if (ensure_lists(h)) return 1;
   if (!h->sorted && swiftgpu_run_sort(h)) return 1;
-  if (phase_begin(h)) return 1;
+  if (phase_begin(h, PH_DENSITY)) return 1;
   const int64_t n = h->n;
   /* the previous ghost raised h_max / h_max_active: start from the uploaded values */
   CK(cudaMemcpyAsync(h->d_cells, h->d_cells_init, sizeof(DevCell) * h->ncells,
@@ -2113,9 +2162,7 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   h->phases_done &= ~(uint32_t)(SWIFTGPU_PHASE_GHOST | SWIFTGPU_PHASE_GRADIENT |
                                 SWIFTGPU_PHASE_EXTRA_GHOST | SWIFTGPU_PHASE_FORCE |
                                 SWIFTGPU_PHASE_END_FORCE);
-  if (phase_end(h, &h->stats.ms_density)) return 1;
-  if (read_counter(h, 8, &h->stats.t_density)) return 1;
-  return read_counter(h, 0, &h->stats.n_density);
+  return phase_end(h, &h->stats.ms_density);
 }
 
 template <int SCHEME>
@@ -2126,10 +2173,19 @@ static int ghost_launch(H *h, const GhostArgs &G) {
   return 0;
 }
 
+/* Start of one ghost iteration, on the device: counts it if there is anything left to do and zeroes the
+ * redo counter the k_ghost pass fills. c[3] redo, c[5] iterations done, c[6] redo before this pass. */
+__global__ void k_ghost_begin(unsigned long long *c, int first) {
+  if (first || c[3] > 0) c[5]++;
+  c[6] = first ? ~0ull : c[3];
+  c[3] = 0;
+}
+
 extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
   if (!h) return 1;
   if (!(h->phases_done & SWIFTGPU_PHASE_DENSITY)) return h->fail("run_ghost before run_density");
-  if (phase_begin(h)) return 1;
+  if (phase_begin(h, PH_GHOST)) return 1;
+  CK(cudaMemsetAsync(h->d_counters + 3, 0, 4 * sizeof(unsigned long long), h->stream)); /* redo, re-run hits, iterations */
   DevList &D = h->L_subset;
   GhostArgs G;
   memset(&G, 0, sizeof(G));
@@ -2156,7 +2212,54 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
   int64_t redo = 0;
   int64_t extra_density = 0;
   const int max_iter = h->cfg.max_smoothing_iterations;
-  if (D.ngroups > 0) {
+  if (D.ngroups > 0 && loop_kind() == 3) {
+    /* The whole loop stays on the device: every iteration enqueues the ghost pass and BOTH re-run
+     * kernels, each gated on the redo counter (many unconverged particles: the TMA pipeline; a handful
+     * per leaf: one warp per target); passes after convergence find nothing to do. The host looks at
+     * the counter only every second iteration (runner_ghost.c:1545-1580 loops until count == 0). */
+    static int direct_thr = -1;
+    if (direct_thr < 0) {
+      const char *e = getenv("SWIFTGPU_DIRECT");
+      direct_thr = e ? atoi(e) : 4; /* unconverged particles per leaf below which the per-target kernel wins */
+    }
+    const unsigned long long thr = (unsigned long long)direct_thr * (unsigned long long)D.ngroups;
+    const unsigned long long *gate = h->d_counters + 3;
+    if (ensure_frames(h)) return 1;
+    for (iter = 0; iter < max_iter; iter++) {
+      G.first_pass = iter == 0;
+      k_ghost_begin<<<1, 1, 0, h->stream>>>(h->d_counters, iter == 0);
+      h->stats.n_launches++;
+      int rc = 0;
+      switch (h->cfg.scheme) {
+        case SCH_MINIMAL: rc = ghost_launch<SCH_MINIMAL>(h, G); break;
+        case SCH_GADGET2: rc = ghost_launch<SCH_GADGET2>(h, G); break;
+        default: rc = ghost_launch<SCH_SPHENIX>(h, G); break;
+      }
+      if (rc) return 1;
+      const bool last = iter + 1 >= max_iter;
+      if ((iter & 1) || last) {
+        if (read_counter(h, 3, &redo)) return 1;
+        if (getenv("SWIFTGPU_VERBOSE"))
+          fprintf(stderr, "ghost iteration %d: %lld to redo in %d leaves\n", iter, (long long)redo, D.ngroups);
+        if (redo == 0 || last) {
+          iter++;
+          break;
+        }
+      }
+      /* re-run the density loop for the unconverged particles
+       * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
+      if (build_task_recs(h, D, gate, thr, ~0ull)) return 1;
+      {
+        LoopArgs A = loop_args(h, D, h->nd, 4);
+        CK((launch_loop1<LOOP_DENSITY, true>(h, A, false)));
+        h->stats.n_launches++;
+      }
+      {
+        LoopArgs A = loop_args(h, D, h->nd, 4);
+        if (launch_direct_density(h, D, A, gate, thr)) return 1;
+      }
+    }
+  } else if (D.ngroups > 0) {
     for (iter = 0; iter < max_iter; iter++) {
       G.first_pass = iter == 0;
       CK(cudaMemsetAsync(h->d_counters + 3, 0, sizeof(unsigned long long), h->stream));
@@ -2178,7 +2281,6 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
       }
       /* re-run the density loop for the unconverged particles
        * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
-      CK(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long), h->stream));
       /* few unconverged particles per leaf: (pipe) one warp per target straight from L2, (tile)
        * smaller CTAs, more of them per SM */
       const bool sparse = redo < (int64_t)sparse_threshold() * D.ngroups;
@@ -2198,14 +2300,11 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
         CK((launch_loop1<LOOP_DENSITY, true>(h, A, sparse)));
         h->stats.n_launches++;
       }
-      int64_t nn = 0;
-      if (read_counter(h, 4, &nn)) return 1;
-      extra_density += nn;
     }
   }
-  h->stats.ghost_iterations = iter;
+  h->stats.ghost_iterations = iter; /* (frame pipeline: replaced by the device's own count in sync_stats) */
   h->stats.ghost_unconverged = (int32_t)redo;
-  h->stats.n_density += extra_density;
+  (void)extra_density;
   h->phases_done |= SWIFTGPU_PHASE_GHOST;
   if (phase_end(h, &h->stats.ms_ghost)) return 1;
   if (redo > 0)
@@ -2277,9 +2376,7 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
     h->stats.n_launches++;
   }
   h->phases_done |= SWIFTGPU_PHASE_GRADIENT;
-  if (phase_end(h, &h->stats.ms_gradient)) return 1;
-  if (read_counter(h, 9, &h->stats.t_gradient)) return 1;
-  return read_counter(h, 1, &h->stats.n_gradient);
+  return phase_end(h, &h->stats.ms_gradient);
 }
 
 extern "C" int swiftgpu_run_extra_ghost(swiftgpu_t *h) {
@@ -2338,9 +2435,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
     h->stats.n_launches++;
   }
   h->phases_done |= SWIFTGPU_PHASE_FORCE;
-  if (phase_end(h, &h->stats.ms_force)) return 1;
-  if (read_counter(h, 10, &h->stats.t_force)) return 1;
-  return read_counter(h, 2, &h->stats.n_force);
+  return phase_end(h, &h->stats.ms_force);
 }
 
 extern "C" int swiftgpu_run_end_force(swiftgpu_t *h) {
@@ -2501,6 +2596,8 @@ extern "C" int swiftgpu_download_sort(swiftgpu_t *h, int32_t cell, int32_t sid, 
 
 extern "C" int swiftgpu_get_stats(swiftgpu_t *h, swiftgpu_stats *out) {
   if (!h || !out) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (sync_stats(h)) return 1;
   *out = h->stats;
   return 0;
 }
