@@ -115,6 +115,22 @@ def make_workload(name, world=1, rank=0, all_active=False):
     c.ids = np.asarray(ic["id"])[c.sub_tree.perm]
     c.time_bin_ic = np.asarray(ic["time_bin"])[c.sub_tree.perm]
     c.active_fraction = active
+    c.synthetic_inactive = False
+    if active < 1.0 and not all_active and (L >= 512 or os.environ.get("SWIFTGPU_SYNTH")):
+        # Too large for the preparatory all-active step (its worklists and frame arrays would not fit
+        # next to the benchmark's own buffers): the inactive neighbours carry the force-union members of
+        # the unperturbed medium instead (rho = rho_bar, P = (gamma-1) u rho, c_s, f = 0, balsara = 0.5).
+        # The kernels do the same work on them; parity of active subsets is tested at small size.
+        rho0 = float(ic["_rho0"])
+        u = host.field(c.parts, c.layout, "u").astype(np.float64)
+        P = (host.HYDRO_GAMMA - 1.0) * u * rho0
+        host.field(c.parts, c.layout, "rho")[:] = rho0
+        host.field(c.parts, c.layout, "pressure")[:] = P.astype(np.float32)
+        host.field(c.parts, c.layout, "soundspeed")[:] = np.sqrt(host.HYDRO_GAMMA * P / rho0).astype(np.float32)
+        host.field(c.parts, c.layout, "f")[:] = 0.0
+        host.field(c.parts, c.layout, "balsara")[:] = 0.5
+        c.synthetic_inactive = True
+    del ic
     return c
 
 
@@ -381,6 +397,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-halo-parity", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (and its pinned host copies): memory-bound configurations")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = DEFAULT_WORKLOAD
@@ -439,13 +456,19 @@ def main():
     if world > 1:
         c.nccl_id = new_nccl_id()
         g.halo_setup(c.nccl_id)
-    if active < 1.0:
+    if active < 1.0 and not c.synthetic_inactive:
         prepare_inactive_state(c, g, world)
 
-    host_in = torch.from_numpy(c.parts).pin_memory()
-    host_out = torch.empty(n_local * psize, dtype=torch.uint8).pin_memory()
-    dev_in = host_in.to("cuda", non_blocking=False)
-    dev_out = torch.empty_like(dev_in)
+    if args.no_e2e:
+        host_in = torch.from_numpy(c.parts)
+        host_out = None
+        dev_in = host_in.to("cuda", non_blocking=False)
+        dev_out = dev_in  # the download of the device-resident leg goes back into the same buffer
+    else:
+        host_in = torch.from_numpy(c.parts).pin_memory()
+        host_out = torch.empty(n_local * psize, dtype=torch.uint8).pin_memory()
+        dev_in = host_in.to("cuda", non_blocking=False)
+        dev_out = torch.empty_like(dev_in)
 
     def barrier():
         torch.cuda.synchronize()
@@ -456,7 +479,8 @@ def main():
     def step_device():
         g.upload_parts_device(dev_in.data_ptr(), n)
         g.run_step(abi.PHASE_ALL)
-        g.download_parts_device(dev_out.data_ptr())
+        if dev_out is not dev_in:
+            g.download_parts_device(dev_out.data_ptr())
 
     def step_e2e():
         # the rank's OWN particles cross the host boundary; proxies arrive over NVLink
@@ -493,16 +517,18 @@ def main():
         executed = int(st.n_density + st.n_gradient + st.n_force)
 
         # ---- end-to-end timing (pinned host buffers through the C ABI) ----
-        step_e2e()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(args.steps):
+        ms_e2e = float("nan")
+        if not args.no_e2e:
             step_e2e()
-        f1.record(stream)
-        barrier()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(args.steps):
+                step_e2e()
+            f1.record(stream)
+            barrier()
+            ms_e2e = f0.elapsed_time(f1)
         sampler.stop()
-        ms_e2e = f0.elapsed_time(f1)
 
     # max over ranks
     t = torch.tensor([ms_total, ms_e2e], device="cuda", dtype=torch.float64)
@@ -519,7 +545,7 @@ def main():
     phase_ms = {k: float(v) for k, v in zip(sorted(phase_ms), ph)}
     ms_step = ms_total / args.steps
     value = useful_all / (ms_step * 1e-3)
-    e2e_value = useful_all / (ms_e2e / args.steps * 1e-3)
+    e2e_value = useful_all / (ms_e2e / args.steps * 1e-3) if ms_e2e == ms_e2e else None
 
     # ---- roofline of the dominant kernel (CUDA-event phase times of the library, max over ranks) ----
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
@@ -565,11 +591,12 @@ def main():
                        args.workload, "x".join(map(str, GRIDS[world])), L),
                    "scheme": scheme, "particles": int(n_all), "particles_per_gpu_incl_halo": int(n),
                    "active_fraction": active,
+                   "inactive_state": ("synthetic (unperturbed medium)" if c.synthetic_inactive else "from an all-active step") if active < 1.0 else None,
                    "l2": "inputs larger than L2 (%.0f MB AoS + SoA state per GPU and step)" % (n * psize / 1e6),
                    "top_grid": list(top_grid_of(L)),
                    "ghost_iterations": int(st.ghost_iterations)},
         "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": n_local * psize,
-                "d2h_bytes_per_step": n_local * psize, "ms_per_step": ms_e2e / args.steps,
+                "d2h_bytes_per_step": n_local * psize, "ms_per_step": (ms_e2e / args.steps) if e2e_value else None,
                 "note": "per GPU: the rank's own particles through the C ABI (pinned host AoS in and out); proxies by NCCL"},
         "gpu_launches": int(launches),
         "interactions_per_step": useful_all, "interactions_incl_ghost_reruns": executed_all,

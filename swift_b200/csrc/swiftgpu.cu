@@ -2356,7 +2356,7 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   if (!h) return 1;
   if (h->cfg.scheme != SCH_SPHENIX) return 0;
   if (!(h->phases_done & SWIFTGPU_PHASE_GHOST)) return h->fail("run_gradient before run_ghost");
-  if (phase_begin(h)) return 1;
+  if (phase_begin(h, PH_GRADIENT)) return 1;
   /* DOSUB_PAIR1/SELF1 of the gradient task evaluate cell_can_recurse_in_subpair/
    * subself_hydro_task (cell.h:951,992) on the h_max_active the ghost just set */
   if (revalidate_list(h, LISTS_GRADIENT)) return 1;
@@ -2383,7 +2383,7 @@ extern "C" int swiftgpu_run_extra_ghost(swiftgpu_t *h) {
   if (!h) return 1;
   if (h->cfg.scheme != SCH_SPHENIX) return 0;
   if (!(h->phases_done & SWIFTGPU_PHASE_GRADIENT)) return h->fail("run_extra_ghost before run_gradient");
-  if (phase_begin(h)) return 1;
+  if (phase_begin(h, PH_EXTRA_GHOST)) return 1;
   ExtraArgs E;
   memset(&E, 0, sizeof(E));
   E.groups = h->L_subset.groups;
@@ -2413,7 +2413,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   if (!h) return 1;
   const uint32_t need = h->cfg.scheme == SCH_SPHENIX ? SWIFTGPU_PHASE_EXTRA_GHOST : SWIFTGPU_PHASE_GHOST;
   if (!(h->phases_done & need)) return h->fail("run_force before the ghost phases");
-  if (phase_begin(h)) return 1;
+  if (phase_begin(h, PH_FORCE)) return 1;
   if (revalidate_list(h, LISTS_FORCE)) return 1;
   CK(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(unsigned long long), h->stream));
@@ -2441,7 +2441,7 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
 extern "C" int swiftgpu_run_end_force(swiftgpu_t *h) {
   if (!h) return 1;
   if (!(h->phases_done & SWIFTGPU_PHASE_FORCE)) return h->fail("run_end_force before run_force");
-  if (phase_begin(h)) return 1;
+  if (phase_begin(h, PH_END_FORCE)) return 1;
   if (h->L_subset.ngroups > 0) {
     k_end_force<<<(h->L_subset.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(
         h->L_subset.groups, h->L_subset.ngroups, h->d_cells, soa_of(h), h->step.max_active_bin,
