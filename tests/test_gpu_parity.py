@@ -596,3 +596,23 @@ def test_gradient_list_follows_the_ghost():
     _check(c, g)
     assert st.gradient_list_rebuilds >= 1, "the test did not move a recursion predicate: strengthen it"
     g.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_c_boundary(scheme):
+    """The drop-in boundary from C (INTEGRATION.md sections 2-3 made compilable):
+    oracle/c_boundary_test.c is compiled against the reference's own headers, fills
+    swiftgpu_part_layout with offsetof() on the REAL `struct part` of the scheme, writes the initial
+    conditions through the struct's members, and in one process runs libswiftgpu (C ABI) and the
+    reference's runner_* functions on the same array, comparing the members the path writes. The
+    binaries are built where the reference tree is present (oracle/Makefile `ctest`) and travel in
+    oracle/_ref/."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", f"c_boundary_test_{scheme}")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/c_boundary_test_* not built (needs the reference tree at build time)")
+    r = subprocess.run([exe, "20"], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-1500:], r.stderr[-1500:])
+    assert r.returncode == 0 and "C_BOUNDARY PASS" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
