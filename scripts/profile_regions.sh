@@ -1,8 +1,8 @@
 #!/bin/bash
-# Appends warp-stall reasons and per-region instruction/sample shares of the k_tile launches of
-# gpurun_out/<tag>_full.ncu-rep to profiles/<tag>_summary.md. Line ranges follow loops_tile.cuh / sph_math.cuh.
+# Appends warp-stall reasons and per-region instruction/sample shares of the k_pipe launches of
+# gpurun_out/<tag>_full.ncu-rep to profiles/<tag>_summary.md. Line ranges follow loops_pipe.cuh / loops_common.cuh / sph_math.cuh.
 TAG=$1
-R="loops_tile.cuh:63-100=mbarrier waits / TMA issue,loops_tile.cuh:146-245=exact sorted-axis path,loops_tile.cuh:248-281=prologue,loops_tile.cuh:282-531=producer,loops_tile.cuh:532-562=consumer setup,loops_tile.cuh:563-656=drain (list merge + exact frames),loops_tile.cuh:657-752=task switch (target loads),loops_tile.cuh:753-809=stage loop + octet cull,loops_tile.cuh:810-878=prefilter test loop,loops_tile.cuh:879-990=flush,sph_math.cuh:60-86=exact r2 / dsubf helpers,sph_math.cuh:87-108=kernel_deval,sph_math.cuh:109-140=sqrt/rcp helpers,sph_math.cuh:141-174=iact_density,sph_math.cuh:175-213=iact_gradient,sph_math.cuh:214-310=iact_force"
+R="loops_pipe.cuh:160-560=producer (task prefetch, fragment layout, TMA issue),loops_pipe.cuh:561-600=consumer setup,loops_pipe.cuh:601-700=drain (list merge, dx from parked floats, hit checks),loops_pipe.cuh:701-805=task switch (target loads),loops_pipe.cuh:806-855=stage loop + octet cull,loops_pipe.cuh:856-880=target frame coordinates,loops_pipe.cuh:881-935=exact test loop,loops_pipe.cuh:936-1013=flush,loops_common.cuh:130-200=mbarrier waits / TMA issue,loops_common.cuh:201-324=exact sorted-axis path,sph_math.cuh:60-86=r2 / dsubf helpers,sph_math.cuh:87-108=kernel_deval,sph_math.cuh:109-140=sqrt/rcp helpers,sph_math.cuh:141-185=iact_density,sph_math.cuh:186-225=iact_gradient,sph_math.cuh:226-330=iact_force"
 {
   echo
   echo "# $TAG: warp-stall reasons (ncu raw page) and where the issued instructions / stall samples fall (SASS samples of the source page joined with nvdisasm -g line info; scripts/ncu_stalls.py, scripts/ncu_lines.py)"
@@ -10,7 +10,7 @@ R="loops_tile.cuh:63-100=mbarrier waits / TMA issue,loops_tile.cuh:146-245=exact
   echo '```'
   python scripts/ncu_stalls.py gpurun_out/${TAG}_full.ncu-rep | grep -E "##|issue_active|warps_active|stalls"
   echo
-  for sel in "k_tile<(int)0, (int)0, (int)4" "k_tile<(int)0, (int)0, (int)2" "k_tile<(int)2"; do
+  for sel in "k_pipe<(int)0, (int)0, (int)7" "k_pipe<(int)0, (int)0, (int)5" "k_pipe<(int)1" "k_pipe<(int)2"; do
     REGIONS="$R" python scripts/ncu_lines.py gpurun_out/${TAG}_full.ncu-rep "$sel" 0 0 | grep -E "kernel|region" | grep -v "ins   0\.[0-4]"
     echo
   done

@@ -29,7 +29,7 @@
 #ifndef SWIFTGPU_LOOPS_CTA_CUH
 #define SWIFTGPU_LOOPS_CTA_CUH
 
-#include "loops.cuh"
+#include "loops_warp.cuh"
 
 namespace swiftgpu {
 

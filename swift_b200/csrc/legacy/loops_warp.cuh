@@ -1,5 +1,6 @@
 /*
- * loops.cuh - the neighbour-loop kernels (K1/K2/K3 of SURVEY 2.1).
+ * legacy/loops_warp.cuh - FIRST generation of the neighbour-loop kernels (kept for reference; built only
+ * with -DSWIFTGPU_LEGACY_LOOPS, `make legacy`): the neighbour-loop kernels (K1/K2/K3 of SURVEY 2.1).
  *
  * One warp owns up to 32 TARGET particles of one target cell (a "task") and
  * walks every directed item of that cell's group (worklist.hpp). The work is
@@ -37,133 +38,15 @@
  * modes and (shift or 0, source double, 0) for the double modes; subtracting
  * an exact zero does not round, so both reproduce the reference bit for bit.
  */
-#ifndef SWIFTGPU_LOOPS_CUH
-#define SWIFTGPU_LOOPS_CUH
+#ifndef SWIFTGPU_LOOPS_WARP_CUH
+#define SWIFTGPU_LOOPS_WARP_CUH
 
-#include "sph_math.cuh"
-#include "worklist.hpp"
+#include "../loops_common.cuh"
 
 namespace swiftgpu {
 
-#define FULL_MASK 0xffffffffu
-
-/* Device view of one cell (80 bytes). */
-struct DevCell {
-  double loc[3];
-  int32_t first;
-  int32_t count;
-  float h_max;
-  float h_max_active;
-  float dx_max_sort;
-  float h_max_allowed;
-  float h_min_allowed;
-  int32_t parent;
-  int64_t sort_base; /* offset of this cell's first sorted index array, -1 if none */
-  uint16_t sort_mask; /* which sids are present */
-  int8_t depth;
-  uint8_t flags; /* bit0 active, bit1 local, bit2 split */
-  float width;   /* max_k width[k] */
-  float dx_max_part; /* how far a particle may sit outside the cell box */
-  int32_t seg_base;  /* index of this cell's first (cell, sid) segment, see seg_index() */
-};
-static_assert(sizeof(DevCell) == 80, "DevCell layout");
-
-/* Index of the (cell, sid) segment: key extrema and sorted index arrays are
- * stored per requested segment, a cell's segments are consecutive. */
-__device__ __forceinline__ int seg_index(const DevCell &c, int sid) {
-  return c.seg_base + __popc((unsigned)c.sort_mask & ((1u << sid) - 1u));
-}
-__device__ __forceinline__ int64_t sort_offset(const DevCell &c, int sid) {
-  return c.sort_base + (int64_t)__popc((unsigned)c.sort_mask & ((1u << sid) - 1u)) * c.count;
-}
-
-struct TaskRec;
-struct LoopArgs {
-  const DevCell *cells;
-  const Item *items;
-  const Group *groups;
-  const int32_t *task_group; /* per task */
-  const int32_t *task_chunk;
-  int ntasks;
-  const int32_t *tgt_list;  /* target particle indices */
-  const int32_t *tgt_first; /* per group: offset into tgt_list */
-  const int32_t *tgt_count; /* per group */
-  const uint32_t *sort_idx;
-  const float2 *ext; /* per (cell, sid) segment: (min, max) sort key = sort[0].d, sort[count-1].d */
-  /* particle state */
-  const double *x;       /* 3n */
-  const float4 *mv;      /* (m, vx, vy, vz) */
-  const float *h;
-  const int8_t *depth_h;
-  const int8_t *time_bin;
-  /* gradient / force inputs */
-  const float4 *fq1; /* (rho, P, f, cs) */
-  const float4 *fq2; /* (balsara, h, u, time_bin) */
-  const float4 *fq3; /* (alpha_visc, alpha_diff, -, -) */
-  /* tile pipeline (loops_tile.cuh): TMA-copyable source records */
-  const float4 *xf;   /* (float x, y, z of the absolute position, (h gamma REL + margin)^2) */
-  const double *xs0, *xs1, *xs2; /* SoA copies of the double positions (8-byte TMA columns) */
-  const float4 *gq;   /* gradient payload (u, rho, cs, alpha_visc) */
-  const float4 *boxes; /* per cell octet: lo.xyz_, hi.xyz_ */
-  const int32_t *cell_box_first;
-  float keyE;   /* r-margin below which the sorted-axis conditions are implied */
-  float margin; /* absolute widening of the float prefilter */
-  int hold;     /* stages a consumer warp holds before it drains (<= NS - 1) */
-  unsigned int *task_counter; /* persistent CTAs draw their tasks from here (zeroed per launch) */
-  /* frame pipeline (loops_pipe.cuh) */
-  const float4 *frames;            /* per-(cell, origin) arrays of (float)(x - origin) */
-  const struct TaskRec *task_recs; /* compacted tasks of this launch (k_task_recs) */
-  const unsigned int *ntask_dev;   /* their number */
-  /* outputs */
-  float4 *dA;      /* (rho, rho_dh, wcount, wcount_dh) */
-  float4 *dB;      /* (div_v, rot_v) */
-  float *g_vsig;   /* gradient: viscosity.v_sig (max) */
-  float *g_lap;    /* gradient: diffusion.laplace_u (sum) */
-  float *g_amax;   /* gradient: force.alpha_visc_max_ngb (max) */
-  float4 *fo1;     /* (ax, ay, az, u_dt) */
-  float *f_hdt;
-  float *f_vsig;
-  int32_t *f_minngb;
-  int32_t *count; /* per-particle directed interaction counter of this loop */
-  unsigned long long *total; /* global interaction counter */
-  unsigned long long *tests; /* global distance-test counter */
-  double dim[3];
-  float a2_Hubble;
-  int max_active_bin;
-};
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
-  return v;
-}
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL_MASK, v, o));
-  return v;
-}
-__device__ __forceinline__ double warp_max_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
-  return v;
-}
-__device__ __forceinline__ double warp_min_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
-  return v;
-}
-
-__device__ __forceinline__ void atomic_max_pos(float *addr, float v) {
-  /* non-negative floats order like their bit patterns */
-  atomicMax((int *)addr, __float_as_int(v));
-}
-
-/* Relative inflation of the prefilter radius^2: covers the difference between
- * the fused r2 of the prefilter and the reference's un-fused r2 (~2^-22). */
-#define PREFILTER_REL 1.00001f
 #define LCAP 64 /* hit-list capacity per target */
 #define TPL 2   /* targets per lane: every staged source is tested against 2 targets */
-#define TASK_TARGETS (32 * TPL)
 
 /* What the drain needs to know about a staged chunk of 32 slots. */
 struct __align__(16) ChunkInfo {

@@ -56,7 +56,7 @@
 #ifndef SWIFTGPU_LOOPS_PIPE_CUH
 #define SWIFTGPU_LOOPS_PIPE_CUH
 
-#include "loops_tile.cuh"
+#include "loops_common.cuh"
 
 namespace swiftgpu {
 

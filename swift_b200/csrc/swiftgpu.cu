@@ -25,9 +25,11 @@
 #include <vector>
 
 #include "../../include/swiftgpu.h"
-#include "loops_cta.cuh"
-#include "loops_tile.cuh"
 #include "loops_pipe.cuh"
+#ifdef SWIFTGPU_LEGACY_LOOPS /* `make legacy`: the three superseded generations, for A/B runs (SWIFTGPU_LOOPS=tile|cta|warp) */
+#include "legacy/loops_cta.cuh"
+#include "legacy/loops_tile.cuh"
+#endif
 #include "loops_direct.cuh"
 
 using namespace swiftgpu;
@@ -190,897 +192,8 @@ typedef swiftgpu_handle H;
 
 static thread_local std::string g_err;
 
-/* ======================================================================== */
-/* Kernels: AoS <-> SoA                                                      */
-/* ======================================================================== */
-struct DevLayout {
-  swiftgpu_part_layout L;
-  int scheme;
-};
-
-template <typename T>
-__device__ __forceinline__ T rd(const char *p, int off) {
-  return *(const T *)(p + off);
-}
-template <typename T>
-__device__ __forceinline__ void wr(char *p, int off, T v) {
-  *(T *)(p + off) = v;
-}
-
-struct Soa {
-  double *x;
-  float4 *mv, *dA, *dB, *fq1, *fq2, *fq3, *fo1;
-  float *h, *u, *rho, *f_hdt, *f_vsig, *g_vsig, *g_lap, *g_amax, *alpha, *alpha_diff, *div_v_prev,
-      *div_v_dt, *div_v;
-  int8_t *time_bin, *depth_h;
-  int32_t *f_minngb;
-};
-
-__global__ void k_iota2(int32_t *a, int32_t *b, int64_t n) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  a[p] = (int32_t)p;
-  b[p] = (int32_t)p;
-}
-
-/* Morton order inside every leaf (one CTA per leaf, bitonic sort of
- * (15-bit Morton code, index) in shared memory). Leaves above LEAF_SORT_MAX
- * particles keep the host order. */
-#define LEAF_SORT_MAX 1024
-__device__ __forceinline__ uint32_t spread5(uint32_t v) {
-  /* 5 bits -> every third bit */
-  v = (v | (v << 8)) & 0x0000100fu;
-  v = (v | (v << 4)) & 0x000010c3u;
-  v = (v | (v << 2)) & 0x00001249u;
-  return v;
-}
-__global__ void __launch_bounds__(128)
-    k_leaf_order(const LeafRec *leaves, int nleaves, const char *aos, int part_size, int x_off,
-                 int32_t *d2h, int32_t *h2d) {
-  __shared__ uint32_t skey[LEAF_SORT_MAX];
-  const int l = blockIdx.x;
-  if (l >= nleaves) return;
-  const LeafRec R = leaves[l];
-  const int n = R.count;
-  if (n <= 1 || n > LEAF_SORT_MAX) return;
-  int N = 1;
-  while (N < n) N <<= 1;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    uint32_t key = 0xffffffffu;
-    if (i < n) {
-      const char *b = aos + (size_t)part_size * (size_t)(R.first + i);
-      uint32_t q[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const float f = (float)(*(const double *)(b + x_off + 8 * k) - R.loc[k]) * R.iwidth[k];
-        q[k] = (uint32_t)min(31, max(0, (int)f));
-      }
-      const uint32_t mort = (spread5(q[0]) << 2) | (spread5(q[1]) << 1) | spread5(q[2]);
-      key = (mort << 10) | (uint32_t)i;
-    }
-    skey[i] = key;
-  }
-  __syncthreads();
-  for (int size = 2; size <= N; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const int j = i ^ stride;
-        if (j > i) {
-          const uint32_t a = skey[i], c = skey[j];
-          const bool up = ((i & size) == 0);
-          if ((a > c) == up) {
-            skey[i] = c;
-            skey[j] = a;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (int r = threadIdx.x; r < n; r += blockDim.x) {
-    const int i = (int)(skey[r] & 1023u);
-    d2h[R.first + r] = R.first + i;
-    h2d[R.first + i] = R.first + r;
-  }
-}
-
-__global__ void k_scatter_i32(const int32_t *src, const int32_t *d2h, int64_t n, int32_t *dst) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  dst[d2h[p]] = src[p];
-}
-
-__global__ void k_aos_to_soa(const char *aos, DevLayout D, Soa S, int64_t n, const int32_t *d2h) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const swiftgpu_part_layout &L = D.L;
-  const char *b = aos + (size_t)L.size * (size_t)d2h[p];
-  S.x[3 * p + 0] = rd<double>(b, L.x);
-  S.x[3 * p + 1] = rd<double>(b, L.x + 8);
-  S.x[3 * p + 2] = rd<double>(b, L.x + 16);
-  const float m = rd<float>(b, L.mass);
-  S.mv[p] = make_float4(m, rd<float>(b, L.v), rd<float>(b, L.v + 4), rd<float>(b, L.v + 8));
-  const float h = rd<float>(b, L.h);
-  S.h[p] = h;
-  const float u = rd<float>(b, D.scheme == SCH_GADGET2 ? L.entropy : L.u);
-  S.u[p] = u;
-  const float rho = rd<float>(b, L.rho);
-  S.rho[p] = rho;
-  const int8_t tb = rd<int8_t>(b, L.time_bin);
-  S.time_bin[p] = tb;
-  S.depth_h[p] = rd<int8_t>(b, L.depth_h);
-  /* The density/force union holds the force members of the last step the
-   * particle was active in: they are what inactive neighbours contribute. */
-  const float P = rd<float>(b, D.scheme == SCH_GADGET2 ? L.P_over_rho2 : L.pressure);
-  S.fq1[p] = make_float4(rho, P, rd<float>(b, L.f), rd<float>(b, L.soundspeed));
-  /* the force loop's test reads the exact h^2 gamma^2 of a source from the spare lane of its payload:
-   * fq2.z (Minimal, Gadget2: u is not read by their force interaction) or fq3.z (SPHENIX) */
-  S.fq2[p] = make_float4(rd<float>(b, L.balsara), h, D.scheme == SCH_SPHENIX ? u : hg2_exact(h),
-                         __int_as_float((int)tb));
-  S.f_hdt[p] = rd<float>(b, L.h_dt);
-  S.f_vsig[p] = rd<float>(b, L.v_sig);
-  S.f_minngb[p] = rd<int8_t>(b, L.min_ngb_time_bin);
-  S.fo1[p] = make_float4(rd<float>(b, L.a_hydro), rd<float>(b, L.a_hydro + 4),
-                         rd<float>(b, L.a_hydro + 8),
-                         rd<float>(b, D.scheme == SCH_GADGET2 ? L.entropy_dt : L.u_dt));
-  if (D.scheme == SCH_SPHENIX) {
-    const float al = rd<float>(b, L.visc_alpha), ad = rd<float>(b, L.diff_alpha);
-    S.alpha[p] = al;
-    S.alpha_diff[p] = ad;
-    S.fq3[p] = make_float4(al, ad, hg2_exact(h), 0.f);
-    S.div_v_prev[p] = rd<float>(b, L.div_v_previous_step);
-    S.div_v_dt[p] = rd<float>(b, L.div_v_dt);
-    S.div_v[p] = rd<float>(b, L.div_v);
-    S.g_vsig[p] = rd<float>(b, L.v_sig);
-    S.g_lap[p] = rd<float>(b, L.laplace_u);
-    S.g_amax[p] = rd<float>(b, L.alpha_visc_max_ngb);
-  }
-}
-
-/* Writes back the fields the phases run so far have made valid, for ACTIVE
- * particles only (inactive particles are read-only on this path). */
-__global__ void k_soa_to_aos(char *aos, DevLayout D, Soa S, int64_t n, int max_active_bin,
-                             int density_only, const int32_t *d2h) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  if (S.time_bin[p] > max_active_bin) return;
-  const swiftgpu_part_layout &L = D.L;
-  char *b = aos + (size_t)L.size * (size_t)d2h[p];
-  wr<float>(b, L.h, S.h[p]);
-  wr<int8_t>(b, L.depth_h, S.depth_h[p]);
-  const float4 a = S.dA[p], c = S.dB[p];
-  if (density_only) {
-    wr<float>(b, L.rho, a.x);
-    wr<float>(b, L.rho_dh, a.y);
-    wr<float>(b, L.wcount, a.z);
-    wr<float>(b, L.wcount_dh, a.w);
-    wr<float>(b, L.div_v, c.x);
-    wr<float>(b, L.rot_v, c.y);
-    wr<float>(b, L.rot_v + 4, c.z);
-    wr<float>(b, L.rot_v + 8, c.w);
-    return;
-  }
-  const float4 q1 = S.fq1[p], q2 = S.fq2[p], o = S.fo1[p];
-  wr<float>(b, L.rho, q1.x);
-  wr<float>(b, D.scheme == SCH_GADGET2 ? L.P_over_rho2 : L.pressure, q1.y);
-  wr<float>(b, L.f, q1.z);
-  wr<float>(b, L.soundspeed, q1.w);
-  wr<float>(b, L.balsara, q2.x);
-  wr<float>(b, L.h_dt, S.f_hdt[p]);
-  wr<float>(b, L.a_hydro, o.x);
-  wr<float>(b, L.a_hydro + 4, o.y);
-  wr<float>(b, L.a_hydro + 8, o.z);
-  wr<float>(b, D.scheme == SCH_GADGET2 ? L.entropy_dt : L.u_dt, o.w);
-  wr<int8_t>(b, L.min_ngb_time_bin, (int8_t)S.f_minngb[p]);
-  if (D.scheme == SCH_SPHENIX) {
-    wr<float>(b, L.div_v, S.div_v[p]);
-    wr<float>(b, L.v_sig, S.g_vsig[p]);
-    wr<float>(b, L.laplace_u, S.g_lap[p]);
-    wr<float>(b, L.alpha_visc_max_ngb, S.g_amax[p]);
-    wr<float>(b, L.visc_alpha, S.alpha[p]);
-    wr<float>(b, L.diff_alpha, S.alpha_diff[p]);
-    wr<float>(b, L.div_v_previous_step, S.div_v_prev[p]);
-    wr<float>(b, L.div_v_dt, S.div_v_dt[p]);
-  } else {
-    wr<float>(b, L.v_sig, S.f_vsig[p]);
-  }
-}
-
-/* ======================================================================== */
-/* Kernel: 13-axis sort (runner_do_hydro_sort, runner_sort.c:203)            */
-/* One CTA per (cell, sid) segment. Keys are (float)(x . runner_shift[sid])  */
-/* of absolute double positions (:411-413); the order of equal keys is       */
-/* irrelevant to the neighbour sets. All-ascending bitonic network with      */
-/* virtual +inf padding.                                                     */
-/* ======================================================================== */
-#define SORT_SMEM_MAX 2048
-__global__ void __launch_bounds__(256)
-    k_sort(const SortSeg *segs, const DevCell *cells, const double *x, uint32_t *sort_idx,
-           float *gkeys /* scratch for segments larger than SORT_SMEM_MAX, may be null */) {
-  __shared__ float skey[SORT_SMEM_MAX];
-  __shared__ uint32_t sidx[SORT_SMEM_MAX];
-  const SortSeg seg = segs[blockIdx.x];
-  const DevCell c = cells[seg.cell];
-  const int n = c.count;
-  uint32_t *out = sort_idx + seg.off;
-  int N = 1;
-  while (N < n) N <<= 1;
-  const bool in_smem = n <= SORT_SMEM_MAX;
-  float *keys = in_smem ? skey : gkeys + seg.off;
-  uint32_t *idx = in_smem ? sidx : out;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const size_t p = (size_t)c.first + i;
-    keys[i] = sort_key(x[3 * p], x[3 * p + 1], x[3 * p + 2], seg.sid);
-    idx[i] = (uint32_t)i;
-  }
-  __syncthreads();
-  for (int size = 2; size <= N; size <<= 1) {
-    for (int stride = size >> 1, first = 1; stride > 0; stride >>= 1, first = 0) {
-      for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const int j = first ? (i ^ (size - 1)) : (i ^ stride);
-        if (j > i && j < n) {
-          const float ki = keys[i], kj = keys[j];
-          if (kj < ki) {
-            keys[i] = kj;
-            keys[j] = ki;
-            const uint32_t t = idx[i];
-            idx[i] = idx[j];
-            idx[j] = t;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  if (in_smem)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = sidx[i];
-}
-
-/* ======================================================================== */
-/* Kernel: key extrema. The loops only need sort[0].d and sort[count-1].d of  */
-/* every (cell, sid) array (dj_min / di_max, functions_hydro.h:1286,1418): the */
-/* candidate culling is done with boxes, not with the sorted order. One warp  */
-/* per cell computes the extrema of all its requested sids in one pass.       */
-/* ======================================================================== */
-__global__ void __launch_bounds__(128)
-    k_extrema(const int32_t *ext_cells, int ncells, const DevCell *cells, const double *x, float2 *ext) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= ncells) return;
-  const DevCell c = cells[ext_cells[w]];
-  const unsigned mask = c.sort_mask;
-  float mn[13], mx[13];
-#pragma unroll
-  for (int s = 0; s < 13; s++) {
-    mn[s] = 3.402823466e+38f;
-    mx[s] = -3.402823466e+38f;
-  }
-  for (int k = lane; k < c.count; k += 32) {
-    const size_t p = (size_t)c.first + k;
-    const double px = x[3 * p], py = x[3 * p + 1], pz = x[3 * p + 2];
-#pragma unroll
-    for (int s = 0; s < 13; s++) {
-      if ((mask >> s) & 1u) {
-        const float key = sort_key(px, py, pz, s);
-        mn[s] = fminf(mn[s], key);
-        mx[s] = fmaxf(mx[s], key);
-      }
-    }
-  }
-  int rank = 0;
-#pragma unroll
-  for (int s = 0; s < 13; s++) {
-    if ((mask >> s) & 1u) {
-      const float a = warp_min(mn[s]), b = warp_max(mx[s]);
-      if (lane == 0) ext[c.seg_base + rank] = make_float2(a, b);
-      rank++;
-    }
-  }
-}
-
-/* ======================================================================== */
-/* Kernels: the TMA-copyable source records of the tile pipeline             */
-/* (loops_tile.cuh). xf/x4 follow the positions (once per upload / xv halo), */
-/* xf.w follows h (again before the force loop), the octet boxes follow xf.  */
-/* ======================================================================== */
-__device__ __forceinline__ float reach2(float h, float margin) {
-  const float re = fmaf(__fmul_rn(h, KERNEL_GAMMA), PREFILTER_REL, margin);
-  return re * re;
-}
-__global__ void k_prep_tiles(const double *x, const float *h, int64_t n, float margin, float4 *xf,
-                             double *xs) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const double px = x[3 * p], py = x[3 * p + 1], pz = x[3 * p + 2];
-  xf[p] = make_float4(__double2float_rn(px), __double2float_rn(py), __double2float_rn(pz),
-                      reach2(h[p], margin));
-  xs[p] = px;
-  xs[(n + 4) + p] = py;
-  xs[2 * (n + 4) + p] = pz;
-}
-__global__ void k_refresh_reach(const float *h, int64_t n, float margin, float4 *xf) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  xf[p].w = reach2(h[p], margin);
-}
-/* gradient payload of every particle: (u, rho, soundspeed, alpha_visc) */
-__global__ void k_prep_gq(const float4 *fq1, const float4 *fq2, const float4 *fq3, int64_t n, float4 *gq) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const float4 q1 = fq1[p];
-  gq[p] = make_float4(fq2[p].z, q1.x, q1.w, fq3[p].x);
-}
-/* One warp per cell (every level): the axis-aligned box of each octet of 8
- * consecutive particles of the cell, in absolute floats. */
-__global__ void __launch_bounds__(128)
-    k_octet_boxes(const DevCell *cells, int ncells, const int32_t *box_first, const float4 *xf,
-                  float4 *boxes) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= ncells) return;
-  const int first = cells[c].first, count = cells[c].count;
-  const int noct = (count + 7) >> 3;
-  float4 *out = boxes + 2 * (size_t)box_first[c];
-  for (int o = lane; o < noct; o += 32) {
-    float lo0 = 3.0e30f, lo1 = 3.0e30f, lo2 = 3.0e30f, hi0 = -3.0e30f, hi1 = -3.0e30f, hi2 = -3.0e30f;
-    const int k1 = min(count, 8 * o + 8);
-    for (int k = 8 * o; k < k1; k++) {
-      const float4 f = xf[first + k];
-      lo0 = fminf(lo0, f.x); lo1 = fminf(lo1, f.y); lo2 = fminf(lo2, f.z);
-      hi0 = fmaxf(hi0, f.x); hi1 = fmaxf(hi1, f.y); hi2 = fmaxf(hi2, f.z);
-    }
-    out[2 * o] = make_float4(lo0, lo1, lo2, 0.f);
-    out[2 * o + 1] = make_float4(hi0, hi1, hi2, 0.f);
-  }
-}
-
-/* ======================================================================== */
-/* Kernels of the frame pipeline (loops_pipe.cuh)                            */
-/* ======================================================================== */
-/* One warp per frame: F[k] = (float)(x_k - origin) for the particles of the
- * frame's cell - the reference's pix / pjx of functions_hydro.h:1327-1338,
- * evaluated once per step instead of once per candidate pair. */
-__global__ void __launch_bounds__(128)
-    k_frames(const swiftgpu_handle::FrameRec *recs, int64_t nframes, const double *xs0, const double *xs1,
-             const double *xs2, float4 *frames) {
-  const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (f >= nframes) return;
-  const swiftgpu_handle::FrameRec R = recs[f];
-  float4 *out = frames + R.off;
-  for (int k = lane; k < R.count; k += 32) {
-    const size_t p = (size_t)R.first + k;
-    out[k] = make_float4(dsubf(xs0[p], R.o[0]), dsubf(xs1[p], R.o[1]), dsubf(xs2[p], R.o[2]), 0.f);
-  }
-}
-/* Octet boxes in the cell's OWN frame (float)(x - loc): what the culls of the
- * frame pipeline compare, shifted by the per-item float offset `d`. */
-__global__ void __launch_bounds__(128)
-    k_octet_boxes_own(const DevCell *cells, int ncells, const int32_t *box_first, const double *xs0,
-                      const double *xs1, const double *xs2, float4 *boxes) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= ncells) return;
-  const DevCell C = cells[c];
-  const int first = C.first, count = C.count;
-  const int noct = (count + 7) >> 3;
-  float4 *out = boxes + 2 * (size_t)box_first[c];
-  for (int o = lane; o < noct; o += 32) {
-    float lo0 = 3.0e30f, lo1 = 3.0e30f, lo2 = 3.0e30f, hi0 = -3.0e30f, hi1 = -3.0e30f, hi2 = -3.0e30f;
-    const int k1 = min(count, 8 * o + 8);
-    for (int k = 8 * o; k < k1; k++) {
-      const size_t p = (size_t)first + k;
-      const float fx = dsubf(xs0[p], C.loc[0]), fy = dsubf(xs1[p], C.loc[1]), fz = dsubf(xs2[p], C.loc[2]);
-      lo0 = fminf(lo0, fx); lo1 = fminf(lo1, fy); lo2 = fminf(lo2, fz);
-      hi0 = fmaxf(hi0, fx); hi1 = fmaxf(hi1, fy); hi2 = fmaxf(hi2, fz);
-    }
-    out[2 * o] = make_float4(lo0, lo1, lo2, 0.f);
-    out[2 * o + 1] = make_float4(hi0, hi1, hi2, 0.f);
-  }
-}
-/* One warp per (group, 64-target chunk) of the host task list: the TaskRec of
- * every NON-EMPTY task, compacted (the order of the heaviest-first list is kept
- * up to the scheduling of the warps). */
-__global__ void __launch_bounds__(128)
-    k_task_recs(const int32_t *task_group, const int32_t *task_chunk, int ntasks, const Group *groups,
-                const DevCell *cells, const int32_t *tgt_first, const int32_t *tgt_count,
-                const int32_t *tgt_list, const double *xs0, const double *xs1, const double *xs2,
-                const float *h, TaskRec *recs, unsigned int *ntask_dev, const unsigned long long *gate,
-                unsigned long long gate_lo, unsigned long long gate_hi) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= ntasks) return;
-  /* ghost re-runs: this launch only if the number of unconverged particles (a device counter the
-   * host never reads in between) is in [gate_lo, gate_hi) - else the other kernel takes the pass */
-  if (gate && (*gate < gate_lo || *gate >= gate_hi)) return;
-  const int g = task_group[w];
-  const int nt = tgt_count[g];
-  const int t0 = task_chunk[w] * PL_TARGETS;
-  if (t0 >= nt) return;
-  const int n = min(PL_TARGETS, nt - t0);
-  const Group G = groups[g];
-  const DevCell C = cells[G.tcell];
-  const int off = tgt_first[g] + t0;
-  float lo[3] = {3.0e30f, 3.0e30f, 3.0e30f}, hi[3] = {-3.0e30f, -3.0e30f, -3.0e30f}, rmax = 0.f;
-  for (int k = lane; k < n; k += 32) {
-    const int ti = tgt_list[off + k];
-    const float f[3] = {dsubf(xs0[ti], C.loc[0]), dsubf(xs1[ti], C.loc[1]), dsubf(xs2[ti], C.loc[2])};
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      lo[a] = fminf(lo[a], f[a]);
-      hi[a] = fmaxf(hi[a], f[a]);
-    }
-    rmax = fmaxf(rmax, __fmul_rn(h[ti], KERNEL_GAMMA));
-  }
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    lo[a] = warp_min(lo[a]);
-    hi[a] = warp_max(hi[a]);
-  }
-  rmax = warp_max(rmax);
-  if (lane == 0) {
-    TaskRec R;
-    R.item_first = G.item_first;
-    R.item_count = G.item_count;
-    R.tgt_off = off;
-    R.ntgt = n;
-    R.tcell = G.tcell;
-    for (int a = 0; a < 3; a++) {
-      R.lo[a] = lo[a];
-      R.hi[a] = hi[a];
-    }
-    R.rmax = rmax;
-    recs[atomicAdd(ntask_dev, 1u)] = R;
-  }
-}
-
-/* ======================================================================== */
-/* Kernel: target lists (active particles of each group's cell)              */
-/* ======================================================================== */
-__global__ void k_build_targets(const Group *groups, int ngroups, const DevCell *cells,
-                                const int8_t *time_bin, int max_active_bin, const int32_t *tgt_first,
-                                int32_t *tgt_count, int32_t *tgt_list, const Item *items,
-                                const int8_t *depth_h, unsigned long long *totals) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= ngroups) return;
-  const Group G = groups[g];
-  const DevCell c = cells[G.tcell];
-  /* A particle takes part in an item only if its depth_h lies in the item's
-   * range (limit_min_h / limit_max_h of the reference's recursion): targets
-   * outside the union of the group's ranges have nothing to do here. In a
-   * multi-level tree most particles of a non-leaf target cell are such. */
-  int lo = 127, hi = 0;
-  for (int k = lane; k < G.item_count; k += 32) {
-    const Item I = items[G.item_first + k];
-    lo = min(lo, (int)I.min_depth);
-    hi = max(hi, (int)I.max_depth);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
-    hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
-  }
-  int32_t *out = tgt_list + tgt_first[g];
-  int nout = 0;
-  for (int base = 0; base < c.count; base += 32) {
-    const int k = base + lane;
-    bool act = (k < c.count) && (time_bin[c.first + k] <= max_active_bin);
-    if (act) {
-      const int d = depth_h[c.first + k];
-      act = d >= lo && d <= hi;
-    }
-    const unsigned m = __ballot_sync(FULL_MASK, act);
-    if (act) out[nout + __popc(m & ((1u << lane) - 1u))] = c.first + k;
-    nout += __popc(m);
-  }
-  if (lane == 0) {
-    tgt_count[g] = nout;
-    if (nout) { /* totals[0] targets, totals[1] non-empty 64-target tasks: the launch picks the CTA size */
-      atomicAdd(totals, (unsigned long long)nout);
-      atomicAdd(totals + 1, (unsigned long long)((nout + TASK_TARGETS - 1) / TASK_TARGETS));
-    }
-  }
-}
-
-/* ======================================================================== */
-/* Per-particle finalisers                                                   */
-/* ======================================================================== */
-struct GhostArgs {
-  const Group *groups; /* subset groups: one per active local leaf */
-  int ngroups;
-  DevCell *cells;
-  int32_t *redo_list;  /* L_subset.tgt_list, indexed by particle slot */
-  int32_t *redo_count; /* L_subset.tgt_count */
-  Soa S;
-  float *left, *right;
-  int32_t *nd, *ng, *nf;
-  unsigned long long *n_redo;
-  int first_pass;
-  int max_active_bin;
-  float h_max, h_min, eps, eta_dim;
-  int use_mass_weighted;
-  float visc_alpha; /* hydro_props->viscosity.alpha (Minimal/Gadget2 Balsara prefactor) */
-  float H, a;
-  float num_reruns;
-};
-
-/* cell_set_part_h_depth, cell.h:1787-1815 */
-__device__ __forceinline__ int part_h_depth(const DevCell *cells, int leaf, float h, int current) {
-  const DevCell *c = &cells[leaf];
-  if (h < c->h_min_allowed) return c->depth;
-  int ci = leaf;
-  while (ci >= 0) {
-    c = &cells[ci];
-    if (h >= c->h_min_allowed && h < c->h_max_allowed) return c->depth;
-    ci = c->parent;
-  }
-  return current;
-}
-
-/* hydro_prepare_force + hydro_reset_acceleration (Minimal hydro.h:669-766,
- * Gadget2 hydro.h:648-744) or hydro_prepare_gradient + hydro_reset_gradient
- * (SPHENIX hydro.h:671-755), from the finished density sums. */
-template <int SCHEME>
-__device__ __forceinline__ void ghost_finalise(const GhostArgs &G, int p, float h, float rho,
-                                               float rho_dh, float wcount, float wcount_dh,
-                                               float div_v, float rx, float ry, float rz) {
-  const Soa &S = G.S;
-  const float u = S.u[p];
-  const int tb = S.time_bin[p];
-  const float curl_v = sqrtf(rx * rx + ry * ry + rz * rz);
-  float f, P, cs, balsara;
-  if (SCHEME == SCH_GADGET2) {
-    const float rho_inv = 1.f / rho;
-    const float h_inv = 1.f / h;
-    const float abs_div = fabsf(div_v + HYDRO_DIMENSION * G.H);
-    const float cb = cbrtf(rho);
-    const float pressure = u * (cb * cb * rho); /* entropy * pow_gamma(rho) */
-    cs = sqrtf(HYDRO_GAMMA * pressure / rho);
-    P = pressure * rho_inv * rho_inv;
-    balsara = G.visc_alpha * abs_div / (abs_div + curl_v + 0.0001f * cs * h_inv);
-    float rdh = rho_dh;
-    if (h > 0.9999f * G.h_max) rdh = 0.f;
-    const float grad_rho_term = HYDRO_DIMENSION_INV * h * rdh * rho_inv;
-    f = (grad_rho_term < -0.9999f) ? 1.f : 1.f / (1.f + grad_rho_term);
-  } else {
-    P = HYDRO_GAMMA_MINUS_ONE * u * rho;
-    cs = sqrtf(HYDRO_GAMMA * P / rho);
-    const float common_factor = h * HYDRO_DIMENSION_INV / wcount;
-    if (h > 0.9999f * G.h_max) {
-      f = 0.f;
-    } else {
-      const float grad_W_term = common_factor * wcount_dh;
-      f = (grad_W_term < -0.9999f) ? 0.f : common_factor * rho_dh / (1.f + grad_W_term);
-    }
-    if (SCHEME == SCH_MINIMAL) {
-      const float h_inv = 1.f / h;
-      const float abs_div = fabsf(div_v + HYDRO_DIMENSION * G.H);
-      balsara = G.visc_alpha * abs_div / (abs_div + curl_v + 0.0001f * cs * h_inv);
-    } else {
-      const float abs_div = fabsf(div_v);
-      balsara = abs_div / (abs_div + curl_v + 0.0001f * cs * 1.f / h);
-    }
-  }
-  S.rho[p] = rho;
-  S.fq1[p] = make_float4(rho, P, f, cs);
-  S.fq2[p] = make_float4(balsara, h, SCHEME == SCH_SPHENIX ? u : hg2_exact(h), __int_as_float(tb));
-  if (SCHEME == SCH_SPHENIX) {
-    const float al = S.alpha[p];
-    S.fq3[p] = make_float4(al, S.alpha_diff[p], hg2_exact(h), 0.f);
-    S.div_v[p] = div_v;
-    S.g_vsig[p] = 2.f * cs; /* hydro_reset_gradient */
-    S.g_amax[p] = al;
-    G.ng[p] = 0;
-  } else {
-    S.fo1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    S.f_hdt[p] = 0.f;
-    S.f_vsig[p] = 2.f * cs;
-    S.f_minngb[p] = NUM_TIME_BINS + 1; /* timestep_limiter_prepare_force */
-    G.nf[p] = 0;
-  }
-  /* keep the finished density members for a density-level download */
-  S.dA[p] = make_float4(rho, rho_dh, wcount, wcount_dh);
-  S.dB[p] = make_float4(div_v, rx, ry, rz);
-}
-
-/* runner_do_ghost leaf loop, runner_ghost.c:1197-1538. One warp per leaf. */
-template <int SCHEME>
-__global__ void __launch_bounds__(128) k_ghost(const GhostArgs G) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= G.ngroups) return;
-  const int leaf = G.groups[g].tcell;
-  const DevCell c = G.cells[leaf];
-  const Soa &S = G.S;
-  const int n_in = G.first_pass ? c.count : G.redo_count[g];
-  int32_t *list = G.redo_list + c.first;
-  int nout = 0;
-  float hmax_conv = 0.f;
-  bool any_conv = false;
-  for (int base = 0; base < n_in; base += 32) {
-    const int k = base + lane;
-    bool valid = k < n_in;
-    int p = -1;
-    if (valid) p = G.first_pass ? c.first + k : list[k];
-    if (valid && G.first_pass) valid = S.time_bin[p] <= G.max_active_bin;
-    bool redo = false;
-    if (valid) {
-      float left = G.first_pass ? 0.f : G.left[p];
-      float right = G.first_pass ? G.h_max : G.right[p];
-      const float h_old = S.h[p];
-      const float h_old_dim = h_old * h_old * h_old;
-      const float h_old_dim_minus_one = h_old * h_old;
-      const float4 a = S.dA[p], b = S.dB[p];
-      const float m = S.mv[p].x;
-      float rho = a.x, rho_dh = a.y, wcount = a.z, wcount_dh = a.w;
-      float div_v = b.x, rx = b.y, ry = b.z, rz = b.w;
-      float h_new = 0.f;
-      bool has_no_ngb = false;
-      bool done_early = false;
-      if (wcount < 1.e-5 * (double)KERNEL_ROOT) {
-        has_no_ngb = true;
-        h_new = 2.f * h_old;
-      } else {
-        /* hydro_end_density: Minimal :543, Gadget2 :526, SPHENIX :613 */
-        const float h_inv = 1.0f / h_old;
-        const float h_inv_dim = h_inv * h_inv * h_inv;
-        const float h_inv_dim_plus_one = h_inv_dim * h_inv;
-        rho += m * KERNEL_ROOT;
-        rho_dh -= HYDRO_DIMENSION * m * KERNEL_ROOT;
-        wcount += KERNEL_ROOT;
-        wcount_dh -= HYDRO_DIMENSION * KERNEL_ROOT;
-        rho *= h_inv_dim;
-        rho_dh *= h_inv_dim_plus_one;
-        wcount *= h_inv_dim;
-        wcount_dh *= h_inv_dim_plus_one;
-        const float rho_inv = 1.f / rho;
-        const float a_inv2 = 1.f / (G.a * G.a);
-        const float fac = h_inv_dim_plus_one * a_inv2 * rho_inv;
-        rx *= fac;
-        ry *= fac;
-        rz *= fac;
-        if (SCHEME == SCH_SPHENIX) {
-          div_v *= h_inv_dim_plus_one * rho_inv * a_inv2;
-          div_v += G.H * HYDRO_DIMENSION;
-        } else {
-          div_v *= fac;
-        }
-        if (G.use_mass_weighted) {
-          const float inv_mass = 1.f / m;
-          wcount = rho * inv_mass;
-          wcount_dh = rho_dh * inv_mass;
-        }
-        const float n_sum = wcount * h_old_dim;
-        const float n_target = G.eta_dim;
-        const float f = n_sum - n_target;
-        const float f_prime = wcount_dh * h_old_dim + HYDRO_DIMENSION * wcount * h_old_dim_minus_one;
-        if (n_sum < n_target)
-          left = fmaxf(left, h_old);
-        else if (n_sum > n_target)
-          right = fminf(right, h_old);
-        if (((h_old >= G.h_max) && (f < 0.f)) || ((h_old <= G.h_min) && (f > 0.f))) {
-          /* already at the limit: tidy up as if converged (:1271-1352) */
-          ghost_finalise<SCHEME>(G, p, h_old, rho, rho_dh, wcount, wcount_dh, div_v, rx, ry, rz);
-          hmax_conv = fmaxf(hmax_conv, h_old);
-          any_conv = true;
-          done_early = true;
-        } else {
-          h_new = h_old - f / (f_prime + 1.17549435e-38f);
-          h_new = fminf(h_new, 2.f * h_old);
-          h_new = fmaxf(h_new, 0.5f * h_old);
-          h_new = fmaxf(h_new, left);
-          h_new = fminf(h_new, right);
-        }
-      }
-      if (!done_early) {
-        float h_final = h_old;
-        if (fabsf(h_new - h_old) > G.eps * h_old) {
-          float h_set;
-          if ((h_new == left && h_old == right) || (h_old == left && h_new == right)) {
-            h_set = cbrtf(0.5f * (left * left * left + right * right * right));
-          } else {
-            h_set = h_new;
-          }
-          if (h_set < G.h_max && h_set > G.h_min) {
-            redo = true;
-            S.h[p] = h_set;
-            G.left[p] = left;
-            G.right[p] = right;
-            /* hydro_init_part */
-            S.dA[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            S.dB[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (SCHEME == SCH_SPHENIX) S.g_lap[p] = 0.f;
-            G.nd[p] = 0;
-          } else if (h_set <= G.h_min) {
-            h_final = G.h_min;
-          } else {
-            h_final = G.h_max;
-            if (has_no_ngb) {
-              /* hydro_part_has_no_neighbours */
-              const float h_inv = 1.0f / h_final;
-              const float h_inv_dim = h_inv * h_inv * h_inv;
-              rho = m * KERNEL_ROOT * h_inv_dim;
-              wcount = KERNEL_ROOT * h_inv_dim;
-              rho_dh = wcount_dh = div_v = rx = ry = rz = 0.f;
-            }
-          }
-        }
-        if (!redo) {
-          S.h[p] = h_final;
-          S.depth_h[p] = (int8_t)part_h_depth(G.cells, leaf, h_final, S.depth_h[p]);
-          hmax_conv = fmaxf(hmax_conv, h_final);
-          any_conv = true;
-          ghost_finalise<SCHEME>(G, p, h_final, rho, rho_dh, wcount, wcount_dh, div_v, rx, ry, rz);
-        }
-      }
-    }
-    __syncwarp();
-    const unsigned m = __ballot_sync(FULL_MASK, redo);
-    if (redo) list[nout + __popc(m & ((1u << lane) - 1u))] = p;
-    nout += __popc(m);
-    __syncwarp();
-  }
-  hmax_conv = warp_max(hmax_conv);
-  const bool anyc = __any_sync(FULL_MASK, any_conv);
-  if (lane == 0) {
-    G.redo_count[g] = nout;
-    if (nout) atomicAdd(G.n_redo, (unsigned long long)nout);
-    if (anyc) {
-      /* atomic_max_f on the leaf and all its parents (:1621-1632) */
-      for (int ci = leaf; ci >= 0; ci = G.cells[ci].parent) {
-        atomic_max_pos(&G.cells[ci].h_max, hmax_conv);
-        atomic_max_pos(&G.cells[ci].h_max_active, hmax_conv);
-      }
-    }
-  }
-}
-
-/* runner_do_extra_ghost (runner_ghost.c:1016): hydro_end_gradient +
- * hydro_prepare_force + hydro_reset_acceleration, SPHENIX hydro.h:762-972. */
-struct ExtraArgs {
-  const Group *groups;
-  int ngroups;
-  const DevCell *cells;
-  Soa S;
-  int32_t *nf;
-  int max_active_bin;
-  double time_base;
-  float a;
-  float alpha_max, alpha_min, length, beta, diff_alpha_max, diff_alpha_min;
-};
-__global__ void __launch_bounds__(128) k_extra_ghost(const ExtraArgs E) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= E.ngroups) return;
-  const DevCell c = E.cells[E.groups[g].tcell];
-  const Soa &S = E.S;
-  for (int k = lane; k < c.count; k += 32) {
-    const int p = c.first + k;
-    const int bin = S.time_bin[p];
-    if (bin > E.max_active_bin) continue;
-    const float h = S.h[p];
-    const float h_inv = 1.0f / h;
-    const float h_inv_dim_plus_one = h_inv * h_inv * h_inv * h_inv;
-    float laplace_u = S.g_lap[p] * (2.f * h_inv_dim_plus_one);
-    /* get_timestep (timeline.h:91), passed as a float argument */
-    const float dt_alpha = (float)((double)(bin <= 0 ? 0LL : 1LL << (bin + 1)) * E.time_base);
-    const float4 q1 = S.fq1[p];
-    const float rho = q1.x;
-    const float u = S.u[p];
-    const float div_v = S.div_v[p];
-    const float kernel_support_physical = h * E.a * KERNEL_GAMMA;
-    const float kernel_support_physical_inv = 1.f / kernel_support_physical;
-    const float v_sig_physical = S.g_vsig[p];
-    const float pressure = HYDRO_GAMMA_MINUS_ONE * u * rho;
-    const float soundspeed_physical = sqrtf(HYDRO_GAMMA * pressure / rho);
-    const float sound_crossing_time_inverse = soundspeed_physical * kernel_support_physical_inv;
-    const float div_v_dt = dt_alpha == 0.f ? 0.f : (div_v - S.div_v_prev[p]) / dt_alpha;
-    const float Sterm = div_v < 0.f ? kernel_support_physical * kernel_support_physical *
-                                          fmaxf(0.f, -1.f * div_v_dt)
-                                    : 0.f;
-    const float soundspeed_square = soundspeed_physical * soundspeed_physical;
-    const float alpha_loc = E.alpha_max * Sterm / (soundspeed_square + Sterm);
-    float alpha = S.alpha[p];
-    if (alpha_loc > alpha) {
-      alpha = alpha_loc;
-    } else {
-      const float timescale_ratio = dt_alpha * sound_crossing_time_inverse * E.length;
-      alpha += alpha_loc * timescale_ratio;
-      alpha /= (1.f + timescale_ratio);
-    }
-    alpha = fmaxf(alpha, E.alpha_min);
-    S.alpha[p] = alpha;
-    S.div_v_prev[p] = div_v;
-    S.div_v_dt[p] = div_v_dt;
-    const float diffusion_timescale_physical_inverse = v_sig_physical * kernel_support_physical_inv;
-    const float sqrt_u_inv = 1.f / sqrtf(u);
-    float alpha_diff_dt = E.beta * kernel_support_physical * laplace_u * sqrt_u_inv * (1.f / (E.a * E.a));
-    const float ad = S.alpha_diff[p];
-    alpha_diff_dt -= (ad - E.diff_alpha_min) * diffusion_timescale_physical_inverse;
-    float new_ad = ad + alpha_diff_dt * dt_alpha;
-    new_ad = fmaxf(new_ad, E.diff_alpha_min);
-    const float viscous_diffusion_limit = E.diff_alpha_max * (1.f - S.g_amax[p] / E.alpha_max);
-    new_ad = fminf(new_ad, viscous_diffusion_limit);
-    S.alpha_diff[p] = new_ad;
-    S.g_lap[p] = laplace_u;
-    S.fq3[p] = make_float4(alpha, new_ad, hg2_exact(h), 0.f);
-    /* hydro_reset_acceleration + timestep_limiter_prepare_force */
-    S.fo1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    S.f_hdt[p] = 0.f;
-    S.f_minngb[p] = NUM_TIME_BINS + 1;
-    E.nf[p] = 0;
-  }
-}
-
-/* runner_do_end_hydro_force (runner_others.c:815): hydro_end_force, and in the
- * same pass hydro_compute_timestep (Minimal hydro.h:440, Gadget2 :444, SPHENIX
- * :475) with the reference's order of operations (separate IEEE multiplies and
- * one divide), so that dt is bit-identical for identical h and v_sig. */
-__global__ void __launch_bounds__(128)
-    k_end_force(const Group *groups, int ngroups, const DevCell *cells, Soa S, int max_active_bin,
-                int scheme, float cfl, float a, float a_factor_sound_speed, float *dt_cfl) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= ngroups) return;
-  const DevCell c = cells[groups[g].tcell];
-  for (int k = lane; k < c.count; k += 32) {
-    const int p = c.first + k;
-    if (S.time_bin[p] > max_active_bin) {
-      dt_cfl[p] = -1.f;
-      continue;
-    }
-    const float h = S.h[p];
-    S.f_hdt[p] *= h * HYDRO_DIMENSION_INV;
-    if (scheme == SCH_GADGET2) {
-      /* 0.5 * gas_entropy_from_internal_energy(rho, entropy_dt) */
-      const float cbrt_inv = 1.f / cbrtf(S.rho[p]);
-      float4 o = S.fo1[p];
-      o.w = 0.5f * (HYDRO_GAMMA_MINUS_ONE * o.w * (cbrt_inv * cbrt_inv));
-      S.fo1[p] = o;
-    }
-    const float v_sig = scheme == SCH_SPHENIX ? S.g_vsig[p] : S.f_vsig[p];
-    const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(2.f, KERNEL_GAMMA), cfl), a), h);
-    dt_cfl[p] = __fdiv_rn(num, __fmul_rn(a_factor_sound_speed, v_sig));
-  }
-}
-
-/* hydro_init_part for the active particles (cell_drift.c:361) */
-__global__ void k_init_parts(Soa S, int32_t *nd, int64_t n, int max_active_bin, int scheme) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  if (S.time_bin[p] > max_active_bin) return;
-  S.dA[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-  S.dB[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (scheme == SCH_SPHENIX) S.g_lap[p] = 0.f;
-  nd[p] = 0;
-}
-
-/* Which h_max-dependent recursion predicates does each cell satisfy NOW?
- * loop 2: cell.h:966 subpair2, :1007 subself2 (h_max, dx_max_part);
- * loop 1: cell.h:951 subpair, :992 subself (h_max_active, dx_max_part_old).
- * Compared with the bits the worklist was built with (Flattener::subpair*);
- * a mismatch triggers a rebuild of that list on the host. */
-__global__ void k_pred_bits(const DevCell *cells, const float *dmin, const float *dx_max_part,
-                            const uint8_t *bits, int ncells, int use_active, int32_t *flag) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncells) return;
-  uint8_t b = 0;
-  if (((cells[c].flags >> 2) & 1) && cells[c].count >= 100) { /* Flattener::recursable */
-    const float hm = use_active ? cells[c].h_max_active : cells[c].h_max;
-    const float gh = __fmul_rn(KERNEL_GAMMA, hm);
-    const float half = __fmul_rn(0.5f, dmin[c]);
-    b = (uint8_t)((__fadd_rn(gh, dx_max_part[c]) < half) ? 1 : 0) | (uint8_t)((gh < half) ? 2 : 0);
-  }
-  if (b != bits[c]) *flag = 1;
-}
-
-__global__ void k_get_cell_hmax(const DevCell *cells, int ncells, float *h_max, float *h_max_active) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncells) return;
-  h_max[c] = cells[c].h_max;
-  h_max_active[c] = cells[c].h_max_active;
-}
+#include "kernels_records.cuh"
+#include "kernels_finalise.cuh"
 
 /* ======================================================================== */
 /* Host side                                                                 */
@@ -1981,14 +1094,20 @@ static int loop_kind() {
     const char *e = getenv("SWIFTGPU_LOOPS");
     const char *w = getenv("SWIFTGPU_WARP_LOOPS");
     v = 3;
+#ifdef SWIFTGPU_LEGACY_LOOPS
     if (e && !strcmp(e, "tile")) v = 2;
     if (e && !strcmp(e, "cta")) v = 1;
     if (e && !strcmp(e, "warp")) v = 0;
     if (w && w[0] == '1') v = 0;
+#else
+    (void)e;
+    (void)w;
+#endif
   }
   return v;
 }
 static bool use_cta_loops() { return loop_kind() >= 1; }
+#ifdef SWIFTGPU_LEGACY_LOOPS
 #ifndef TL_FORCE_NS
 #define TL_FORCE_NS 4 /* ring stages of the force kernel (SPHENIX: one less, 4 payload columns) */
 #endif
@@ -2030,6 +1149,8 @@ static cudaError_t launch_tile(H *h, const LoopArgs &A, bool sparse = false) {
   if (sparse) return launch_tile_cw<LOOP, SCHEME, 4>(h, A);
   return launch_tile_cw<LOOP, SCHEME, 8>(h, A);
 }
+#endif /* SWIFTGPU_LEGACY_LOOPS */
+
 /* sparse target sets (late ghost iterations): one warp per target, loops_direct.cuh */
 static int launch_direct_density(H *h, const DevList &D, const LoopArgs &A, const unsigned long long *gate = nullptr,
                                  unsigned long long gate_hi = ~0ull) {
@@ -2104,6 +1225,7 @@ static cudaError_t launch_pipe(H *h, const LoopArgs &A) {
   return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_DENSITY, 64>(h, A);
 }
 
+#ifdef SWIFTGPU_LEGACY_LOOPS
 template <int LOOP, bool SUBSET, int SCHEME>
 static cudaError_t launch_cta(H *h, const LoopArgs &A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
@@ -2119,21 +1241,32 @@ static cudaError_t launch_cta(H *h, const LoopArgs &A) {
   k_cta<LOOP, SUBSET, SCHEME><<<A.ntasks, CTA_THREADS, bytes, h->stream>>>(A);
   return cudaGetLastError();
 }
+#endif
 template <int LOOP, bool SUBSET>
 static cudaError_t launch_loop1(H *h, const LoopArgs &A, bool sparse = false) {
   if (loop_kind() == 3) return launch_pipe<LOOP, SUBSET, 0>(h, A);
+#ifdef SWIFTGPU_LEGACY_LOOPS
   if (loop_kind() == 2) return launch_tile<LOOP, 0>(h, A, sparse);
   if (use_cta_loops()) return launch_cta<LOOP, SUBSET, 0>(h, A);
   k_loop1<LOOP, SUBSET><<<A.ntasks, 32, Tile1<LOOP, SUBSET>::kBytes, h->stream>>>(A);
   return cudaGetLastError();
+#else
+  (void)sparse;
+  return cudaErrorNotSupported;
+#endif
 }
 template <int SCHEME>
 static cudaError_t launch_loop2(H *h, const LoopArgs &A, bool sparse = false) {
   if (loop_kind() == 3) return launch_pipe<LOOP_FORCE, false, SCHEME>(h, A);
+#ifdef SWIFTGPU_LEGACY_LOOPS
   if (loop_kind() == 2) return launch_tile<LOOP_FORCE, SCHEME>(h, A, sparse);
   if (use_cta_loops()) return launch_cta<LOOP_FORCE, false, SCHEME>(h, A);
   k_loop2<SCHEME><<<A.ntasks, 32, Tile2<SCHEME>::kBytes, h->stream>>>(A);
   return cudaGetLastError();
+#else
+  (void)sparse;
+  return cudaErrorNotSupported;
+#endif
 }
 
 extern "C" int swiftgpu_run_density(swiftgpu_t *h) {

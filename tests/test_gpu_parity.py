@@ -241,14 +241,15 @@ print("ALT_OK", rep["flips"])
 """
 
 
-@pytest.mark.parametrize("env", [{"SWIFTGPU_LOOPS": "tile"}, {"SWIFTGPU_LOOPS": "cta"}, {"SWIFTGPU_LOOPS": "warp"},
-                                 {"SWIFTGPU_NO_REORDER": "1"}],
-                         ids=["loops=tile", "loops=cta", "loops=warp", "no_reorder"])
-def test_alternative_kernels_stay_green(env):
-    """The older loop generations (k_cta, k_loop1/2), the host particle order,
-    the 4-warp CTAs for every ghost re-run and a 1-deep hold are selected by
-    environment variables read once per process: run each in a subprocess on a
-    small SPHENIX box (all three loops) against the C restatement."""
+@pytest.mark.parametrize("env", [{"SWIFTGPU_NO_REORDER": "1"}, {"SWIFTGPU_DIRECT": "1000"}, {"SWIFTGPU_DIRECT": "0"},
+                                 {"SWIFTGPU_HOLD": "2"}],
+                         ids=["no_reorder", "direct_reruns", "pipe_reruns", "serial_fragment_layout"])
+def test_alternative_paths_stay_green(env):
+    """Code paths chosen by data or by environment variables read once per process: the host particle
+    order (no Morton order inside the leaves), the per-target kernel for EVERY ghost re-run
+    (loops_direct.cuh) or for none, and the producer's serial fragment layout for every window
+    (loops_pipe.cuh: the fallback for double-mode items larger than a stage's double columns). Each
+    runs in a subprocess on a small SPHENIX box (all three loops) against the C restatement."""
     import os
     import subprocess
     import sys
