@@ -1,6 +1,8 @@
 """Turns the ncu outputs of a gpurun call into the tracked text summaries under
-profiles/:  python scripts/profile_summary.py <tag> <launches.csv> <full.ncu-rep>"""
-import collections, csv, io, os, subprocess, sys
+profiles/:  python scripts/profile_summary.py <tag> <launches.csv> <full.ncu-rep> [workload]
+With a workload name it also writes profiles/<tag>_traffic.json (DRAM bytes per launch of the
+neighbour-loop kernels: what bench.py reports as roofline.traffic)."""
+import collections, csv, io, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 out = []
@@ -33,5 +35,19 @@ for r in rr[2:]:
         if w in HH:
             out.append(f"- {w} = {r[HH.index(w)]} {rr[1][HH.index(w)]}")
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+if len(sys.argv) > 4:
+    traffic = {}
+    for r in rr[2:]:
+        nm = r[HH.index("Kernel Name")]
+        mm = re.match(r"void k_pipe<(\d+), (\d+), (\d+), (\d+), (\d+)>", nm)
+        if not mm: continue
+        loop = {"0": "density", "1": "gradient", "2": "force"}[mm.group(1)]
+        if loop == "density" and mm.group(5) == "256": loop = "subset"
+        def val(name):
+            v, u = float(r[HH.index(name)].replace(",", "")), rr[1][HH.index(name)]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        traffic.setdefault("k_pipe:" + loop, val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+    json.dump({sys.argv[4]: traffic, "source": f"ncu --set full --clock-control none, first captured launch of each kernel ({os.path.basename(rep)})"},
+              open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("wrote", f"profiles/{tag}_summary.md")
