@@ -27,6 +27,7 @@ def load(scheme_name):
         lib.port_get_cells.argtypes = [VP, VP]
         lib.port_get_counts.argtypes = [VP, VP, VP, VP]
         lib.port_ghost_iterations.argtypes = [VP]
+        lib.port_ghost_redo.argtypes = [VP, VP]
         lib.port_get_gross.argtypes = [VP] * 10
         lib.port_kernel_deval.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.port_sub_pairs.argtypes = [C.c_int, VP, VP]
@@ -77,6 +78,12 @@ class Port:
 
     def ghost_iterations(self):
         return self.lib.port_ghost_iterations(self.h)
+
+    def ghost_redo(self):
+        """particles that entered re-run k of the ghost, k = 0..31"""
+        out = (C.c_longlong * 32)()
+        self.lib.port_ghost_redo(self.h, out)
+        return [int(v) for v in out]
 
     def close(self):
         if self.h:

@@ -119,6 +119,7 @@ typedef struct port {
   float *nz_B, *nz_ad, *nz_al;
   int *leaf_of; /* leaf cell index of each particle */
   int ghost_iterations;
+  long long ghost_redo[32]; /* particles sent to re-run k of the ghost (diagnostic) */
   int ghost_failed;
 } port_t;
 
@@ -1250,6 +1251,7 @@ static void ghost_leaf(port_t *s, int c_, int *ngb_top) {
     }
     count = redo;
     if (count > 0) {
+      s->ghost_redo[num_reruns < 31 ? num_reruns : 31] += count;
       /* climb to the top level, where the density tasks are linked (:1548) */
       int finger = c_;
       while (s->cells[finger].parent >= 0) finger = s->cells[finger].parent;
@@ -1386,6 +1388,7 @@ int port_run(port_t *s, unsigned mask) {
   if (mask & SWIFTGPU_PHASE_GHOST) {
     int *ngb = (int *)malloc(sizeof(int) * s->ntop);
     s->ghost_iterations = 0;
+    memset(s->ghost_redo, 0, sizeof(s->ghost_redo));
     s->ghost_failed = 0;
     for (int a = 0; a < s->ntop; a++)
       if (s->cells[s->top[a]].nodeID == s->cfg.rank) ghost_recurse(s, s->top[a], ngb);
@@ -1491,6 +1494,8 @@ void port_get_counts(const port_t *s, int *nd, int *ng, int *nf) {
   if (nf) memcpy(nf, s->nf, sizeof(int) * s->n);
 }
 int port_ghost_iterations(const port_t *s) { return s->ghost_iterations; }
+/* particles that entered re-run k of the ghost (k = 0..31), summed over the leaves */
+void port_ghost_redo(const port_t *s, long long out[32]) { memcpy(out, s->ghost_redo, sizeof(s->ghost_redo)); }
 /* The un-cancelled sums (sum over neighbours of |pair term|, finalised with the
  * same factors as the sums) of a_hydro (norm), u_dt | entropy_dt, h_dt, div_v,
  * rho_dh and laplace_u: what the parity metric floors its relative errors with. */

@@ -153,7 +153,8 @@ _host = None
 
 
 def lib_path():
-    return os.path.join(HERE, "libswiftgpu.so")
+    # SWIFTGPU_LIB: another BUILD of the same CUDA library (A/B of compile-time parameters)
+    return os.environ.get("SWIFTGPU_LIB") or os.path.join(HERE, "libswiftgpu.so")
 
 
 def load():

@@ -60,7 +60,9 @@
 
 namespace swiftgpu {
 
-#define PL_SLOTS 256 /* source slots per stage (8-bit slot field of the list entries) */
+#ifndef PL_SLOTS
+#define PL_SLOTS 256 /* source slots per stage (8-bit slot field of the list entries); multiple of 8, <= 256 */
+#endif
 #define PL_OCT (PL_SLOTS / 8)
 #define PL_FRAGS 8 /* fragments (items) per stage */
 #define PL_TARGETS 64 /* targets of a task (host task list chunk = TASK_TARGETS) */
@@ -714,8 +716,13 @@ __global__ void __launch_bounds__(32 * (CW + 1), 2) k_pipe(const LoopArgs A) {
       mbar_wait(sFull + s0, (uint32_t)((it / NS) & 1));
       const int32_t *const meta0 = (const int32_t *)(smem + s0 * SM::kStageBytes + SM::kStageMeta);
       if (meta0[PM_FLAG] == 2) break;
-      const int slot_t = warp * 8 + t8;
-      tvalid = slot_t < meta0[PM_NTGT];
+      /* the task's targets are dealt evenly to the CW warps (a sparse task - ghost re-runs, few
+       * active particles - keeps every warp busy with a small target box instead of filling the
+       * first warps only); 64 targets: 8 per warp as they lie */
+      const int ntgt = meta0[PM_NTGT];
+      const int per = (ntgt + CW - 1) / CW;
+      const int slot_t = warp * per + t8;
+      tvalid = t8 < per && slot_t < ntgt;
       ti = tvalid ? A.tgt_list[meta0[PM_TGT_OFF] + slot_t] : -1;
       const double *const ml = (const double *)(meta0 + PM_LOC);
       const double l0 = ml[0], l1 = ml[1], l2 = ml[2];

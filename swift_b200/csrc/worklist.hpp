@@ -436,6 +436,60 @@ class Flattener {
       emit(MODE_SUB_SELF, cur_leaf_, ci, 0, nullptr, 0, 127, 0, ci);
   }
 
+  /* Order of the items INSIDE a group (free: it only permutes sums). The loops stream the source
+   * cells of a group through a ring of stages that the 8 consumer warps of a CTA - each owning one
+   * octant of the target leaf - drain in lock-step up to the ring depth. A source cell on the +x
+   * side keeps the +x warps busy and the -x warps idle; a run of same-side cells (the sid order
+   * the recursion emits) therefore piles up skew that the ring cannot absorb. Greedy re-ordering:
+   * next comes the item that keeps the running sum of (direction x source count) smallest, which
+   * alternates opposite sides. */
+  void balance_directions(std::vector<uint32_t> &order) const {
+    std::vector<uint32_t> tmp;
+    std::vector<float> d;
+    std::vector<char> used;
+    for (size_t g0 = 0; g0 < order.size();) {
+      size_t g1 = g0 + 1;
+      const int32_t tc = raw_[order[g0]].it.tcell;
+      while (g1 < order.size() && raw_[order[g1]].it.tcell == tc) g1++;
+      const size_t n = g1 - g0;
+      if (n > 2 && n <= 4096) {
+        d.assign(3 * n, 0.f);
+        const swiftgpu_cell &T = c_[tc];
+        for (size_t k = 0; k < n; k++) {
+          const swiftgpu_cell &S = c_[raw_[order[g0 + k]].it.scell];
+          for (int a = 0; a < 3; a++) {
+            double x = (S.loc[a] + 0.5 * S.width[a]) - (T.loc[a] + 0.5 * T.width[a]);
+            if (periodic_) x -= dim_[a] * std::floor(x / dim_[a] + 0.5);
+            d[3 * k + a] = (float)(x / T.width[a]) * (float)S.count;
+          }
+        }
+        used.assign(n, 0);
+        tmp.resize(n);
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (size_t pos = 0; pos < n; pos++) {
+          size_t best = 0;
+          float bestv = 3.0e38f;
+          for (size_t k = 0; k < n; k++) {
+            if (used[k]) continue;
+            const float ax = sx + d[3 * k], ay = sy + d[3 * k + 1], az = sz + d[3 * k + 2];
+            const float v = ax * ax + ay * ay + az * az;
+            if (v < bestv) {
+              bestv = v;
+              best = k;
+            }
+          }
+          used[best] = 1;
+          tmp[pos] = order[g0 + best];
+          sx += d[3 * best];
+          sy += d[3 * best + 1];
+          sz += d[3 * best + 2];
+        }
+        for (size_t k = 0; k < n; k++) order[g0 + k] = tmp[k];
+      }
+      g0 = g1;
+    }
+  }
+
   void finish(WorkList &out, bool keep_aux) {
     /* group by target cell, stable */
     std::vector<uint32_t> order(raw_.size());
@@ -443,6 +497,7 @@ class Flattener {
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
       return raw_[a].it.tcell < raw_[b].it.tcell;
     });
+    if (!getenv("SWIFTGPU_NO_BALANCE")) balance_directions(order); /* A/B knob */
     out.items.resize(raw_.size());
     out.groups.clear();
     sorted_aux_.clear();
