@@ -251,7 +251,8 @@ int swiftgpu_run_step(swiftgpu_t *h, uint32_t phase_mask);
 int swiftgpu_download_parts(swiftgpu_t *h, void *parts_aos, int64_t nparts);
 int swiftgpu_download_parts_device(swiftgpu_t *h, void *d_parts_aos,
                                    int64_t nparts);
-/* Per-cell h_max / h_max_active after the ghost (runner_ghost.c:1621-1632). */
+/* Per-cell h_max / h_max_active after the ghost (runner_ghost.c:1621-1632);
+ * after swiftgpu_run_drift also dx_max_part / dx_max_sort. */
 int swiftgpu_download_cells(swiftgpu_t *h, swiftgpu_cell *cells, int32_t ncells);
 /* hydro_compute_timestep (hydro/Minimal/hydro.h:440, Gadget2/hydro.h:444,
  * SPHENIX/hydro.h:475): the CFL time-step 2 kernel_gamma CFL a h /
@@ -261,6 +262,48 @@ int swiftgpu_download_cells(swiftgpu_t *h, swiftgpu_cell *cells, int32_t ncells)
  * dt). Inactive particles get -1. dt_cfl holds nparts floats in the host's
  * particle order. */
 int swiftgpu_download_timestep(swiftgpu_t *h, float *dt_cfl, int64_t nparts);
+/*
+ * Drift on the device: cell_drift_part (src/cell_drift.c:159-400)
+ * with force = 1 over every LOCAL top-level cell, i.e. engine_drift_all's mapper
+ * (src/engine_drift.c:83) / the drift_part tasks of a step in which every cell
+ * is drifted from the same ti_old_part. Per particle: drift_part
+ * (src/drift.h:141-215: x += v_full dt_drift, v += a_hydro dt_kick_hydro,
+ * hydro_predict_extra of the scheme - Minimal hydro.h:815, Gadget2 :798,
+ * SPHENIX :1029 -, x_diff / x_diff_sort -= v_full dt_drift), the h_min/h_max
+ * clamp, cell_set_part_h_depth, optionally part_init -> hydro_init_part of the
+ * ACTIVE particles (runner_drift.c:45 passes init_particles = 1); per cell: the
+ * reductions h_max, h_max_active, dx_max_part, dx_max_sort up the tree
+ * (cell_drift.c:219-232,380-390).
+ *
+ * It works on the device copy of the caller's struct part[] (what
+ * swiftgpu_upload_parts brought, with the results of the last step written
+ * back into it first) and of struct xpart[] (only x_diff, x_diff_sort, v_full
+ * are touched; gravity, cosmological factors, entropy / pressure floors,
+ * forcing and particle removal at non-periodic borders are the host's). After
+ * the call swiftgpu_download_parts / _xparts / _cells return the drifted state
+ * and the next swiftgpu_run_step starts from it, without the particles
+ * crossing the host boundary in between.
+ */
+typedef struct swiftgpu_xpart_layout {
+  int32_t size;        /* sizeof(struct xpart) */
+  int32_t x_diff;      /* offsetof(struct xpart, x_diff), float[3] */
+  int32_t x_diff_sort; /* float[3] */
+  int32_t v_full;      /* float[3] */
+} swiftgpu_xpart_layout;
+
+typedef struct swiftgpu_drift_args {
+  /* the factors cell_drift_part derives (cell_drift.c:236-252): without
+   * cosmology all three are (ti_current - ti_old_part) * time_base */
+  double dt_drift, dt_kick_hydro, dt_therm;
+  float minimal_internal_energy; /* hydro_props->minimal_internal_energy */
+  int32_t init_particles;        /* 1: hydro_init_part of the active particles */
+} swiftgpu_drift_args;
+
+int swiftgpu_upload_xparts(swiftgpu_t *h, const swiftgpu_xpart_layout *layout,
+                           const void *xparts_aos, int64_t nparts);
+int swiftgpu_download_xparts(swiftgpu_t *h, void *xparts_aos, int64_t nparts);
+int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args);
+
 /* Per-particle directed interaction counts of the last density / gradient /
  * force loops (the reference's N_density/N_gradient/N_force debugging counters,
  * hydro/SPHENIX/hydro_iact.h:121-126, minus the self term). Any pointer may be

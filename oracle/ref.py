@@ -39,6 +39,10 @@ def load(variant):
         lib.swiftref_get_sort.argtypes = [VP, C.c_int, C.c_int, VP, VP]
         lib.swiftref_get_timesteps.argtypes = [VP, VP]
         lib.swiftref_layout.argtypes = [C.POINTER(abi.PartLayout)]
+        lib.swiftref_xpart_layout.argtypes = [C.POINTER(abi.XpartLayout)]
+        lib.swiftref_set_xparts.argtypes = [VP, VP]
+        lib.swiftref_get_xparts.argtypes = [VP, VP]
+        lib.swiftref_run_drift.argtypes = [VP, C.c_longlong, C.c_float, C.c_int]
         _libs[variant] = lib
     return _libs[variant]
 
@@ -95,6 +99,23 @@ class Reference:
         dt = np.zeros(self.nparts, np.float32)
         self.lib.swiftref_get_timesteps(self.h, dt.ctypes.data)
         return dt
+
+    def xpart_layout(self):
+        X = abi.XpartLayout()
+        self.lib.swiftref_xpart_layout(C.byref(X))
+        return X
+
+    def set_xparts(self, xparts_u8):
+        self.lib.swiftref_set_xparts(self.h, xparts_u8.ctypes.data)
+
+    def xparts(self):
+        out = np.zeros(self.nparts * self.xpart_layout().size, dtype=np.uint8)
+        self.lib.swiftref_get_xparts(self.h, out.ctypes.data)
+        return out
+
+    def drift(self, ti_old, minimal_internal_energy=0.0, init_particles=1):
+        """The reference's cell_drift_part on every local top-level cell, from ti_old to ti_current."""
+        self.lib.swiftref_run_drift(self.h, int(ti_old), float(minimal_internal_energy), int(init_particles))
 
     def sort(self, cell, sid):
         n = int(self._cells["count"][cell])

@@ -626,8 +626,40 @@ int swiftref_get_cells(swiftref_t *s, swiftgpu_cell *cells) {
   for (int i = 0; i < s->ncells; i++) {
     cells[i].h_max = s->cells[i].hydro.h_max;
     cells[i].h_max_active = s->cells[i].hydro.h_max_active;
+    cells[i].dx_max_part = s->cells[i].hydro.dx_max_part;
     cells[i].dx_max_sort = s->cells[i].hydro.dx_max_sort;
     cells[i].dx_max_sort_old = s->cells[i].hydro.dx_max_sort_old;
+  }
+  return 0;
+}
+
+/* ---- drift: the reference's own cell_drift_part ---- */
+
+/* offsetof() table of this build's struct xpart in swiftgpu_xpart_layout order. */
+void swiftref_xpart_layout(swiftgpu_xpart_layout *X) {
+  X->size = (int)sizeof(struct xpart);
+  X->x_diff = (int)offsetof(struct xpart, x_diff);
+  X->x_diff_sort = (int)offsetof(struct xpart, x_diff_sort);
+  X->v_full = (int)offsetof(struct xpart, v_full);
+}
+int swiftref_set_xparts(swiftref_t *s, const void *xparts_aos) {
+  memcpy(s->xparts, xparts_aos, s->nparts * sizeof(struct xpart));
+  return 0;
+}
+int swiftref_get_xparts(swiftref_t *s, void *xparts_aos) {
+  memcpy(xparts_aos, s->xparts, s->nparts * sizeof(struct xpart));
+  return 0;
+}
+/* cell_drift_part(c, e, force = 1, init_particles, NULL) on every local top-level cell
+ * (engine_drift.c:83), all cells drifted from ti_old to the step's ti_current. */
+int swiftref_run_drift(swiftref_t *s, long long ti_old, float minimal_internal_energy,
+                       int init_particles) {
+  s->hp.minimal_internal_energy = minimal_internal_energy;
+  for (int i = 0; i < s->ncells; i++) s->cells[i].hydro.ti_old_part = ti_old;
+  for (int a = 0; a < s->ntop; a++) {
+    struct cell *c = &s->cells[s->top[a]];
+    if (c->nodeID != s->cfg.rank) continue;
+    cell_drift_part(c, &s->engine, /*force=*/1, init_particles, /*replication_list=*/NULL);
   }
   return 0;
 }

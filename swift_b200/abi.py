@@ -67,6 +67,15 @@ class Step(C.Structure):
     ]
 
 
+class XpartLayout(C.Structure):
+    _fields_ = [("size", C.c_int32), ("x_diff", C.c_int32), ("x_diff_sort", C.c_int32), ("v_full", C.c_int32)]
+
+
+class DriftArgs(C.Structure):
+    _fields_ = [("dt_drift", C.c_double), ("dt_kick_hydro", C.c_double), ("dt_therm", C.c_double),
+                ("minimal_internal_energy", C.c_float), ("init_particles", C.c_int32)]
+
+
 class Cell(C.Structure):
     _fields_ = [
         ("loc", C.c_double * 3), ("width", C.c_double * 3),
@@ -139,6 +148,9 @@ EXPORTS = [
     ("swiftgpu_download_cells", C.c_int, [VP, VP, I32]),
     ("swiftgpu_download_counts", C.c_int, [VP, VP, VP, VP, I64]),
     ("swiftgpu_download_timestep", C.c_int, [VP, VP, I64]),
+    ("swiftgpu_upload_xparts", C.c_int, [VP, C.POINTER(XpartLayout), VP, I64]),
+    ("swiftgpu_download_xparts", C.c_int, [VP, VP, I64]),
+    ("swiftgpu_run_drift", C.c_int, [VP, C.POINTER(DriftArgs)]),
     ("swiftgpu_get_stats", C.c_int, [VP, C.POINTER(Stats)]),
     ("swiftgpu_download_sort", C.c_int, [VP, I32, I32, VP, VP, VP]),
     ("swiftgpu_worklist_stats", C.c_int, [C.POINTER(Config), C.POINTER(Step), VP, I32, VP, I32, C.c_int, VP]),

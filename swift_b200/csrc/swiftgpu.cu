@@ -104,6 +104,9 @@ struct swiftgpu_handle {
   uint8_t *d_loop1_bits = nullptr, *d_grad_bits = nullptr;
   bool gradient_own = false; /* L_gradient was rebuilt after the ghost (else the density list is used) */
   char *d_aos = nullptr;
+  char *d_xaos = nullptr; /* device copy of the caller's struct xpart[] (drift) */
+  swiftgpu_xpart_layout xlayout = {0, 0, 0, 0};
+  int64_t n_x = 0;
   size_t aos_bytes = 0;
   double *x = nullptr;
   float4 *mv = nullptr, *dA = nullptr, *dB = nullptr, *fq1 = nullptr, *fq2 = nullptr, *fq3 = nullptr,
@@ -194,6 +197,7 @@ static thread_local std::string g_err;
 
 #include "kernels_records.cuh"
 #include "kernels_finalise.cuh"
+#include "kernels_drift.cuh"
 
 /* ======================================================================== */
 /* Host side                                                                 */
@@ -295,6 +299,9 @@ extern "C" int swiftgpu_init(swiftgpu_t **out, const swiftgpu_config *cfg) {
 }
 
 static void free_parts(H *h) {
+  cudaFree(h->d_xaos);
+  h->d_xaos = nullptr;
+  h->n_x = 0;
   cudaFree(h->d_aos); cudaFree(h->x); cudaFree(h->mv); cudaFree(h->dA); cudaFree(h->dB);
   cudaFree(h->fq1); cudaFree(h->fq2); cudaFree(h->fq3); cudaFree(h->fo1); cudaFree(h->hh);
   cudaFree(h->u); cudaFree(h->rho); cudaFree(h->f_hdt); cudaFree(h->f_vsig); cudaFree(h->g_vsig);
@@ -1612,6 +1619,8 @@ extern "C" int swiftgpu_run_step(swiftgpu_t *h, uint32_t mask) {
 }
 
 static int transpose_out(H *h) {
+  /* nothing ran since the particles were transposed in (or drifted): the AoS copy is current */
+  if (!(h->phases_done & SWIFTGPU_PHASE_DENSITY)) return 0;
   DevLayout D;
   D.L = h->cfg.layout;
   D.scheme = h->cfg.scheme;
@@ -1661,8 +1670,102 @@ extern "C" int swiftgpu_download_cells(swiftgpu_t *h, swiftgpu_cell *cells, int3
   for (int c = 0; c < ncells; c++) {
     cells[c].h_max = hm[c];
     cells[c].h_max_active = hma[c];
+    cells[c].dx_max_part = h->cells[c].dx_max_part; /* as the last drift left them */
+    cells[c].dx_max_sort = h->cells[c].dx_max_sort;
   }
   return 0;
+}
+
+/* ---- drift on the device (kernels_drift.cuh) ---- */
+extern "C" int swiftgpu_upload_xparts(swiftgpu_t *h, const swiftgpu_xpart_layout *layout, const void *xparts_aos,
+                                      int64_t nparts) {
+  if (!h || !layout || !xparts_aos || nparts <= 0) return 1;
+  cudaSetDevice(h->cfg.device);
+  const int64_t nh = h->n_host > 0 ? h->n_host : h->n;
+  if (nparts != nh) return h->fail("upload_xparts: one xpart per uploaded part (upload the parts first)");
+  if (layout->size <= 0 || layout->x_diff < 0 || layout->x_diff_sort < 0 || layout->v_full < 0 ||
+      layout->x_diff + 12 > layout->size || layout->x_diff_sort + 12 > layout->size ||
+      layout->v_full + 12 > layout->size)
+    return h->fail("upload_xparts: bad struct xpart layout");
+  if (h->n_x != nparts || h->xlayout.size != layout->size) {
+    cudaFree(h->d_xaos);
+    h->d_xaos = nullptr;
+    CK(cudaMalloc((void **)&h->d_xaos, (size_t)layout->size * (size_t)nparts));
+    h->n_x = nparts;
+  }
+  h->xlayout = *layout;
+  CK(cudaMemcpyAsync(h->d_xaos, xparts_aos, (size_t)layout->size * (size_t)nparts, cudaMemcpyHostToDevice,
+                     h->stream));
+  return 0;
+}
+
+extern "C" int swiftgpu_download_xparts(swiftgpu_t *h, void *xparts_aos, int64_t nparts) {
+  if (!h || !xparts_aos || nparts != h->n_x || !h->d_xaos) return 1;
+  cudaSetDevice(h->cfg.device);
+  CK(cudaMemcpyAsync(xparts_aos, h->d_xaos, (size_t)h->xlayout.size * (size_t)nparts, cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.n_host_syncs++;
+  return 0;
+}
+
+extern "C" int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args) {
+  if (!h || !args) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (!h->d_xaos) return h->fail("run_drift before upload_xparts");
+  if (!(args->dt_drift >= 0.)) return h->fail("run_drift: attempt to drift to the past");
+  if (ensure_lists(h)) return 1; /* the device cell table */
+  if (transpose_out(h)) return 1; /* a_hydro, h_dt, u_dt ... of the last step into the AoS copy */
+  DriftArgs A;
+  A.aos = h->d_aos;
+  A.xaos = h->d_xaos;
+  A.D.L = h->cfg.layout;
+  A.D.scheme = h->cfg.scheme;
+  A.X = h->xlayout;
+  A.cells = h->d_cells;
+  A.ncells = h->ncells;
+  A.d2h = h->d_d2h;
+  A.dt_drift = args->dt_drift;
+  A.dt_kick_hydro = args->dt_kick_hydro;
+  A.dt_therm = args->dt_therm;
+  A.min_u = args->minimal_internal_energy; /* / cosmo->a_factor_internal_energy = 1 */
+  A.h_max = h->cfg.h_max;
+  A.h_min = h->cfg.h_min;
+  A.init_particles = args->init_particles;
+  A.max_active_bin = h->step.max_active_bin;
+  A.n_host = h->n_x;
+  const int nc = h->ncells;
+  k_drift_begin<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_cells, nc);
+  const unsigned grid = (unsigned)(((int64_t)nc * 32 + 127) / 128);
+  if (h->cfg.scheme == SCH_MINIMAL) k_drift<SCH_MINIMAL><<<grid, 128, 0, h->stream>>>(A);
+  else if (h->cfg.scheme == SCH_GADGET2) k_drift<SCH_GADGET2><<<grid, 128, 0, h->stream>>>(A);
+  else k_drift<SCH_SPHENIX><<<grid, 128, 0, h->stream>>>(A);
+  float *d_tmp = nullptr;
+  CK(cudaMalloc((void **)&d_tmp, 4 * sizeof(float) * (size_t)nc));
+  k_get_cell_drift<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_cells, nc, d_tmp);
+  h->stats.n_launches += 3;
+  std::vector<float> v(4 * (size_t)nc);
+  cudaError_t e = cudaMemcpyAsync(v.data(), d_tmp, sizeof(float) * v.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_tmp);
+  if (e != cudaSuccess) return h->fail(cudaGetErrorString(e));
+  h->stats.n_host_syncs++;
+  /* the host mirror of the cells follows (the worklists' recursion predicates read h_max and
+   * dx_max_part, cell.h:951-1007): lists and cell table are rebuilt at the next phase */
+  for (int c = 0; c < nc; c++) {
+    swiftgpu_cell &C = h->cells[c];
+    if (C.nodeID != h->cfg.rank && h->cfg.nranks > 1) continue;
+    if (C.count == 0) continue;
+    C.h_max = v[c];
+    C.h_max_active = v[(size_t)nc + c];
+    C.dx_max_part = v[2 * (size_t)nc + c];
+    C.dx_max_sort = v[3 * (size_t)nc + c];
+    h->up_hmax[c] = C.h_max;
+    h->up_hmax_active[c] = C.h_max_active;
+  }
+  h->lists_built = false;
+  /* device order, SoA columns, frames: from the drifted AoS copy */
+  return transpose_in(h);
 }
 
 extern "C" int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density, int32_t *n_gradient,

@@ -130,6 +130,27 @@ class SwiftGPU:
         self._ck(self.lib.swiftgpu_download_timestep(self.h, dt.ctypes.data, self.nparts), "download_timestep")
         return dt
 
+    # ---- drift on the device ----
+    def upload_xparts(self, xlayout, xparts_u8):
+        """struct xpart[] of the caller (one per uploaded part), layout = offsetof() of x_diff, x_diff_sort, v_full."""
+        xparts_u8 = np.ascontiguousarray(xparts_u8, dtype=np.uint8)
+        self._xlayout = xlayout
+        self._nx = xparts_u8.size // xlayout.size
+        self._ck(self.lib.swiftgpu_upload_xparts(self.h, C.byref(xlayout), xparts_u8.ctypes.data, self._nx),
+                 "upload_xparts")
+
+    def download_xparts(self):
+        out = np.zeros(self._nx * self._xlayout.size, dtype=np.uint8)
+        self._ck(self.lib.swiftgpu_download_xparts(self.h, out.ctypes.data, self._nx), "download_xparts")
+        return out
+
+    def run_drift(self, dt_drift, dt_kick_hydro=None, dt_therm=None, minimal_internal_energy=0.0, init_particles=1):
+        """cell_drift_part (force = 1) over every local cell; the three factors as cell_drift.c:236-252 derives them."""
+        a = abi.DriftArgs(float(dt_drift), float(dt_drift if dt_kick_hydro is None else dt_kick_hydro),
+                          float(dt_drift if dt_therm is None else dt_therm), float(minimal_internal_energy),
+                          int(init_particles))
+        self._ck(self.lib.swiftgpu_run_drift(self.h, C.byref(a)), "run_drift")
+
     def download_counts(self):
         nd = np.zeros(self.nparts, np.int32)
         ng = np.zeros_like(nd)
