@@ -412,12 +412,17 @@ def test_drift_matches_reference(scheme, active_fraction):
     moved = np.abs(host.field(want, c.layout, "x") - host.field(c.parts, c.layout, "x")).max()
     assert moved > 1e-5, "the drift did not move anything"
     ent = "entropy" if scheme == "gadget2" else "u"
-    exact = ["x", "v", "h", "rho", "depth_h", ent, "wcount", "wcount_dh", "rho_dh", "rot_v"]
-    for name in exact:
-        a, b = host.field(got, c.layout, name), host.field(want, c.layout, name)
-        assert np.array_equal(a, b), f"{name}: {(a != b).sum()} values differ"
     tb = host.field(c.parts, c.layout, "time_bin")
     inactive = tb > mab
+    for name in ["x", "v", "h", "rho", "depth_h", ent]:
+        a, b = host.field(got, c.layout, name), host.field(want, c.layout, name)
+        assert np.array_equal(a, b), f"{name}: {(a != b).sum()} values differ"
+    for name in ["wcount", "wcount_dh", "rho_dh", "rot_v"]:
+        # hydro_init_part of the ACTIVE particles (in the inactive ones these members alias the
+        # predicted force members, compared below)
+        a, b = host.field(got, c.layout, name), host.field(want, c.layout, name)
+        a, b = a.reshape(n, -1)[~inactive], b.reshape(n, -1)[~inactive]
+        assert np.array_equal(a, b) and not a.any(), name
     close = ["soundspeed", "v_sig", "P_over_rho2" if scheme == "gadget2" else "pressure"]
     for name in close:
         # hydro_init_part zeroes the density members, which share storage with the force members:
