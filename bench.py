@@ -397,6 +397,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-halo-parity", action="store_true")
+    ap.add_argument("--no-resident", action="store_true", help="skip the device-resident drift + step leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (and its pinned host copies): memory-bound configurations")
     args = ap.parse_args()
     if args.workload is None:
@@ -528,6 +529,37 @@ def main():
             f1.record(stream)
             barrier()
             ms_e2e = f0.elapsed_time(f1)
+        # ---- device-resident leg: drift + step without the particles crossing the host boundary ----
+        resident = None
+        if world == 1 and not args.no_resident:
+            X = abi.XpartLayout(48, 0, 12, 24)  # synthetic struct xpart: x_diff, x_diff_sort, v_full + padding
+            xp = np.zeros((n, 48), np.uint8)
+            xp[:, 24:36] = np.ascontiguousarray(host.field(c.parts, c.layout, "v").reshape(n, 3),
+                                                dtype=np.float32).view(np.uint8).reshape(n, 12)
+            g.upload_parts_device(dev_in.data_ptr(), n)
+            g.upload_xparts(X, xp.ravel())
+            del xp
+            dt = 1e-3 / L / 0.05  # a drift of ~1e-3 particle spacings per step (|v| ~ 0.05)
+
+            def step_resident():
+                g.run_drift(dt, init_particles=1)
+                g.run_step(abi.PHASE_ALL)
+            g.run_step(abi.PHASE_ALL)  # a_hydro, h_dt, u_dt to drift with
+            step_resident()
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(args.steps):
+                step_resident()
+            r1.record(stream)
+            barrier()
+            ms_res = r0.elapsed_time(r1) / args.steps
+            rd, rg, rf = g.download_counts()
+            useful_res = int(rd.sum()) + int(rg.sum()) + int(rf.sum())
+            resident = {"value": useful_res / (ms_res * 1e-3), "unit": "interactions/s", "ms_per_step": ms_res,
+                        "interactions_per_step": useful_res,
+                        "what": "swiftgpu_run_drift + swiftgpu_run_step per step on the device-resident state: no "
+                                "particle crosses the host boundary (SURVEY 8f row 2; the kick stays on the host in a real run)"}
         sampler.stop()
 
     # max over ranks
@@ -607,6 +639,8 @@ def main():
     }
     if halo_parity is not None:
         line["halo_parity"] = halo_parity
+    if resident is not None:
+        line["resident"] = resident
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             info, _, _, _ = cpu_reference_run(args.workload, 1, 0)

@@ -166,9 +166,11 @@ __global__ void __launch_bounds__(128) k_drift(const DriftArgs A) {
   }
 }
 
-__global__ void k_get_cell_drift(const DevCell *cells, int ncells, float *out /* 4 x ncells */) {
+__global__ void k_get_cell_drift(const DevCell *cells, int ncells, float *out /* 4 x ncells */,
+                                 float *dx_max_part /* the array k_pred_bits reads */) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncells) return;
+  dx_max_part[c] = cells[c].dx_max_part;
   out[c] = cells[c].h_max;
   out[ncells + c] = cells[c].h_max_active;
   out[2 * ncells + c] = cells[c].dx_max_part;

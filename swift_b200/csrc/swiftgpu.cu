@@ -1742,16 +1742,24 @@ extern "C" int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args
   else k_drift<SCH_SPHENIX><<<grid, 128, 0, h->stream>>>(A);
   float *d_tmp = nullptr;
   CK(cudaMalloc((void **)&d_tmp, 4 * sizeof(float) * (size_t)nc));
-  k_get_cell_drift<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_cells, nc, d_tmp);
-  h->stats.n_launches += 3;
+  k_get_cell_drift<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_cells, nc, d_tmp, h->d_dxp);
+  /* the drifted cell table is the state every following step starts from (run_density restores it) */
+  CK(cudaMemcpyAsync(h->d_cells_init, h->d_cells, sizeof(DevCell) * (size_t)nc, cudaMemcpyDeviceToDevice, h->stream));
+  /* do the worklists survive? the density / subset lists were flattened with the predicates
+   * cell.h:951,992 on h_max_active (the force list is revalidated by run_force in every step) */
+  CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int32_t), h->stream));
+  k_pred_bits<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->d_dmin, h->d_dxp_old, h->d_loop1_bits, nc, 1,
+                                                     h->d_flag);
+  h->stats.n_launches += 4;
   std::vector<float> v(4 * (size_t)nc);
+  int32_t flag = 0;
   cudaError_t e = cudaMemcpyAsync(v.data(), d_tmp, sizeof(float) * v.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, h->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(d_tmp);
   if (e != cudaSuccess) return h->fail(cudaGetErrorString(e));
   h->stats.n_host_syncs++;
-  /* the host mirror of the cells follows (the worklists' recursion predicates read h_max and
-   * dx_max_part, cell.h:951-1007): lists and cell table are rebuilt at the next phase */
+  /* the host mirror of the cells follows: a later list rebuild flattens the recursion with it */
   for (int c = 0; c < nc; c++) {
     swiftgpu_cell &C = h->cells[c];
     if (C.nodeID != h->cfg.rank && h->cfg.nranks > 1) continue;
@@ -1763,7 +1771,7 @@ extern "C" int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args
     h->up_hmax[c] = C.h_max;
     h->up_hmax_active[c] = C.h_max_active;
   }
-  h->lists_built = false;
+  if (flag) h->lists_built = false;
   /* device order, SoA columns, frames: from the drifted AoS copy */
   return transpose_in(h);
 }
