@@ -43,6 +43,7 @@ def load(variant):
         lib.swiftref_set_xparts.argtypes = [VP, VP]
         lib.swiftref_get_xparts.argtypes = [VP, VP]
         lib.swiftref_run_drift.argtypes = [VP, C.c_longlong, C.c_float, C.c_int]
+        lib.swiftref_space_split.argtypes = [C.POINTER(abi.Config), C.POINTER(abi.Step), VP, C.c_longlong, VP, VP, VP, C.c_int]
         _libs[variant] = lib
     return _libs[variant]
 
@@ -51,6 +52,22 @@ def layout(variant):
     L = abi.PartLayout()
     load(variant).swiftref_layout(C.byref(L))
     return L
+
+
+def space_split(variant, cfg, step, parts_u8, loc, width, max_cells=1 << 16):
+    """The reference's space_split_recursive on one top-level cell. Returns (cells, parts re-ordered
+    as the reference's cell_split left them)."""
+    lib = load(variant)
+    parts = np.ascontiguousarray(parts_u8, dtype=np.uint8).copy()
+    n = parts.size // cfg.layout.size
+    loc = np.ascontiguousarray(loc, dtype=np.float64)
+    width = np.ascontiguousarray(width, dtype=np.float64)
+    cells = np.zeros(max_cells, dtype=abi.cell_dtype())
+    nc = lib.swiftref_space_split(C.byref(cfg), C.byref(step), parts.ctypes.data, n, loc.ctypes.data,
+                                  width.ctypes.data, cells.ctypes.data, max_cells)
+    if nc < 0:
+        raise RuntimeError(f"swiftref_space_split failed ({nc})")
+    return cells[:nc].copy(), parts
 
 
 class Reference:

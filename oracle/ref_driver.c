@@ -633,6 +633,110 @@ int swiftref_get_cells(swiftref_t *s, swiftgpu_cell *cells) {
   return 0;
 }
 
+/* ---- the reference's own tree builder (checks swift_b200/csrc/host_tree.cpp) ---- */
+static int emit_subtree(const struct cell *c, const struct part *parts0, int parent, int top,
+                        swiftgpu_cell *out, int max_cells, int *n) {
+  if (*n >= max_cells) return -1;
+  const int me = (*n)++;
+  swiftgpu_cell *g = &out[me];
+  memset(g, 0, sizeof(*g));
+  for (int k = 0; k < 3; k++) {
+    g->loc[k] = c->loc[k];
+    g->width[k] = c->width[k];
+  }
+  g->dmin = c->dmin;
+  g->h_min_allowed = c->h_min_allowed;
+  g->h_max_allowed = c->h_max_allowed;
+  g->h_max = c->hydro.h_max;
+  g->h_max_active = c->hydro.h_max_active;
+  g->depth = c->depth;
+  g->split = c->split;
+  g->parent = parent;
+  g->top = top;
+  g->nodeID = c->nodeID;
+  g->count = c->hydro.count;
+  g->first_part = (long long)(c->hydro.parts - parts0);
+  g->ti_end_min = c->hydro.ti_end_min;
+  for (int k = 0; k < 8; k++) {
+    g->progeny[k] = -1;
+    if (c->split && c->progeny[k] != NULL) {
+      g->progeny[k] = *n;
+      if (emit_subtree(c->progeny[k], parts0, me, top, out, max_cells, n) < 0) return -1;
+    }
+  }
+  return me;
+}
+
+/* space_split_recursive (src/space_split.c:53; cell_split src/cell_split.c) on ONE top-level cell
+ * [loc, loc + width) holding parts_aos[0..n), set up as space_regrid does (space_regrid.c:300-330).
+ * The particles are re-ordered in place by the reference's cell_split; the subtree comes back in
+ * depth-first pre-order (progeny 0..7), indices relative to this subtree, first_part relative to
+ * parts_aos[0]. Returns the number of cells, or -1 if max_cells is too small. */
+int swiftref_space_split(const swiftgpu_config *cfg, const swiftgpu_step *step, void *parts_aos,
+                         long long n, const double loc[3], const double width[3],
+                         swiftgpu_cell *out, int max_cells) {
+  if (cfg->scheme != SWIFTREF_SCHEME || cfg->layout.size != (int)sizeof(struct part)) return -2;
+  struct space *s = (struct space *)calloc(1, sizeof(struct space));
+  struct engine *e = (struct engine *)calloc(1, sizeof(struct engine));
+  struct part *parts = NULL;
+  struct xpart *xparts = NULL;
+  if (posix_memalign((void **)&parts, part_align, (n + 1) * sizeof(struct part)) != 0) return -2;
+  if (posix_memalign((void **)&xparts, xpart_align, (n + 1) * sizeof(struct xpart)) != 0) return -2;
+  memcpy(parts, parts_aos, n * sizeof(struct part));
+  bzero(xparts, (n + 1) * sizeof(struct xpart));
+  for (long long k = 0; k < n; k++) parts[k].gpart = NULL;
+  e->ti_current = step->ti_current;
+  e->max_active_bin = step->max_active_bin;
+  e->time_base = step->time_base;
+  e->policy = engine_policy_hydro;
+  e->s = s;
+  s->e = e;
+  s->periodic = cfg->periodic;
+  for (int k = 0; k < 3; k++) s->dim[k] = cfg->dim[k];
+  s->parts = parts;
+  s->xparts = xparts;
+  s->nr_parts = n;
+  s->with_self_gravity = 0;
+  s->cells_sub = (struct cell **)calloc(4, sizeof(struct cell *));
+  s->multipoles_sub = (struct gravity_tensors **)calloc(4, sizeof(struct gravity_tensors *));
+  lock_init(&s->lock);
+  struct cell *c = NULL;
+  if (posix_memalign((void **)&c, cell_align, sizeof(struct cell)) != 0) return -2;
+  bzero(c, sizeof(struct cell));
+  for (int k = 0; k < 3; k++) {
+    c->loc[k] = loc[k];
+    c->width[k] = width[k];
+  }
+  c->dmin = (float)fmin(width[0], fmin(width[1], width[2]));
+  c->h_min_allowed = c->dmin * 0.5 * (1. / kernel_gamma);
+  c->h_max_allowed = c->dmin * (1. / kernel_gamma);
+  c->depth = 0;
+  c->split = 0;
+  c->hydro.count = (int)n;
+  c->hydro.count_total = (int)n;
+  c->hydro.parts = parts;
+  c->hydro.xparts = xparts;
+  c->hydro.ti_old_part = step->ti_current;
+  c->nodeID = cfg->rank;
+  c->parent = NULL;
+  c->top = c;
+  c->super = c;
+  c->hydro.super = c;
+  lock_init(&c->hydro.lock);
+  space_split_recursive(s, c, NULL, NULL, NULL, NULL, NULL, /*tpid=*/0);
+  int nc = 0;
+  const int r = emit_subtree(c, parts, -1, 0, out, max_cells, &nc);
+  memcpy(parts_aos, parts, n * sizeof(struct part));
+  free(parts);
+  free(xparts);
+  free(c); /* the progeny live in the space's cell chunks (swift_ignore_leak'ed by the reference) */
+  free(s->multipoles_sub);
+  free(s->cells_sub);
+  free(s);
+  free(e);
+  return r < 0 ? -1 : nc;
+}
+
 /* ---- drift: the reference's own cell_drift_part ---- */
 
 /* offsetof() table of this build's struct xpart in swiftgpu_xpart_layout order. */

@@ -221,3 +221,64 @@ def test_reference_flips_under_leaf_permutation(scheme, L):
     assert rep["flips"] <= 3 + int(4 * util.REF_FLIP_RATE * rep["n"])
     assert abs(rep["flip_max"] - 1e-4) < 2e-6  # a flip is exactly one accepted-vs-repeated Newton step at the tolerance
     util.assert_parity(rep, tol=5e-6)
+
+
+@pytest.mark.parametrize("gen", ("jittered", "clustered", "active"))
+def test_host_tree_matches_reference_space_split(gen):
+    """The tree both arms of every parity test are fed comes from the repo's
+    swift_b200/csrc/host_tree.cpp. Here the REFERENCE builds it: space_split_recursive
+    (src/space_split.c:53) + cell_split on every top-level cell, set up as space_regrid does.
+    Geometry, depth, split flags, counts, particle ranges, h limits, h_max, h_max_active, ti_end_min
+    must be identical cell by cell, every cell must hold the same SET of particles, and every
+    particle the same depth_h (cell_set_part_h_depth)."""
+    if not ref.available("sphenix"):
+        pytest.skip("needs oracle/_ref")
+    scheme = "sphenix"
+    if gen == "clustered":
+        ic = host.clustered_box(32, abi.SCHEME_SPHENIX, seed=9, sigma=2.0)
+        cdim = (2, 2, 2)
+    else:
+        ic = host.jittered_box(24, abi.SCHEME_SPHENIX, jitter=0.3, h_scatter=0.2, seed=4,
+                               active_fraction=0.3 if gen == "active" else 1.0)
+        cdim = (2, 2, 2)
+    c = util.make_case(scheme, ic, cdim, max_active_bin=1 if gen == "active" else 56)
+    cells, size = c.tree.cells, c.layout.size
+    rows = c.parts.reshape(-1, size)
+    ncompared = 0
+    max_depth = 0
+    for t in c.tree.top:
+        T = cells[t]
+        f, n = int(T["first_part"]), int(T["count"])
+        if n == 0:
+            continue
+        # hand the reference the top-level cell's particles in a scrambled order
+        rng = np.random.default_rng(int(t))
+        sub = rows[f:f + n][rng.permutation(n)].copy()
+        rcells, rparts = ref.space_split(scheme, c.cfg, c.step, sub.ravel(), T["loc"], T["width"])
+        rrows = rparts.reshape(-1, size)
+        # walk both trees together (pre-order, progeny 0..7)
+        stack = [(int(t), 0)]
+        while stack:
+            a, b = stack.pop()
+            A, B = cells[a], rcells[b]
+            for name in ("loc", "width", "dmin", "h_min_allowed", "h_max_allowed", "h_max", "h_max_active",
+                         "depth", "split", "count", "ti_end_min"):
+                assert np.array_equal(A[name], B[name]), (name, a, b, A[name], B[name])
+            assert int(A["first_part"]) - f == int(B["first_part"]), "particle range"
+            ia = np.sort(host.field(rows[int(A["first_part"]):int(A["first_part"]) + int(A["count"])].ravel(), c.layout, "id"))
+            ib = np.sort(host.field(rrows[int(B["first_part"]):int(B["first_part"]) + int(B["count"])].ravel(), c.layout, "id"))
+            assert np.array_equal(ia, ib), "a cell holds different particles"
+            max_depth = max(max_depth, int(A["depth"]))
+            ncompared += 1
+            for k in range(8):
+                pa, pb = int(A["progeny"][k]), int(B["progeny"][k])
+                assert (pa < 0) == (pb < 0), "progeny slot"
+                if pa >= 0:
+                    stack.append((pa, pb))
+        # depth_h per particle id
+        da = dict(zip(host.field(rows[f:f + n].ravel(), c.layout, "id").tolist(),
+                      host.field(rows[f:f + n].ravel(), c.layout, "depth_h").tolist()))
+        db = dict(zip(host.field(rrows.ravel(), c.layout, "id").tolist(),
+                      host.field(rrows.ravel(), c.layout, "depth_h").tolist()))
+        assert da == db, "depth_h differs"
+    assert ncompared > len(c.tree.top) and max_depth >= (2 if gen == "clustered" else 1)
