@@ -403,18 +403,25 @@ __global__ void __launch_bounds__(128)
                 const DevCell *cells, const int32_t *tgt_first, const int32_t *tgt_count,
                 const int32_t *tgt_list, const double *xs0, const double *xs1, const double *xs2,
                 const float *h, TaskRec *recs, unsigned int *ntask_dev, const unsigned long long *gate,
-                unsigned long long gate_lo, unsigned long long gate_hi) {
+                unsigned long long gate_lo, unsigned long long gate_hi, int chunk /* targets per task */,
+                const unsigned long long *gate_den) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= ntasks) return;
   /* ghost re-runs: this launch only if the number of unconverged particles (a device counter the
    * host never reads in between) is in [gate_lo, gate_hi) - else the other kernel takes the pass */
-  if (gate && (*gate < gate_lo || *gate >= gate_hi)) return;
+  if (gate) {
+    /* with gate_den the bounds are per unit of *gate_den (targets per 64-target chunk of the list) */
+    const unsigned long long v = *gate, den = gate_den ? *gate_den : 1ull;
+    if (v < gate_lo * den) return;
+    if (gate_hi != ~0ull && v >= gate_hi * den) return;
+  }
   const int g = task_group[w];
   const int nt = tgt_count[g];
-  const int t0 = task_chunk[w] * PL_TARGETS;
+  /* the host's task list is cut for the smallest task size; a launch with larger tasks uses its head */
+  const int t0 = task_chunk[w] * chunk;
   if (t0 >= nt) return;
-  const int n = min(PL_TARGETS, nt - t0);
+  const int n = min(chunk, nt - t0);
   const Group G = groups[g];
   const DevCell C = cells[G.tcell];
   const int off = tgt_first[g] + t0;

@@ -65,7 +65,10 @@ namespace swiftgpu {
 #endif
 #define PL_OCT (PL_SLOTS / 8)
 #define PL_FRAGS 8 /* fragments (items) per stage */
-#define PL_TARGETS 64 /* targets of a task (host task list chunk = TASK_TARGETS) */
+#define PL_TARGETS 64 /* targets of a task of the 8-warp kernel (8 per consumer warp) */
+#ifndef PL_SPARSE_CW
+#define PL_SPARSE_CW 4 /* consumer warps of the variant for sparse target sets: tasks of 8 * PL_SPARSE_CW targets */
+#endif
 #define PL_PRE_REL2 1.00002f /* relative widening of a prefilter limit r^2 (double modes) */
 
 /* One task = up to 64 targets of one group. Built on the device after the
@@ -123,16 +126,15 @@ enum { PM_NFR = 0, PM_NOCT = 1, PM_FLAG = 2, PM_TASK = 3, PM_TGT_OFF = 4, PM_NTG
 /* force payload lane of the exact hj^2 gamma^2 of the source (k_ghost / k_aos_to_soa keep it there) */
 #define PL_HG2_COL(SCHEME) ((SCHEME) == SCH_SPHENIX ? 3 : 2)
 
-#define PL_MIN_BLOCKS(LOOP) 2
+#define PL_MIN_BLOCKS(CW) ((CW) >= 8 ? 2 : 4)
 
 template <int LOOP, int SCHEME, int NS, int CW, int DS>
-__global__ void __launch_bounds__(32 * (CW + 1), 2) k_pipe(const LoopArgs A) {
+__global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const LoopArgs A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
   constexpr int QCAP = FORCE ? TL_SUBCAP2 : TL_SUBCAP1;
   typedef PipeSmem<NP, NS, QCAP, CW, DS> SM;
-  constexpr int CTA_TGT = 8 * CW;
-  static_assert(CW == 8, "a task is 64 targets: 8 consumer warps");
+  static_assert(CW >= 1 && CW <= 8, "a task is 8 * CW targets");
   extern __shared__ __align__(128) char smem_pl[];
   char *const smem = smem_pl;
   uint16_t *const sList = (uint16_t *)(smem + SM::kList);

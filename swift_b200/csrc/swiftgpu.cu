@@ -451,6 +451,10 @@ static uint32_t frame_of(H *h, const Item &it) {
   return F.off;
 }
 
+static int loop_kind();
+/* targets per entry of the host task list: the frame pipeline has a variant with small tasks for
+ * sparse target sets and cuts the list for it (k_task_recs of a launch with larger tasks uses its head) */
+static int task_list_chunk() { return loop_kind() == 3 ? 8 * PL_SPARSE_CW : TASK_TARGETS; }
 static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
   D.release();
   D.ngroups = (int)W.groups.size();
@@ -470,7 +474,8 @@ static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
   }
   for (int32_t g : order) {
     const swiftgpu_cell &c = h->cells[W.groups[g].tcell];
-    const int nch = (c.count + TASK_TARGETS - 1) / TASK_TARGETS;
+    const int tt = task_list_chunk();
+    const int nch = (c.count + tt - 1) / tt;
     for (int k = 0; k < nch; k++) {
       tg.push_back(g);
       tc.push_back(k);
@@ -1069,15 +1074,16 @@ static int build_targets(H *h, DevList &D, bool *sparse_out = nullptr) {
 
 /* The compacted TaskRecs of one launch of the frame pipeline, from the target lists as they are NOW
  * (no host round trip: the kernel reads the number of tasks from device memory). */
-static int build_task_recs(H *h, const DevList &D, const unsigned long long *gate = nullptr,
-                           unsigned long long gate_lo = 0, unsigned long long gate_hi = ~0ull) {
+static int build_task_recs(H *h, const DevList &D, int chunk, const unsigned long long *gate = nullptr,
+                           unsigned long long gate_lo = 0, unsigned long long gate_hi = ~0ull,
+                           const unsigned long long *gate_den = nullptr) {
   CK(cudaMemsetAsync(h->d_counters + 15, 0, sizeof(unsigned long long), h->stream));
   if (D.ntasks == 0) return 0;
   const int64_t n = h->n;
   k_task_recs<<<(unsigned)(((int64_t)D.ntasks * 32 + 127) / 128), 128, 0, h->stream>>>(
       D.task_group, D.task_chunk, D.ntasks, D.groups, h->d_cells, D.tgt_first, D.tgt_count, D.tgt_list, h->xs,
       h->xs + (n + 4), h->xs + 2 * (n + 4), h->hh, D.task_recs, (unsigned int *)(h->d_counters + 15), gate, gate_lo,
-      gate_hi);
+      gate_hi, chunk, gate_den);
   h->stats.n_launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1181,11 +1187,10 @@ static int launch_direct_density(H *h, const DevList &D, const LoopArgs &A, cons
 
 /* frame pipeline (loops_pipe.cuh): DS = double-column slots per stage (64: only the self item of a
  * main loop is evaluated on doubles; 256: the ghost re-runs, where every pair item is) */
-template <int LOOP, int SCHEME, int NS, int DS>
+template <int LOOP, int SCHEME, int NS, int DS, int CW = 8>
 static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  constexpr int CW = 8;
   constexpr int bytes = PipeSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1), CW, DS>::kBytes;
   static bool configured = false;
   if (!configured) {
@@ -1204,7 +1209,7 @@ static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
     if (e != cudaSuccess) return e;
     resident = std::max(1, per_sm) * std::max(1, sms);
     if (getenv("SWIFTGPU_VERBOSE"))
-      fprintf(stderr, "k_pipe<%d,%d,NS=%d,DS=%d>: %d B smem, %d CTAs/SM\n", LOOP, SCHEME, NS, DS, bytes, per_sm);
+      fprintf(stderr, "k_pipe<%d,%d,NS=%d,CW=%d,DS=%d>: %d B smem, %d CTAs/SM\n", LOOP, SCHEME, NS, CW, DS, bytes, per_sm);
   }
   const int grid = (int)std::min<long long>(A.ntasks, resident);
   if (grid <= 0) return cudaSuccess;
@@ -1223,13 +1228,68 @@ static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
 #define PL_NS_FORCE 4
 #define PL_NS_FORCE_SPHENIX 3
 #endif
+#ifndef PL_NS_SPARSE
+/* the small-task variant (PL_SPARSE_CW consumer warps): 3-4 CTAs per SM */
+#define PL_NS_SPARSE 3
+#define PL_NS_SPARSE_FORCE 2
+#endif
+/* small = the variant with tasks of 8 * PL_SPARSE_CW targets: per task every consumer warp walks all
+ * stages of the group's sources whatever the number of its targets, so a sparse target set (ghost
+ * re-runs, few active particles) is served by fewer warps per task and more tasks in flight */
 template <int LOOP, bool SUBSET, int SCHEME>
-static cudaError_t launch_pipe(H *h, const LoopArgs &A) {
+static cudaError_t launch_pipe(H *h, const LoopArgs &A, bool small = false) {
+  if (small) {
+    if (LOOP == LOOP_FORCE) return launch_pipe_ns<LOOP_FORCE, SCHEME, PL_NS_SPARSE_FORCE, 64, PL_SPARSE_CW>(h, A);
+    if (LOOP == LOOP_GRADIENT) return launch_pipe_ns<LOOP_GRADIENT, 0, PL_NS_SPARSE, 64, PL_SPARSE_CW>(h, A);
+    if (SUBSET) return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SPARSE, 256, PL_SPARSE_CW>(h, A);
+    return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SPARSE, 64, PL_SPARSE_CW>(h, A);
+  }
   if (LOOP == LOOP_FORCE)
     return launch_pipe_ns<LOOP_FORCE, SCHEME, (SCHEME == SCH_SPHENIX ? PL_NS_FORCE_SPHENIX : PL_NS_FORCE), 64>(h, A);
   if (LOOP == LOOP_GRADIENT) return launch_pipe_ns<LOOP_GRADIENT, 0, PL_NS_GRADIENT, 64>(h, A);
   if (SUBSET) return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SUBSET, 256>(h, A);
   return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_DENSITY, 64>(h, A);
+}
+/* Fraction of a list's potential targets below which the small-task variant takes the launch
+ * (SWIFTGPU_SPARSE_FRAC, A/B knob; 0 = never, > 1 = always). The choice is made ON THE DEVICE: both
+ * variants are enqueued, k_task_recs of the one whose gate is closed emits no task. */
+static double sparse_frac() {
+  static double v = -1.;
+  if (v < 0.) {
+    const char *e = getenv("SWIFTGPU_SPARSE_FRAC");
+    v = e ? atof(e) : 0.4;
+  }
+  return v;
+}
+
+/* One neighbour loop of the frame pipeline over the targets list D holds NOW. Both task sizes are
+ * enqueued; which one finds tasks is decided on the device: `gate` (targets of the list, or
+ * unconverged particles) in [lo, split) -> small tasks, [split, inf) -> 64-target tasks; below lo the
+ * caller's direct kernel. With `den` the bounds are per 64-target chunk (the mean fill of the tasks). */
+template <int LOOP, bool SUBSET, int SCHEME>
+static int run_pipe_loop(H *h, DevList &D, int32_t *counts, int counter_slot, const unsigned long long *gate,
+                         unsigned long long lo, unsigned long long split, const unsigned long long *den) {
+  if (ensure_frames(h)) return 1;
+  if (split != ~0ull) {
+    if (build_task_recs(h, D, PL_TARGETS, gate, std::max(lo, split), ~0ull, den)) return 1;
+    LoopArgs A = loop_args(h, D, counts, counter_slot);
+    CK((launch_pipe<LOOP, SUBSET, SCHEME>(h, A, false)));
+    h->stats.n_launches++;
+  }
+  if (split > lo) {
+    if (build_task_recs(h, D, 8 * PL_SPARSE_CW, gate, lo, split, den)) return 1;
+    LoopArgs A = loop_args(h, D, counts, counter_slot);
+    CK((launch_pipe<LOOP, SUBSET, SCHEME>(h, A, true)));
+    h->stats.n_launches++;
+  }
+  return 0;
+}
+/* main loops: split on the mean number of targets per 64-target chunk of the list (k_build_targets' totals) */
+static unsigned long long main_split() {
+  const double f = sparse_frac();
+  if (f <= 0.) return 0ull;
+  if (f > 1.) return ~0ull;
+  return (unsigned long long)(f * TASK_TARGETS + 0.5);
 }
 
 #ifdef SWIFTGPU_LEGACY_LOOPS
@@ -1292,8 +1352,11 @@ extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 8, 0, sizeof(unsigned long long), h->stream));
   bool sparse = false;
   if (build_targets(h, h->L_density, &sparse)) return 1;
-  if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, h->L_density))) return 1;
-  if (h->L_density.ntasks > 0) {
+  if (h->L_density.ntasks > 0 && loop_kind() == 3) {
+    if (run_pipe_loop<LOOP_DENSITY, false, 0>(h, h->L_density, h->nd, 0, h->d_counters + 12, 0, main_split(),
+                                              h->d_counters + 13))
+      return 1;
+  } else if (h->L_density.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_density, h->nd, 0);
     CK((launch_loop1<LOOP_DENSITY, false>(h, A, sparse)));
     h->stats.n_launches++;
@@ -1364,6 +1427,10 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
     }
     const unsigned long long thr = (unsigned long long)direct_thr * (unsigned long long)D.ngroups;
     const unsigned long long *gate = h->d_counters + 3;
+    /* re-runs with fewer unconverged particles than this fraction of the list's particles: small tasks */
+    const double sf = sparse_frac();
+    const unsigned long long thr_small =
+        sf <= 0. ? 0ull : (sf > 1. ? ~0ull : (unsigned long long)(sf * (double)(h->n_host > 0 ? h->n_host : h->n)));
     if (ensure_frames(h)) return 1;
     for (iter = 0; iter < max_iter; iter++) {
       G.first_pass = iter == 0;
@@ -1388,12 +1455,7 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
       }
       /* re-run the density loop for the unconverged particles
        * (runner_dosub_{self,pair}_subset_density, runner_ghost.c:1548-1572) */
-      if (build_task_recs(h, D, gate, thr, ~0ull)) return 1;
-      {
-        LoopArgs A = loop_args(h, D, h->nd, 4);
-        CK((launch_loop1<LOOP_DENSITY, true>(h, A, false)));
-        h->stats.n_launches++;
-      }
+      if (run_pipe_loop<LOOP_DENSITY, true, 0>(h, D, h->nd, 4, gate, thr, std::max(thr, thr_small), nullptr)) return 1;
       {
         LoopArgs A = loop_args(h, D, h->nd, 4);
         if (launch_direct_density(h, D, A, gate, thr)) return 1;
@@ -1435,7 +1497,7 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
         LoopArgs A = loop_args(h, D, h->nd, 4);
         if (launch_direct_density(h, D, A)) return 1;
       } else {
-        if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, D))) return 1;
+        if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, D, PL_TARGETS))) return 1;
         LoopArgs A = loop_args(h, D, h->nd, 4);
         CK((launch_loop1<LOOP_DENSITY, true>(h, A, sparse)));
         h->stats.n_launches++;
@@ -1505,12 +1567,14 @@ extern "C" int swiftgpu_run_gradient(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 9, 0, sizeof(unsigned long long), h->stream));
   bool sparse = false;
   if (build_targets(h, L, &sparse)) return 1; /* depth_h changed in the ghost */
-  if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, L))) return 1;
   if (loop_kind() >= 2) {
     k_prep_gq<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->fq1, h->fq2, h->fq3, h->n, h->gq);
     h->stats.n_launches++;
   }
-  if (L.ntasks > 0) {
+  if (L.ntasks > 0 && loop_kind() == 3) {
+    if (run_pipe_loop<LOOP_GRADIENT, false, 0>(h, L, h->ng, 1, h->d_counters + 12, 0, main_split(), h->d_counters + 13))
+      return 1;
+  } else if (L.ntasks > 0) {
     LoopArgs A = loop_args(h, L, h->ng, 1);
     CK((launch_loop1<LOOP_GRADIENT, false>(h, A, sparse)));
     h->stats.n_launches++;
@@ -1559,13 +1623,21 @@ extern "C" int swiftgpu_run_force(swiftgpu_t *h) {
   CK(cudaMemsetAsync(h->d_counters + 10, 0, sizeof(unsigned long long), h->stream));
   bool sparse = false;
   if (build_targets(h, h->L_force, &sparse)) return 1;
-  if (loop_kind() == 3 && (ensure_frames(h) || build_task_recs(h, h->L_force))) return 1;
   if (loop_kind() == 2) { /* h changed in the ghost (and the rho halo): source reach of the prefilter */
     k_refresh_reach<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->hh, h->n, tile_margin(h),
                                                                           h->xf);
     h->stats.n_launches++;
   }
-  if (h->L_force.ntasks > 0) {
+  if (h->L_force.ntasks > 0 && loop_kind() == 3) {
+    const unsigned long long *g = h->d_counters + 12, *d = h->d_counters + 13;
+    int rc;
+    switch (h->cfg.scheme) {
+      case SCH_MINIMAL: rc = run_pipe_loop<LOOP_FORCE, false, SCH_MINIMAL>(h, h->L_force, h->nf, 2, g, 0, main_split(), d); break;
+      case SCH_GADGET2: rc = run_pipe_loop<LOOP_FORCE, false, SCH_GADGET2>(h, h->L_force, h->nf, 2, g, 0, main_split(), d); break;
+      default: rc = run_pipe_loop<LOOP_FORCE, false, SCH_SPHENIX>(h, h->L_force, h->nf, 2, g, 0, main_split(), d); break;
+    }
+    if (rc) return 1;
+  } else if (h->L_force.ntasks > 0) {
     LoopArgs A = loop_args(h, h->L_force, h->nf, 2);
     switch (h->cfg.scheme) {
       case SCH_MINIMAL: CK(launch_loop2<SCH_MINIMAL>(h, A, sparse)); break;

@@ -242,13 +242,17 @@ print("ALT_OK", rep["flips"])
 
 
 @pytest.mark.parametrize("env", [{"SWIFTGPU_NO_REORDER": "1"}, {"SWIFTGPU_DIRECT": "1000"}, {"SWIFTGPU_DIRECT": "0"},
-                                 {"SWIFTGPU_HOLD": "2"}],
-                         ids=["no_reorder", "direct_reruns", "pipe_reruns", "serial_fragment_layout"])
+                                 {"SWIFTGPU_HOLD": "2"}, {"SWIFTGPU_SPARSE_FRAC": "2"}, {"SWIFTGPU_SPARSE_FRAC": "0"},
+                                 {"SWIFTGPU_NO_BALANCE": "1"}],
+                         ids=["no_reorder", "direct_reruns", "pipe_reruns", "serial_fragment_layout", "small_tasks_always",
+                              "small_tasks_never", "recursion_item_order"])
 def test_alternative_paths_stay_green(env):
     """Code paths chosen by data or by environment variables read once per process: the host particle
     order (no Morton order inside the leaves), the per-target kernel for EVERY ghost re-run
-    (loops_direct.cuh) or for none, and the producer's serial fragment layout for every window
-    (loops_pipe.cuh: the fallback for double-mode items larger than a stage's double columns). Each
+    (loops_direct.cuh) or for none, the producer's serial fragment layout for every window
+    (loops_pipe.cuh: the fallback for double-mode items larger than a stage's double columns), the
+    small-task variant of the pipeline (4 consumer warps, 32-target tasks) for every launch or for
+    none, and the items of a group in recursion order instead of the direction-balanced order. Each
     runs in a subprocess on a small SPHENIX box (all three loops) against the C restatement."""
     import os
     import subprocess
