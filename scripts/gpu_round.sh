@@ -11,10 +11,10 @@ echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
 tail -3 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --workload $WL > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
-  --log-file gpurun_out/${TAG}_launches.csv python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline --no-e2e \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
+  --log-file gpurun_out/${TAG}_launches.csv python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-resident \
   > gpurun_out/${TAG}_ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_pipe|k_direct' -s 8 -c 8 \
-  -f -o gpurun_out/${TAG}_full python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline --no-e2e \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_pipe|k_direct' -s 51 -c 17 \
+  -f -o gpurun_out/${TAG}_full python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-resident \
   > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out

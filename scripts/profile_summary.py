@@ -46,8 +46,10 @@ if len(sys.argv) > 4:
         def val(name):
             v, u = float(r[HH.index(name)].replace(",", "")), rr[1][HH.index(name)]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-        traffic.setdefault("k_pipe:" + loop, val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
-    json.dump({sys.argv[4]: traffic, "source": f"ncu --set full --clock-control none, first captured launch of each kernel ({os.path.basename(rep)})"},
+        # the launch that did the work (device-gated launches of the other task size move nothing)
+        key = "k_pipe:" + loop
+        traffic[key] = max(traffic.get(key, 0.0), val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+    json.dump({sys.argv[4]: traffic, "source": f"ncu --set full --clock-control none, largest captured launch of each kernel ({os.path.basename(rep)})"},
               open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("wrote", f"profiles/{tag}_summary.md")
