@@ -100,16 +100,16 @@ struct __align__(16) PipeItem {
 static_assert(sizeof(PipeItem) == 96, "PipeItem");
 static_assert(offsetof(PipeItem, relq) % 8 == 0, "relq/padd are read as one float2");
 
-template <int NP, int NS, int QCAP, int CW, int DS>
+template <int NP, int NS, int QCAP, int CW, int DS, int SL = PL_SLOTS>
 struct PipeSmem {
   static constexpr int kDCol = DS + 2 * PL_FRAGS; /* double column: 2 spare entries per fragment (alignment) */
   static constexpr int kStageF = 0;
-  static constexpr int kStageP = kStageF + PL_SLOTS * 16;
-  static constexpr int kStageD = kStageP + NP * PL_SLOTS * 16;
+  static constexpr int kStageP = kStageF + SL * 16;
+  static constexpr int kStageD = kStageP + NP * SL * 16;
   static constexpr int kStageOB = kStageD + 3 * kDCol * 8;
-  static constexpr int kStageIT = kStageOB + PL_OCT * 32;
+  static constexpr int kStageIT = kStageOB + (SL / 8) * 32;
   static constexpr int kStageO2F = kStageIT + PL_FRAGS * (int)sizeof(PipeItem);
-  static constexpr int kStageMeta = kStageO2F + PL_OCT;
+  static constexpr int kStageMeta = kStageO2F + (SL / 8);
   static constexpr int kStageBytes = ((kStageMeta + 64) + 127) & ~127;
   static constexpr int kList = NS * kStageBytes;
   static constexpr int kTP = kList + QCAP * 32 * CW * 2; /* float4 [CW][2][PL_FRAGS][8] */
@@ -128,12 +128,13 @@ enum { PM_NFR = 0, PM_NOCT = 1, PM_FLAG = 2, PM_TASK = 3, PM_TGT_OFF = 4, PM_NTG
 
 #define PL_MIN_BLOCKS(CW) ((CW) >= 8 ? 2 : 4)
 
-template <int LOOP, int SCHEME, int NS, int CW, int DS>
+template <int LOOP, int SCHEME, int NS, int CW, int DS, int SL = PL_SLOTS>
 __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const LoopArgs A) {
+  static_assert(SL % 8 == 0 && SL <= 256 && SL >= 64, "stage slots: whole octets, 8-bit slot field");
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
   constexpr int QCAP = FORCE ? TL_SUBCAP2 : TL_SUBCAP1;
-  typedef PipeSmem<NP, NS, QCAP, CW, DS> SM;
+  typedef PipeSmem<NP, NS, QCAP, CW, DS, SL> SM;
   static_assert(CW >= 1 && CW <= 8, "a task is 8 * CW targets");
   extern __shared__ __align__(128) char smem_pl[];
   char *const smem = smem_pl;
@@ -398,15 +399,15 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
           tma_load(P + my_pool, A.mv + first, n16, sFull + s);
           bytes = 2u * n16;
           if (LOOP == LOOP_GRADIENT) {
-            tma_load(P + PL_SLOTS + my_pool, A.gq + first, n16, sFull + s);
+            tma_load(P + SL + my_pool, A.gq + first, n16, sFull + s);
             bytes += n16;
           }
           if (FORCE) {
-            tma_load(P + PL_SLOTS + my_pool, A.fq1 + first, n16, sFull + s);
-            tma_load(P + 2 * PL_SLOTS + my_pool, A.fq2 + first, n16, sFull + s);
+            tma_load(P + SL + my_pool, A.fq1 + first, n16, sFull + s);
+            tma_load(P + 2 * SL + my_pool, A.fq2 + first, n16, sFull + s);
             bytes += 2u * n16;
             if (SCHEME == SCH_SPHENIX) {
-              tma_load(P + 3 * PL_SLOTS + my_pool, A.fq3 + first, n16, sFull + s);
+              tma_load(P + 3 * SL + my_pool, A.fq3 + first, n16, sFull + s);
               bytes += n16;
             }
           }
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
           km = win_finish(T, cur_cell, win_base, W, cur_buf);
         }
         /* ---- layout of the window's kept items in a virtual source array cut into stages of
-         * PL_SLOTS (lane = item): exclusive prefix sum of the padded sizes. An item takes at least
+         * SL (lane = item): exclusive prefix sum of the padded sizes. An item takes at least
          * 40 slots, so a stage holds at most 2 partial + 6 whole items = PL_FRAGS fragments. ---- */
         const int4 myaux = sWinAux[cur_buf * 32 + lane];
         const bool kept = (km >> lane) & 1u;
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
         /* a double-mode item larger than the stage's double columns: serial fallback below */
         /* (... or, in the main loops whose double columns hold one small item, a second double-mode item) */
         const bool big = (A.hold & 2) || __any_sync(FULL_MASK, mydbl && pn > (DS & ~7)) ||
-                         (DS < PL_SLOTS && __popc(__ballot_sync(FULL_MASK, mydbl)) > 1);
+                         (DS < SL && __popc(__ballot_sync(FULL_MASK, mydbl)) > 1);
         if (!big) {
           const int v = kept ? max(pn, 40) : 0;
           int V = v;
@@ -480,9 +481,9 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
           }
           const int vstart = V - v;
           const int total = __shfl_sync(FULL_MASK, V, 31);
-          const int nstages = (total + PL_SLOTS - 1) / PL_SLOTS;
+          const int nstages = (total + SL - 1) / SL;
           for (int k = 0; k < nstages; k++) {
-            const int lo = k * PL_SLOTS, hi = lo + PL_SLOTS;
+            const int lo = k * SL, hi = lo + SL;
             const int a0 = max(vstart, lo), b0 = min(vstart + pn, hi);
             const bool has = kept && a0 < b0;
             const int my_off = a0 - vstart;
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
              * look like sources */
             const int gap_from = kept ? min(max(vstart + pn, lo), hi) - lo : 0;
             const int gap_to = kept ? min(min(max(vstart + v, lo), hi) - lo, used) : 0;
-            publish(has, myfrag, nfr, used, lane, my_off, my_n, my_pool, DS >= PL_SLOTS ? my_pool + 2 * myfrag : 0,
+            publish(has, myfrag, nfr, used, lane, my_off, my_n, my_pool, DS >= SL ? my_pool + 2 * myfrag : 0,
                     gap_from, gap_to);
           }
         } else {
@@ -506,13 +507,13 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
           for (;;) {
             int used = 0, nfr = 0, dused = 0;
             int my_w = 0, my_off = 0, my_n = 0, my_pool = 0, my_dbase = 0;
-            while (nfr < PL_FRAGS && used < PL_SLOTS) {
+            while (nfr < PL_FRAGS && used < SL) {
               const unsigned mm = j >= 32 ? 0u : (km >> j) << j;
               if (!mm) break;
               const int jj = __ffs(mm) - 1;
               const int4 aux = sWinAux[cur_buf * 32 + jj];
               const bool dbl = sWin[cur_buf * 32 + jj].dbl != 0;
-              const int left = aux.y - off, room = PL_SLOTS - used;
+              const int left = aux.y - off, room = SL - used;
               int take = left <= room ? left : (room & ~7);
               if (dbl) {
                 const int droom = (DS - dused) & ~7;
@@ -660,14 +661,14 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
           if (LOOP == LOOP_DENSITY) {
             iact_density(dacc, r2, dx, dy, dz, th_inv, tvx, tvy, tvz, f0.x, f0.y, f0.z, f0.w);
           } else {
-            const float4 f1 = P[PL_SLOTS + sl];
+            const float4 f1 = P[SL + sl];
             iact_gradient(gacc, r2, dx, dy, dz, th, tvx, tvy, tvz, tu, tcs, f0.x, f0.y, f0.z, f0.w,
                           f1.x, f1.y, f1.z, f1.w, A.a2_Hubble);
           }
           nhit++;
         }
       } else {
-        const float4 q2 = P[2 * PL_SLOTS + sl];
+        const float4 q2 = P[2 * SL + sl];
         const float sh = act ? q2.y : 1.f;
         const float shg2 = hg2_exact(sh);
         const bool a1 = r2 < thg2, a2 = r2 < shg2;
@@ -688,13 +689,13 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
         }
         if (ok) {
           ForceQ sq;
-          const float4 q0 = P[sl], q1 = P[PL_SLOTS + sl];
+          const float4 q0 = P[sl], q1 = P[SL + sl];
           sq.m = q0.x; sq.vx = q0.y; sq.vy = q0.z; sq.vz = q0.w;
           sq.rho = q1.x; sq.P = q1.y; sq.f = q1.z; sq.cs = q1.w;
           sq.balsara = q2.x; sq.h = q2.y; sq.u = q2.z; sq.time_bin = __float_as_int(q2.w);
           sq.alpha_visc = sq.alpha_diff = 0.f;
           if (SCHEME == SCH_SPHENIX) {
-            const float4 q3 = P[3 * PL_SLOTS + sl];
+            const float4 q3 = P[3 * SL + sl];
             sq.alpha_visc = q3.x;
             sq.alpha_diff = q3.y;
           }
@@ -908,7 +909,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const
           float lima, limc;
           int cdbl = 0;
           if (FORCE) {
-            const float *const HQ = (const float *)(st + SM::kStageP) + (PL_HG2_COL(SCHEME) * PL_SLOTS + sl) * 4 + 2;
+            const float *const HQ = (const float *)(st + SM::kStageP) + (PL_HG2_COL(SCHEME) * SL + sl) * 4 + 2;
             const float2 rq = *(const float2 *)&IT[fl].relq;
             lima = fmaf(fmaxf(thg2, HQ[0]), rq.x, rq.y);
             limc = fmaf(fmaxf(thg2, HQ[4]), rq.x, rq.y);

@@ -1187,14 +1187,14 @@ static int launch_direct_density(H *h, const DevList &D, const LoopArgs &A, cons
 
 /* frame pipeline (loops_pipe.cuh): DS = double-column slots per stage (64: only the self item of a
  * main loop is evaluated on doubles; 256: the ghost re-runs, where every pair item is) */
-template <int LOOP, int SCHEME, int NS, int DS, int CW = 8>
+template <int LOOP, int SCHEME, int NS, int DS, int CW = 8, int SL = PL_SLOTS>
 static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  constexpr int bytes = PipeSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1), CW, DS>::kBytes;
+  constexpr int bytes = PipeSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1), CW, DS, SL>::kBytes;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_pipe<LOOP, SCHEME, NS, CW, DS>,
+    cudaError_t e = cudaFuncSetAttribute(k_pipe<LOOP, SCHEME, NS, CW, DS, SL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -1204,18 +1204,18 @@ static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
     int per_sm = 0, sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipe<LOOP, SCHEME, NS, CW, DS>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipe<LOOP, SCHEME, NS, CW, DS, SL>,
                                                                   32 * (CW + 1), bytes);
     if (e != cudaSuccess) return e;
     resident = std::max(1, per_sm) * std::max(1, sms);
     if (getenv("SWIFTGPU_VERBOSE"))
-      fprintf(stderr, "k_pipe<%d,%d,NS=%d,CW=%d,DS=%d>: %d B smem, %d CTAs/SM\n", LOOP, SCHEME, NS, CW, DS, bytes, per_sm);
+      fprintf(stderr, "k_pipe<%d,%d,NS=%d,CW=%d,DS=%d,SL=%d>: %d B smem, %d CTAs/SM\n", LOOP, SCHEME, NS, CW, DS, SL, bytes, per_sm);
   }
   const int grid = (int)std::min<long long>(A.ntasks, resident);
   if (grid <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(A.task_counter, 0, sizeof(unsigned int), h->stream);
   if (e != cudaSuccess) return e;
-  k_pipe<LOOP, SCHEME, NS, CW, DS><<<grid, 32 * (CW + 1), bytes, h->stream>>>(A);
+  k_pipe<LOOP, SCHEME, NS, CW, DS, SL><<<grid, 32 * (CW + 1), bytes, h->stream>>>(A);
   return cudaGetLastError();
 }
 #ifndef PL_NS_DENSITY
@@ -1226,7 +1226,10 @@ static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
 #define PL_NS_SUBSET 5
 #define PL_NS_GRADIENT 5
 #define PL_NS_FORCE 4
+/* SPHENIX force: 5 float4 per source, 256-slot stages fit 3 times only. 192-slot stages x 4 were
+ * measured: -7 % before the direction-balanced item order, +-0 after it (sweeps in profiles/r02_sweeps.log) */
 #define PL_NS_FORCE_SPHENIX 3
+#define PL_SLOTS_FORCE_SPHENIX 256
 #endif
 #ifndef PL_NS_SPARSE
 /* the small-task variant (PL_SPARSE_CW consumer warps): 3-4 CTAs per SM */
@@ -1244,8 +1247,9 @@ static cudaError_t launch_pipe(H *h, const LoopArgs &A, bool small = false) {
     if (SUBSET) return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SPARSE, 256, PL_SPARSE_CW>(h, A);
     return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SPARSE, 64, PL_SPARSE_CW>(h, A);
   }
-  if (LOOP == LOOP_FORCE)
-    return launch_pipe_ns<LOOP_FORCE, SCHEME, (SCHEME == SCH_SPHENIX ? PL_NS_FORCE_SPHENIX : PL_NS_FORCE), 64>(h, A);
+  if (LOOP == LOOP_FORCE && SCHEME == SCH_SPHENIX)
+    return launch_pipe_ns<LOOP_FORCE, SCHEME, PL_NS_FORCE_SPHENIX, 64, 8, PL_SLOTS_FORCE_SPHENIX>(h, A);
+  if (LOOP == LOOP_FORCE) return launch_pipe_ns<LOOP_FORCE, SCHEME, PL_NS_FORCE, 64>(h, A);
   if (LOOP == LOOP_GRADIENT) return launch_pipe_ns<LOOP_GRADIENT, 0, PL_NS_GRADIENT, 64>(h, A);
   if (SUBSET) return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SUBSET, 256>(h, A);
   return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_DENSITY, 64>(h, A);
