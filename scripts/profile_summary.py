@@ -39,13 +39,13 @@ if len(sys.argv) > 4:
     traffic = {}
     for r in rr[2:]:
         nm = r[HH.index("Kernel Name")]
-        mm = re.match(r"void k_pipe<(\d+), (\d+), (\d+), (\d+), (\d+)>", nm)
+        mm = re.match(r"void k_pipe<(\d+), (\d+), (\d+), (\d+), (\d+)(?:, \d+)?>", nm)
         if not mm: continue
         loop = {"0": "density", "1": "gradient", "2": "force"}[mm.group(1)]
         if loop == "density" and mm.group(5) == "256": loop = "subset"
         def val(name):
             v, u = float(r[HH.index(name)].replace(",", "")), rr[1][HH.index(name)]
-            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+            return 0.0 if v != v else v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         # the launch that did the work (device-gated launches of the other task size move nothing)
         key = "k_pipe:" + loop
         traffic[key] = max(traffic.get(key, 0.0), val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))

@@ -654,6 +654,33 @@ def test_sedov64_vs_reference(scheme, with_velocity):
     g.close()
 
 
+def test_active5_64cubed_vs_reference():
+    """BASELINE config 5's shape (SPHENIX, ~5 % of the particles active, bench.py's brick generator
+    and its activity pattern) at 64^3 against the unmodified reference: sparse target lists in every
+    loop, inactive neighbours contributing the force members of "their last step" (taken from an
+    all-active reference run), inactive particles untouched byte for byte (src/active.h:349-366)."""
+    scheme = "sphenix"
+    ic = host.brick_box(64, abi.SCHEME_SPHENIX, grid=(1, 1, 1), rank=0, top=host.default_top_grid(64)[0],
+                        active_fraction=0.05)
+    frac = float((ic["time_bin"] <= 1).mean())
+    assert 0.02 < frac < 0.1, frac
+    c = util.make_case(scheme, ic, host.default_top_grid(64), max_active_bin=1)
+    c_all = util.make_case(scheme, dict(ic, time_bin=np.ones_like(ic["time_bin"])), host.default_top_grid(64))
+    o_all, _ = util.run_oracle(c_all)
+    c.parts = o_all.parts()
+    tb = host.field(c.parts, c.layout, "time_bin")
+    tb[:] = ic["time_bin"][c.tree.perm]
+    g = util.run_gpu(c)
+    got = g.download_parts()
+    inactive = tb > 1
+    size = c.layout.size
+    assert np.array_equal(got.reshape(-1, size)[inactive], c.parts.reshape(-1, size)[inactive]), \
+        "an inactive particle was modified"
+    rep = _check(c, g)
+    assert rep["n"] == 64 ** 3
+    g.close()
+
+
 def test_flip_rate_against_the_references_own():
     """the flip allowance is tied to what the reference does
     to ITSELF. Same 64^3 box: (a) the reference against the reference with the
