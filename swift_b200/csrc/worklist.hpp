@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "../../include/swiftgpu.h"
@@ -103,14 +104,53 @@ class Flattener {
     for (int k = 0; k < 3; k++) dim_[k] = dim[k];
   }
 
+  /* Host threads of the flattening (SWIFTGPU_HOST_THREADS, default: the hardware's, at most 16). The
+   * result does not depend on it: every worker walks a contiguous range of top-level cells with its
+   * own emission buffers, which are concatenated in the serial order. */
+  static int host_threads() {
+    static int v = 0;
+    if (v == 0) {
+      const char *e = getenv("SWIFTGPU_HOST_THREADS");
+      v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+      v = std::max(1, std::min(v, 16));
+    }
+    return v;
+  }
+  template <class Fn>
+  void parallel_ranges(int n, Fn body /* (Flattener &worker, int lo, int hi, int part) */) const {
+    const int T = std::max(1, std::min(host_threads(), n / 8));
+    std::vector<Flattener> workers;
+    workers.reserve(T);
+    for (int t = 0; t < T; t++) workers.emplace_back(c_, ncells_, top_, ntop_, dim_, periodic_, rank_, ti_current_);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) {
+      const int lo = (int)((int64_t)n * t / T), hi = (int)((int64_t)n * (t + 1) / T);
+      if (T == 1)
+        body(workers[t], lo, hi, t);
+      else
+        th.emplace_back([&, t, lo, hi]() { body(workers[t], lo, hi, t); });
+    }
+    for (std::thread &x : th) x.join();
+  }
+
   /* loop: 0 density, 1 gradient (same decomposition as density), 2 force */
   void build_loop(int loop, WorkList &out) {
     raw_.clear();
-    for (int a = 0; a < ntop_; a++) {
-      const int ca = top_[a];
-      if (c_[ca].nodeID == rank_) dosub_self(loop, ca, 0);
-    }
-    for_each_top_pair([&](int ca, int cb) { dosub_pair(loop, ca, cb, 0); });
+    const int T = std::max(1, std::min(host_threads(), ntop_ / 8));
+    std::vector<std::vector<Raw>> selfs(T), pairs(T);
+    parallel_ranges(ntop_, [&](Flattener &w, int lo, int hi, int part) {
+      w.raw_.clear();
+      for (int a = lo; a < hi; a++) {
+        const int ca = top_[a];
+        if (c_[ca].nodeID == rank_) w.dosub_self(loop, ca, 0);
+      }
+      selfs[part].swap(w.raw_);
+      w.raw_.clear();
+      w.for_each_top_pair([&](int ca, int cb) { w.dosub_pair(loop, ca, cb, 0); }, lo, hi);
+      pairs[part].swap(w.raw_);
+    });
+    for (int t = 0; t < T; t++) raw_.insert(raw_.end(), selfs[t].begin(), selfs[t].end());
+    for (int t = 0; t < T; t++) raw_.insert(raw_.end(), pairs[t].begin(), pairs[t].end());
     finish(out, /*by_leaf=*/false);
   }
 
@@ -125,18 +165,25 @@ class Flattener {
     /* neighbour lists of the top-level cells */
     std::vector<std::vector<int>> ngb(ntop_);
     for_each_top_pair_all([&](int a, int b) { ngb[a].push_back(b); });
-    std::vector<int> leaves;
-    for (int a = 0; a < ntop_; a++) {
-      const int ca = top_[a];
-      if (c_[ca].nodeID != rank_) continue;
-      leaves.clear();
-      collect_active_leaves(ca, leaves);
-      for (int leaf : leaves) {
-        cur_leaf_ = leaf;
-        dosub_self_subset(ca);
-        for (int b : ngb[a]) dosub_pair_subset(ca, top_[b]);
+    const int T = std::max(1, std::min(host_threads(), ntop_ / 8));
+    std::vector<std::vector<Raw>> parts(T);
+    parallel_ranges(ntop_, [&](Flattener &w, int lo, int hi, int part) {
+      w.raw_.clear();
+      std::vector<int> leaves;
+      for (int a = lo; a < hi; a++) {
+        const int ca = top_[a];
+        if (c_[ca].nodeID != rank_) continue;
+        leaves.clear();
+        w.collect_active_leaves(ca, leaves);
+        for (int leaf : leaves) {
+          w.cur_leaf_ = leaf;
+          w.dosub_self_subset(ca);
+          for (int b : ngb[a]) w.dosub_pair_subset(ca, top_[b]);
+        }
       }
-    }
+      parts[part].swap(w.raw_);
+    });
+    for (int t = 0; t < T; t++) raw_.insert(raw_.end(), parts[t].begin(), parts[t].end());
     finish(out, /*by_leaf=*/true);
     aux.swap(sorted_aux_);
   }
@@ -212,6 +259,21 @@ class Flattener {
    * 2 -> y, 1 -> z (space_split.c:243-245); octants pid of ci and pjd of cj
    * form a sub-pair iff they touch when cj sits at dir(sid) from ci. */
   static int sub_pairs(int sid, int pid[16], int pjd[16]) {
+    /* 13 small tables, computed once */
+    struct Table {
+      int n[13], a[13][16], b[13][16];
+      Table() {
+        for (int s = 0; s < 13; s++) n[s] = sub_pairs_compute(s, a[s], b[s]);
+      }
+    };
+    static const Table T;
+    for (int k = 0; k < T.n[sid]; k++) {
+      pid[k] = T.a[sid][k];
+      pjd[k] = T.b[sid][k];
+    }
+    return T.n[sid];
+  }
+  static int sub_pairs_compute(int sid, int pid[16], int pjd[16]) {
     int d[3];
     for (int k = 0; k < 3; k++)
       d[k] = kRunnerShift[sid][k] > 0 ? 1 : (kRunnerShift[sid][k] < 0 ? -1 : 0);
@@ -233,8 +295,9 @@ class Flattener {
   }
 
   template <class F>
-  void for_each_top_pair_all(F f) const {
-    /* every ordered couple (a,b), a != b, of touching top-level cells */
+  void for_each_top_pair_all(F f, int a_lo = 0, int a_hi = -1) const {
+    /* every ordered couple (a,b), a != b, of touching top-level cells, a in [a_lo, a_hi) */
+    if (a_hi < 0) a_hi = ntop_;
     const swiftgpu_cell &c0 = c_[top_[0]];
     int cdim[3];
     for (int k = 0; k < 3; k++) cdim[k] = (int)std::floor(dim_[k] / c0.width[k] + 0.5);
@@ -247,7 +310,7 @@ class Flattener {
       grid[((size_t)idx(c, 0) * cdim[1] + idx(c, 1)) * cdim[2] + idx(c, 2)] = a;
     }
     std::vector<int> seen;
-    for (int a = 0; a < ntop_; a++) {
+    for (int a = a_lo; a < a_hi; a++) {
       const swiftgpu_cell &c = c_[top_[a]];
       const int ix = idx(c, 0), iy = idx(c, 1), iz = idx(c, 2);
       seen.clear();
@@ -272,14 +335,14 @@ class Flattener {
     }
   }
   template <class F>
-  void for_each_top_pair(F f) const {
+  void for_each_top_pair(F f, int a_lo = 0, int a_hi = -1) const {
     /* unordered couples with at least one local side
-     * (engine_maketasks.c:3562-3569) */
+     * (engine_maketasks.c:3562-3569), the smaller index in [a_lo, a_hi) */
     for_each_top_pair_all([&](int a, int b) {
       if (b < a) return;
       if (!local(top_[a]) && !local(top_[b])) return;
       f(top_[a], top_[b]);
-    });
+    }, a_lo, a_hi);
   }
 
   void emit(int mode, int t, int s, int sid, const int8_t shift[3], int min_depth,
@@ -444,13 +507,32 @@ class Flattener {
    * next comes the item that keeps the running sum of (direction x source count) smallest, which
    * alternates opposite sides. */
   void balance_directions(std::vector<uint32_t> &order) const {
+    /* groups are independent: the threads take contiguous slices of `order` cut at group boundaries */
+    const int T = order.size() < 100000 ? 1 : host_threads();
+    std::vector<size_t> cut(T + 1, order.size());
+    cut[0] = 0;
+    for (int t = 1; t < T; t++) {
+      size_t p = order.size() * (size_t)t / (size_t)T;
+      while (p > 0 && p < order.size() && raw_[order[p]].it.tcell == raw_[order[p - 1]].it.tcell) p++;
+      cut[t] = std::max(p, cut[t - 1]);
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) {
+      if (T == 1)
+        balance_range(order, cut[t], cut[t + 1]);
+      else
+        th.emplace_back([&, t]() { balance_range(order, cut[t], cut[t + 1]); });
+    }
+    for (std::thread &x : th) x.join();
+  }
+  void balance_range(std::vector<uint32_t> &order, size_t begin, size_t end) const {
     std::vector<uint32_t> tmp;
     std::vector<float> d;
     std::vector<char> used;
-    for (size_t g0 = 0; g0 < order.size();) {
+    for (size_t g0 = begin; g0 < end;) {
       size_t g1 = g0 + 1;
       const int32_t tc = raw_[order[g0]].it.tcell;
-      while (g1 < order.size() && raw_[order[g1]].it.tcell == tc) g1++;
+      while (g1 < end && raw_[order[g1]].it.tcell == tc) g1++;
       const size_t n = g1 - g0;
       if (n > 2 && n <= 4096) {
         d.assign(3 * n, 0.f);
@@ -491,12 +573,14 @@ class Flattener {
   }
 
   void finish(WorkList &out, bool keep_aux) {
-    /* group by target cell, stable */
+    /* group by target cell, stable: counting sort on the cell index */
     std::vector<uint32_t> order(raw_.size());
-    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-      return raw_[a].it.tcell < raw_[b].it.tcell;
-    });
+    {
+      std::vector<uint32_t> first((size_t)ncells_ + 1, 0);
+      for (const Raw &r : raw_) first[(size_t)r.it.tcell + 1]++;
+      for (int c = 0; c < ncells_; c++) first[c + 1] += first[c];
+      for (uint32_t i = 0; i < (uint32_t)raw_.size(); i++) order[first[raw_[i].it.tcell]++] = i;
+    }
     if (!getenv("SWIFTGPU_NO_BALANCE")) balance_directions(order); /* A/B knob */
     out.items.resize(raw_.size());
     out.groups.clear();
