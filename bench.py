@@ -532,7 +532,7 @@ def main():
         # ---- device-resident leg: drift + step without the particles crossing the host boundary ----
         resident = None
         if world == 1 and not args.no_resident:
-            X = abi.XpartLayout(48, 0, 12, 24)  # synthetic struct xpart: x_diff, x_diff_sort, v_full + padding
+            X = abi.XpartLayout(48, 0, 12, 24, 36)  # synthetic struct xpart: x_diff, x_diff_sort, v_full, u_full + padding
             xp = np.zeros((n, 48), np.uint8)
             xp[:, 24:36] = np.ascontiguousarray(host.field(c.parts, c.layout, "v").reshape(n, 3),
                                                 dtype=np.float32).view(np.uint8).reshape(n, 12)

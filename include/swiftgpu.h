@@ -289,6 +289,7 @@ typedef struct swiftgpu_xpart_layout {
   int32_t x_diff;      /* offsetof(struct xpart, x_diff), float[3] */
   int32_t x_diff_sort; /* float[3] */
   int32_t v_full;      /* float[3] */
+  int32_t u_full;      /* float: u_full (Minimal, SPHENIX) | entropy_full (Gadget2); -1 if the kick is not used */
 } swiftgpu_xpart_layout;
 
 typedef struct swiftgpu_drift_args {
@@ -303,6 +304,23 @@ int swiftgpu_upload_xparts(swiftgpu_t *h, const swiftgpu_xpart_layout *layout,
                            const void *xparts_aos, int64_t nparts);
 int swiftgpu_download_xparts(swiftgpu_t *h, void *xparts_aos, int64_t nparts);
 int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args);
+
+/*
+ * Kick on the device (the kick half): runner_do_kick1 (which = 1,
+ * src/runner_time_integration.c:87) for the particles STARTING their step and
+ * runner_do_kick2 (which = 2, :360) for the ACTIVE ones, hydro particles
+ * without gravity: kick_part (src/kick.h:113: v_full += a_hydro dt_kick_hydro,
+ * hydro_kick_extra of the scheme - u_full | entropy_full += du/dt dt_therm, at
+ * most halved, floored at minimal_internal_energy) with the half time-step of
+ * the particle's own time_bin, (ti_step / 2) * time_base; kick2 then calls
+ * hydro_reset_predicted_values (p->v, p->u | entropy, pressure | P_over_rho2,
+ * sound speed, v_sig from the full-step values). Works on the device copies of
+ * struct part[] / struct xpart[] like the drift; together with it and
+ * swiftgpu_run_step a fixed-time-step leapfrog runs without the particles
+ * crossing the host boundary. Not covered: the time-step limiter loop, the
+ * assignment of new time bins (runner_do_timestep), cosmological kick factors.
+ */
+int swiftgpu_run_kick(swiftgpu_t *h, int which, float minimal_internal_energy);
 
 /* Per-particle directed interaction counts of the last density / gradient /
  * force loops (the reference's N_density/N_gradient/N_force debugging counters,

@@ -43,6 +43,7 @@ def load(variant):
         lib.swiftref_set_xparts.argtypes = [VP, VP]
         lib.swiftref_get_xparts.argtypes = [VP, VP]
         lib.swiftref_run_drift.argtypes = [VP, C.c_longlong, C.c_float, C.c_int]
+        lib.swiftref_run_kick.argtypes = [VP, C.c_int, C.c_float]
         lib.swiftref_space_split.argtypes = [C.POINTER(abi.Config), C.POINTER(abi.Step), VP, C.c_longlong, VP, VP, VP, C.c_int]
         _libs[variant] = lib
     return _libs[variant]
@@ -133,6 +134,10 @@ class Reference:
     def drift(self, ti_old, minimal_internal_energy=0.0, init_particles=1):
         """The reference's cell_drift_part on every local top-level cell, from ti_old to ti_current."""
         self.lib.swiftref_run_drift(self.h, int(ti_old), float(minimal_internal_energy), int(init_particles))
+
+    def kick(self, which, minimal_internal_energy=0.0):
+        """The reference's runner_do_kick1 (which=1) / runner_do_kick2 (which=2) on every local top-level cell."""
+        self.lib.swiftref_run_kick(self.h, int(which), float(minimal_internal_energy))
 
     def sort(self, cell, sid):
         n = int(self._cells["count"][cell])

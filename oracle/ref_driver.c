@@ -745,6 +745,11 @@ void swiftref_xpart_layout(swiftgpu_xpart_layout *X) {
   X->x_diff = (int)offsetof(struct xpart, x_diff);
   X->x_diff_sort = (int)offsetof(struct xpart, x_diff_sort);
   X->v_full = (int)offsetof(struct xpart, v_full);
+#if defined(GADGET2_SPH)
+  X->u_full = (int)offsetof(struct xpart, entropy_full);
+#else
+  X->u_full = (int)offsetof(struct xpart, u_full);
+#endif
 }
 int swiftref_set_xparts(swiftref_t *s, const void *xparts_aos) {
   memcpy(s->xparts, xparts_aos, s->nparts * sizeof(struct xpart));
@@ -754,6 +759,34 @@ int swiftref_get_xparts(swiftref_t *s, void *xparts_aos) {
   memcpy(xparts_aos, s->xparts, s->nparts * sizeof(struct xpart));
   return 0;
 }
+/* runner_do_kick1 / runner_do_kick2 (src/runner_time_integration.c:87,360) on every local top-level
+ * cell: the reference's own kick of the hydro particles (no gravity, no mesh). */
+int swiftref_run_kick(swiftref_t *s, int which, float minimal_internal_energy) {
+  static struct pm_mesh mesh;
+  bzero(&mesh, sizeof(mesh));
+  mesh.ti_beg_mesh_next = -1;
+  mesh.ti_end_mesh_next = -1;
+  mesh.ti_beg_mesh_last = -1;
+  mesh.ti_end_mesh_last = -1;
+  s->engine.mesh = &mesh;
+  s->hp.minimal_internal_energy = minimal_internal_energy;
+  struct runner r;
+  bzero(&r, sizeof(r));
+  r.e = &s->engine;
+  for (int i = 0; i < s->ncells; i++) /* cell_is_starting_hydro: ti_beg_max == ti_current */
+    if (s->cells[i].hydro.ti_end_min == s->engine.ti_current)
+      s->cells[i].hydro.ti_beg_max = s->engine.ti_current;
+  for (int a = 0; a < s->ntop; a++) {
+    struct cell *c = &s->cells[s->top[a]];
+    if (c->nodeID != s->cfg.rank) continue;
+    if (which == 1)
+      runner_do_kick1(&r, c, /*timer=*/0);
+    else
+      runner_do_kick2(&r, c, /*timer=*/0);
+  }
+  return 0;
+}
+
 /* cell_drift_part(c, e, force = 1, init_particles, NULL) on every local top-level cell
  * (engine_drift.c:83), all cells drifted from ti_old to the step's ti_current. */
 int swiftref_run_drift(swiftref_t *s, long long ti_old, float minimal_internal_energy,

@@ -68,7 +68,8 @@ class Step(C.Structure):
 
 
 class XpartLayout(C.Structure):
-    _fields_ = [("size", C.c_int32), ("x_diff", C.c_int32), ("x_diff_sort", C.c_int32), ("v_full", C.c_int32)]
+    _fields_ = [("size", C.c_int32), ("x_diff", C.c_int32), ("x_diff_sort", C.c_int32), ("v_full", C.c_int32),
+                ("u_full", C.c_int32)]
 
 
 class DriftArgs(C.Structure):
@@ -151,6 +152,7 @@ EXPORTS = [
     ("swiftgpu_upload_xparts", C.c_int, [VP, C.POINTER(XpartLayout), VP, I64]),
     ("swiftgpu_download_xparts", C.c_int, [VP, VP, I64]),
     ("swiftgpu_run_drift", C.c_int, [VP, C.POINTER(DriftArgs)]),
+    ("swiftgpu_run_kick", C.c_int, [VP, C.c_int, C.c_float]),
     ("swiftgpu_get_stats", C.c_int, [VP, C.POINTER(Stats)]),
     ("swiftgpu_download_sort", C.c_int, [VP, I32, I32, VP, VP, VP]),
     ("swiftgpu_worklist_stats", C.c_int, [C.POINTER(Config), C.POINTER(Step), VP, I32, VP, I32, C.c_int, VP]),

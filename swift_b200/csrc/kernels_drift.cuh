@@ -177,4 +177,81 @@ __global__ void k_get_cell_drift(const DevCell *cells, int ncells, float *out /*
   out[3 * ncells + c] = cells[c].dx_max_sort;
 }
 
+/* ---- kick (runner_do_kick1 / runner_do_kick2, src/runner_time_integration.c:87,360) ---- */
+struct KickArgs {
+  char *aos;
+  char *xaos;
+  DevLayout D;
+  swiftgpu_xpart_layout X;
+  int64_t n;
+  int which; /* 1: kick1 (part_is_starting), 2: kick2 (part_is_active) + hydro_reset_predicted_values */
+  int max_active_bin;
+  double time_base;
+  float min_u;
+};
+
+template <int SCHEME>
+__global__ void __launch_bounds__(256) k_kick(const KickArgs A) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const swiftgpu_part_layout &L = A.D.L;
+  char *b = A.aos + (size_t)L.size * (size_t)i;
+  char *xb = A.xaos + (size_t)A.X.size * (size_t)i;
+  const int tb = rd<int8_t>(b, L.time_bin);
+  /* part_is_starting / part_is_active (src/active.h:349,472): time_bin <= max_active_bin */
+  if (tb > A.max_active_bin) return;
+  /* half of the particle's own step: get_integer_timestep (timeline.h:59), no cosmology */
+  const long long ti_step = tb <= 0 ? 0ll : (1ll << (tb + 1));
+  const double dt = (double)(ti_step / 2) * A.time_base;
+  const float dt_therm = (float)dt;
+  /* kick_part, src/kick.h:113 */
+  float vf[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    vf[a] = (float)__dadd_rn((double)rd<float>(xb, A.X.v_full + 4 * a),
+                             __dmul_rn((double)rd<float>(b, L.a_hydro + 4 * a), dt));
+    wr<float>(xb, A.X.v_full + 4 * a, vf[a]);
+  }
+  /* hydro_kick_extra: Minimal hydro.h:880, Gadget2 :862, SPHENIX :1093 */
+  const int rate_off = SCHEME == SCH_GADGET2 ? L.entropy_dt : L.u_dt;
+  const float rho = rd<float>(b, L.rho);
+  float full = rd<float>(xb, A.X.u_full);
+  const float delta = __fmul_rn(rd<float>(b, rate_off), dt_therm);
+  full = fmaxf(__fadd_rn(full, delta), __fmul_rn(0.5f, full));
+  float floor_v = 0.f; /* entropy floor none */
+  if (SCHEME == SCH_GADGET2) {
+    if (A.min_u > 0.f) {
+      const float cb = cbrtf(rho);
+      floor_v = fmaxf(floor_v, __fmul_rn(__fmul_rn(HYDRO_GAMMA_MINUS_ONE, A.min_u), __fdiv_rn(1.f, __fmul_rn(cb, cb))));
+    }
+  } else {
+    floor_v = fmaxf(A.min_u, 0.f);
+  }
+  if (full < floor_v) {
+    full = floor_v;
+    wr<float>(b, rate_off, 0.f);
+  }
+  wr<float>(xb, A.X.u_full, full);
+  if (A.which != 2) return;
+  /* hydro_reset_predicted_values: Minimal hydro.h:786, Gadget2 :765, SPHENIX :983 */
+#pragma unroll
+  for (int a = 0; a < 3; a++) wr<float>(b, L.v + 4 * a, vf[a]);
+  if (SCHEME == SCH_GADGET2) {
+    wr<float>(b, L.entropy, full);
+    const float cb = cbrtf(rho);
+    const float P = __fmul_rn(full, __fmul_rn(__fmul_rn(cb, cb), rho));
+    const float cs = __fsqrt_rn(__fdiv_rn(__fmul_rn(HYDRO_GAMMA, P), rho));
+    const float rho_inv = __fdiv_rn(1.f, rho);
+    wr<float>(b, L.soundspeed, cs);
+    wr<float>(b, L.P_over_rho2, __fmul_rn(__fmul_rn(P, rho_inv), rho_inv));
+  } else {
+    wr<float>(b, L.u, full);
+    const float P = __fmul_rn(__fmul_rn(HYDRO_GAMMA_MINUS_ONE, full), rho);
+    const float cs = __fsqrt_rn(__fdiv_rn(__fmul_rn(HYDRO_GAMMA, P), rho));
+    wr<float>(b, L.pressure, P);
+    wr<float>(b, L.soundspeed, cs);
+    wr<float>(b, L.v_sig, fmaxf(rd<float>(b, L.v_sig), __fmul_rn(2.f, cs)));
+  }
+}
+
 #endif

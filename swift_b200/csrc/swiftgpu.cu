@@ -105,7 +105,7 @@ struct swiftgpu_handle {
   bool gradient_own = false; /* L_gradient was rebuilt after the ghost (else the density list is used) */
   char *d_aos = nullptr;
   char *d_xaos = nullptr; /* device copy of the caller's struct xpart[] (drift) */
-  swiftgpu_xpart_layout xlayout = {0, 0, 0, 0};
+  swiftgpu_xpart_layout xlayout = {0, 0, 0, 0, -1};
   int64_t n_x = 0;
   size_t aos_bytes = 0;
   double *x = nullptr;
@@ -1763,6 +1763,7 @@ extern "C" int swiftgpu_upload_xparts(swiftgpu_t *h, const swiftgpu_xpart_layout
       layout->x_diff + 12 > layout->size || layout->x_diff_sort + 12 > layout->size ||
       layout->v_full + 12 > layout->size)
     return h->fail("upload_xparts: bad struct xpart layout");
+  if (layout->u_full >= 0 && layout->u_full + 4 > layout->size) return h->fail("upload_xparts: bad u_full offset");
   if (h->n_x != nparts || h->xlayout.size != layout->size) {
     cudaFree(h->d_xaos);
     h->d_xaos = nullptr;
@@ -1850,6 +1851,39 @@ extern "C" int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args
   if (flag) h->lists_built = false;
   /* device order, SoA columns, frames: from the drifted AoS copy */
   return transpose_in(h);
+}
+
+extern "C" int swiftgpu_run_kick(swiftgpu_t *h, int which, float minimal_internal_energy) {
+  if (!h || (which != 1 && which != 2)) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (!h->d_xaos) return h->fail("run_kick before upload_xparts");
+  if (h->xlayout.u_full < 0) return h->fail("run_kick: the xpart layout has no u_full / entropy_full offset");
+  if (!h->has_step) return h->fail("swiftgpu_set_step must be called before run_kick");
+  if (transpose_out(h)) return 1; /* a_hydro, u_dt | entropy_dt of the last step into the AoS copy */
+  KickArgs A;
+  A.aos = h->d_aos;
+  A.xaos = h->d_xaos;
+  A.D.L = h->cfg.layout;
+  A.D.scheme = h->cfg.scheme;
+  A.X = h->xlayout;
+  A.n = h->n_x;
+  A.which = which;
+  A.max_active_bin = h->step.max_active_bin;
+  A.time_base = h->step.time_base;
+  A.min_u = minimal_internal_energy;
+  const unsigned grid = (unsigned)((A.n + 255) / 256);
+  if (h->cfg.scheme == SCH_MINIMAL) k_kick<SCH_MINIMAL><<<grid, 256, 0, h->stream>>>(A);
+  else if (h->cfg.scheme == SCH_GADGET2) k_kick<SCH_GADGET2><<<grid, 256, 0, h->stream>>>(A);
+  else k_kick<SCH_SPHENIX><<<grid, 256, 0, h->stream>>>(A);
+  h->stats.n_launches++;
+  CK(cudaGetLastError());
+  /* the SoA columns follow the AoS copy: v, u and the force members changed (kick2); positions did
+   * not move, so the device order, frames and lists stay */
+  if (which == 2) return transpose_in(h);
+  /* kick1 leaves struct part untouched except a zeroed rate at the energy floor; the results of the
+   * last step are already in the AoS copy, which is now the current state */
+  h->phases_done = 0;
+  return 0;
 }
 
 extern "C" int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density, int32_t *n_gradient,

@@ -151,6 +151,10 @@ class SwiftGPU:
                           int(init_particles))
         self._ck(self.lib.swiftgpu_run_drift(self.h, C.byref(a)), "run_drift")
 
+    def run_kick(self, which, minimal_internal_energy=0.0):
+        """runner_do_kick1 (which=1) / runner_do_kick2 (which=2, + hydro_reset_predicted_values) on the device."""
+        self._ck(self.lib.swiftgpu_run_kick(self.h, int(which), float(minimal_internal_energy)), "run_kick")
+
     def download_counts(self):
         nd = np.zeros(self.nparts, np.int32)
         ng = np.zeros_like(nd)

@@ -456,6 +456,89 @@ def test_drift_matches_reference(scheme, active_fraction):
     o.close()
 
 
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_kick_and_resident_leapfrog_match_reference(scheme):
+    """SURVEY 8f row 4 (the kick half) and rows 2 + 4 together. (A) swiftgpu_run_kick against the
+    reference's own runner_do_kick2 / runner_do_kick1 (src/runner_time_integration.c:360,87: kick_part,
+    hydro_kick_extra, hydro_reset_predicted_values) from identical particles: struct xpart[] (v_full,
+    u_full | entropy_full) and the re-set v, u | entropy must be bit-identical, pressure and sound
+    speed within 1e-6. (B) three steps of a fixed-time-step leapfrog - kick1, drift, the hydro step,
+    kick2 - entirely from the device-resident state (no particle upload after the first) against the
+    reference doing the same with its own kicks, drift and loops: positions and velocities must agree
+    to rounding, the hydro fields within the parity bars of one step times the number of steps."""
+    from oracle import ref
+    from swift_b200.engine import SwiftGPU
+    if not ref.available(scheme):
+        pytest.skip("needs oracle/_ref (the reference's kicks and drift)")
+    ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.03, seed=41)
+    ic["time_bin"] = np.full_like(ic["time_bin"], 9)  # ti_step = 1024 -> dt = 1.024e-3
+    c = util.make_case(scheme, ic, (3, 3, 3))
+    ti_step = 1 << 10
+    dt = ti_step * c.step.time_base
+    o = ref.Reference(scheme, c.cfg, c.step, c.tree.cells, c.tree.top, c.parts)
+    o.run(threads=4)
+    start = o.parts()  # a full step: accelerations and rates exist
+    X = o.xpart_layout()
+    n = c.n
+    xp = np.zeros((n, X.size), np.uint8)
+    xp[:, X.v_full:X.v_full + 12] = np.ascontiguousarray(host.field(start, c.layout, "v").reshape(n, 3)).view(np.uint8).reshape(n, 12)
+    ent = "entropy" if scheme == "gadget2" else "u"
+    xp[:, X.u_full:X.u_full + 4] = np.ascontiguousarray(host.field(start, c.layout, ent)).view(np.uint8).reshape(n, 4)
+    xp = xp.ravel()
+    o.set_xparts(xp)
+
+    g = SwiftGPU(c.cfg)
+    g.upload_cells(c.tree.cells, c.tree.top)
+    g.upload_parts(start)
+    g.set_step(c.step)
+    g.upload_xparts(X, xp)
+
+    def compare_exact(tag):
+        got, got_x = g.download_parts(), g.download_xparts()
+        want, want_x = o.parts(), o.xparts()
+        assert np.array_equal(got_x, want_x), f"{tag}: struct xpart[] differs"
+        for name in ("x", "v", ent, "h"):
+            a, b = host.field(got, c.layout, name), host.field(want, c.layout, name)
+            assert np.array_equal(a, b), f"{tag}: {name}: {(a != b).sum()} values differ"
+        for name in ("soundspeed", "P_over_rho2" if scheme == "gadget2" else "pressure"):
+            a, b = host.field(got, c.layout, name).astype(np.float64), host.field(want, c.layout, name).astype(np.float64)
+            assert (np.abs(a - b) / np.maximum(np.abs(b), 1e-30)).max() < 1e-6, (tag, name)
+
+    # ---- (A) single kicks from identical states ----
+    o.kick(2)
+    g.run_kick(2)
+    compare_exact("kick2")
+    assert not np.array_equal(o.xparts(), xp), "the kick changed nothing"
+    o.kick(1)
+    g.run_kick(1)
+    compare_exact("kick1")
+
+    # ---- (B) leapfrog: [drift, step, kick2, kick1] x 3 from the device-resident state ----
+    nsteps = 3
+    for k in range(nsteps):
+        o.drift(c.step.ti_current - ti_step, 0.0, 1)
+        g.run_drift(dt, init_particles=1)
+        o.run(threads=4)
+        g.run_step(abi.PHASE_ALL)
+        if k + 1 < nsteps:
+            o.kick(2); g.run_kick(2)
+            o.kick(1); g.run_kick(1)
+    got, want = g.download_parts(), o.parts()
+    dx = np.abs(host.field(got, c.layout, "x") - host.field(want, c.layout, "x")).max()
+    moved = np.abs(host.field(want, c.layout, "x") - host.field(start, c.layout, "x")).max()
+    dv = np.abs(host.field(got, c.layout, "v") - host.field(want, c.layout, "v")).max()
+    print(scheme, "leapfrog: moved", moved, "max |dx|", dx, "max |dv|", dv)
+    assert moved > 1e-5 and dx < 1e-9 and dv < 2e-6
+    pp = util.run_port(c)  # floors of the cancelling sums (same box, first step: the scale is what matters)
+    rep = util.parity_report(got, want, c.layout, scheme, c.cfg.h_tolerance, time_base=c.step.time_base,
+                             alpha_max=c.cfg.viscosity_alpha_max, diffusion_beta=c.cfg.diffusion_beta,
+                             gross=pp.gross())
+    print({k: v for k, v in rep.items() if k != "_clean"})
+    util.assert_parity(rep, nsteps * TOL, h_tolerance=c.cfg.h_tolerance)
+    g.close()
+    o.close()
+
+
 def test_full_size_properties_clustered128_sphenix():
     """BASELINE config 2 shape (clustered lognormal box, SPHENIX, wide h range,
     multi-level tree) at 2 097 152 particles: properties that do not need the
