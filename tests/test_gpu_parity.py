@@ -471,10 +471,11 @@ def test_kick_and_resident_leapfrog_match_reference(scheme):
     if not ref.available(scheme):
         pytest.skip("needs oracle/_ref (the reference's kicks and drift)")
     ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.03, seed=41)
-    ic["time_bin"] = np.full_like(ic["time_bin"], 9)  # ti_step = 1024 -> dt = 1.024e-3
     c = util.make_case(scheme, ic, (3, 3, 3))
-    ti_step = 1 << 10
-    dt = ti_step * c.step.time_base
+    ti_step = 4  # time_bin 1 (timeline.h:59); ti_current = 8 is a step boundary of that bin
+    c.step.time_base = 2.56e-4
+    dt = ti_step * c.step.time_base  # 1.024e-3: a fifth of the CFL step of this box
+    assert (ic["time_bin"] == 1).all()
     o = ref.Reference(scheme, c.cfg, c.step, c.tree.cells, c.tree.top, c.parts)
     o.run(threads=4)
     start = o.parts()  # a full step: accelerations and rates exist
