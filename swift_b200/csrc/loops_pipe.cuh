@@ -126,10 +126,13 @@ enum { PM_NFR = 0, PM_NOCT = 1, PM_FLAG = 2, PM_TASK = 3, PM_TGT_OFF = 4, PM_NTG
 /* force payload lane of the exact hj^2 gamma^2 of the source (k_ghost / k_aos_to_soa keep it there) */
 #define PL_HG2_COL(SCHEME) ((SCHEME) == SCH_SPHENIX ? 3 : 2)
 
-#define PL_MIN_BLOCKS(CW) ((CW) >= 8 ? 2 : 4)
+#ifndef PL_BLOCKS_TYPE1
+#define PL_BLOCKS_TYPE1 2 /* CTAs per SM the 8-warp density / gradient kernels are compiled for (3: 72 registers) */
+#endif
+#define PL_MIN_BLOCKS(LOOP, CW) ((CW) >= 8 ? ((LOOP) == LOOP_FORCE ? 2 : PL_BLOCKS_TYPE1) : 4)
 
 template <int LOOP, int SCHEME, int NS, int CW, int DS, int SL = PL_SLOTS>
-__global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(CW)) k_pipe(const LoopArgs A) {
+__global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP, CW)) k_pipe(const LoopArgs A) {
   static_assert(SL % 8 == 0 && SL <= 256 && SL >= 64, "stage slots: whole octets, 8-bit slot field");
   constexpr bool FORCE = (LOOP == LOOP_FORCE);
   constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
