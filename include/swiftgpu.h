@@ -322,6 +322,21 @@ int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args);
  */
 int swiftgpu_run_kick(swiftgpu_t *h, int which, float minimal_internal_energy);
 
+/*
+ * The time-step limiter loop (the loop half):
+ * runner_dosub_self1_limiter / runner_dosub_pair1_limiter (runner_main.c:233,292;
+ * runner_doiact_functions_limiter.h) with runner_iact_nonsym_limiter
+ * (timestep_limiter_iact.h:106-117) - every particle within the kernel of a
+ * particle STARTING its step whose time bin lies more than
+ * time_bin_neighbour_max_delta_bin (2) above it gets limiter_data.wakeup =
+ * max(wakeup, -time_bin of the starter). Runs after the ghost (any time after
+ * the step) on the decomposition of the density loop; wakeup_offset =
+ * offsetof(struct part, limiter_data.wakeup). swiftgpu_download_parts returns
+ * the field with the particles. The follow-up runner_do_limiter (re-binning
+ * the woken particles) is the host's. Single rank only.
+ */
+int swiftgpu_run_limiter(swiftgpu_t *h, int32_t wakeup_offset);
+
 /* Per-particle directed interaction counts of the last density / gradient /
  * force loops (the reference's N_density/N_gradient/N_force debugging counters,
  * hydro/SPHENIX/hydro_iact.h:121-126, minus the self term). Any pointer may be

@@ -44,6 +44,7 @@ def load(variant):
         lib.swiftref_get_xparts.argtypes = [VP, VP]
         lib.swiftref_run_drift.argtypes = [VP, C.c_longlong, C.c_float, C.c_int]
         lib.swiftref_run_kick.argtypes = [VP, C.c_int, C.c_float]
+        lib.swiftref_run_limiter.argtypes = [VP, C.c_int]
         lib.swiftref_space_split.argtypes = [C.POINTER(abi.Config), C.POINTER(abi.Step), VP, C.c_longlong, VP, VP, VP, C.c_int]
         _libs[variant] = lib
     return _libs[variant]
@@ -138,6 +139,13 @@ class Reference:
     def kick(self, which, minimal_internal_energy=0.0):
         """The reference's runner_do_kick1 (which=1) / runner_do_kick2 (which=2) on every local top-level cell."""
         self.lib.swiftref_run_kick(self.h, int(which), float(minimal_internal_energy))
+
+    def wakeup_offset(self):
+        return int(self.lib.swiftref_wakeup_offset())
+
+    def limiter(self, threads=1):
+        """The reference's runner_dosub_{self,pair}1_limiter over the density tasks."""
+        self.lib.swiftref_run_limiter(self.h, int(threads))
 
     def sort(self, cell, sid):
         n = int(self._cells["count"][cell])

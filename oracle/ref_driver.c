@@ -421,7 +421,8 @@ enum ref_kind {
   K_GRADIENT,
   K_EXTRA_GHOST,
   K_FORCE,
-  K_END_FORCE
+  K_END_FORCE,
+  K_LIMITER
 };
 
 struct worker {
@@ -475,6 +476,12 @@ static void run_per_cell(struct worker *w, struct cell *c) {
   }
 }
 
+/* defined by src/runner_doiact_limiter.c (runner_doiact_functions_limiter.h:852,957) */
+void runner_dosub_self1_limiter(struct runner *r, struct cell *c, int recurse_below_h_max,
+                                const int gettimer);
+void runner_dosub_pair1_limiter(struct runner *r, struct cell *ci, struct cell *cj,
+                                int recurse_below_h_max, const int gettimer);
+
 static void run_task(struct worker *w, struct ref_task *t) {
   struct runner *r = &w->runner;
   struct cell *ci = t->t.ci, *cj = t->t.cj;
@@ -498,6 +505,12 @@ static void run_task(struct worker *w, struct ref_task *t) {
         runner_dosub_self2_force(r, ci, 0, 0);
       else
         runner_dosub_pair2_force(r, ci, cj, 0, 0);
+      break;
+    case K_LIMITER: /* runner_main.c:233-234,292-293 */
+      if (cj == NULL)
+        runner_dosub_self1_limiter(r, ci, /*below_h_max=*/0, 0);
+      else
+        runner_dosub_pair1_limiter(r, ci, cj, /*below_h_max=*/0, 0);
       break;
     default:
       break;
@@ -735,6 +748,17 @@ int swiftref_space_split(const swiftgpu_config *cfg, const swiftgpu_step *step, 
   free(s);
   free(e);
   return r < 0 ? -1 : nc;
+}
+
+/* ---- the time-step limiter loop: runner_dosub_{self,pair}1_limiter over the
+ * density tasks, after a step (sorts and h as the step left them) ---- */
+int swiftref_wakeup_offset(void) { return (int)offsetof(struct part, limiter_data.wakeup); }
+int swiftref_run_limiter(swiftref_t *s, int nthreads) {
+  for (int i = 0; i < s->ncells; i++) /* cell_is_starting_hydro: ti_beg_max == ti_current */
+    if (s->cells[i].hydro.ti_end_min == s->engine.ti_current)
+      s->cells[i].hydro.ti_beg_max = s->engine.ti_current;
+  run_kind(s, K_LIMITER, nthreads);
+  return 0;
 }
 
 /* ---- drift: the reference's own cell_drift_part ---- */

@@ -153,6 +153,7 @@ EXPORTS = [
     ("swiftgpu_download_xparts", C.c_int, [VP, VP, I64]),
     ("swiftgpu_run_drift", C.c_int, [VP, C.POINTER(DriftArgs)]),
     ("swiftgpu_run_kick", C.c_int, [VP, C.c_int, C.c_float]),
+    ("swiftgpu_run_limiter", C.c_int, [VP, I32]),
     ("swiftgpu_get_stats", C.c_int, [VP, C.POINTER(Stats)]),
     ("swiftgpu_download_sort", C.c_int, [VP, I32, I32, VP, VP, VP]),
     ("swiftgpu_worklist_stats", C.c_int, [C.POINTER(Config), C.POINTER(Step), VP, I32, VP, I32, C.c_int, VP]),

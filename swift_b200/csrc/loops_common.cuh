@@ -93,6 +93,7 @@ struct LoopArgs {
   float *f_hdt;
   float *f_vsig;
   int32_t *f_minngb;
+  int32_t *wakeup; /* limiter loop: limiter_data.wakeup of every particle (scatter, atomicMax) */
   int32_t *count; /* per-particle directed interaction counter of this loop */
   unsigned long long *total; /* global interaction counter */
   unsigned long long *tests; /* global distance-test counter */

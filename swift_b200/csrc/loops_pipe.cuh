@@ -65,6 +65,7 @@ namespace swiftgpu {
 #endif
 #define PL_OCT (PL_SLOTS / 8)
 #define PL_FRAGS 8 /* fragments (items) per stage */
+#define TIME_BIN_NEIGHBOUR_MAX_DELTA_BIN 2 /* timeline.h:51 */
 #define PL_TARGETS 64 /* targets of a task of the 8-warp kernel (8 per consumer warp) */
 #ifndef PL_SPARSE_CW
 #define PL_SPARSE_CW 4 /* consumer warps of the variant for sparse target sets: tasks of 8 * PL_SPARSE_CW targets */
@@ -399,7 +400,8 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP, CW)) k_pipe
           const uint32_t n16 = (uint32_t)my_n * 16u;
           tma_load(F + my_pool, A.frames + ((size_t)(uint32_t)aux.z + (size_t)my_off), n16, sFull + s);
           float4 *P = (float4 *)(st + SM::kStageP);
-          tma_load(P + my_pool, A.mv + first, n16, sFull + s);
+          /* first payload column: (m, v) - the limiter loop only needs the source's time_bin (fq2.w) */
+          tma_load(P + my_pool, (LOOP == LOOP_LIMITER ? A.fq2 : A.mv) + first, n16, sFull + s);
           bytes = 2u * n16;
           if (LOOP == LOOP_GRADIENT) {
             tma_load(P + SL + my_pool, A.gq + first, n16, sFull + s);
@@ -589,7 +591,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP, CW)) k_pipe
 
   /* my target of the current task (4 lanes share one) */
   bool tvalid = false;
-  int ti = -1, tdepth = 0;
+  int ti = -1, tdepth = 0, ttb = 0;
   double tx = 0., ty = 0., tz = 0.;
   float th = 1.f, tvx = 0.f, tvy = 0.f, tvz = 0.f, tu = 0.f, tcs = 0.f;
   float thg2 = 0.f, th_inv = 1.f, thg = 0.f, tsure2 = 0.f, r2e = 0.f;
@@ -663,6 +665,9 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP, CW)) k_pipe
           const float4 f0 = P[sl];
           if (LOOP == LOOP_DENSITY) {
             iact_density(dacc, r2, dx, dy, dz, th_inv, tvx, tvy, tvz, f0.x, f0.y, f0.z, f0.w);
+          } else if (LOOP == LOOP_LIMITER) {
+            /* runner_iact_nonsym_limiter, timestep_limiter_iact.h:106-117: wake up the neighbour? */
+            if (__float_as_int(f0.w) > ttb + TIME_BIN_NEIGHBOUR_MAX_DELTA_BIN) atomicMax(&A.wakeup[gi], -ttb);
           } else {
             const float4 f1 = P[SL + sl];
             iact_gradient(gacc, r2, dx, dy, dz, th, tvx, tvy, tvz, tu, tcs, f0.x, f0.y, f0.z, f0.w,
@@ -764,6 +769,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP, CW)) k_pipe
           th = tq.h;
         } else {
           th = A.h[ti];
+          if (LOOP == LOOP_LIMITER) ttb = A.time_bin[ti];
           if (LOOP == LOOP_GRADIENT) {
             tu = A.fq2[ti].z;
             tcs = A.fq1[ti].w;
@@ -987,7 +993,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP, CW)) k_pipe
         atomicAdd(&A.g_lap[ti], gacc.laplace_u);
         atomic_max_pos(&A.g_amax[ti], gacc.alpha_max);
       }
-    } else {
+    } else if (FORCE) {
 #pragma unroll
       for (int o = 8; o < 32; o <<= 1) {
         facc.ax += __shfl_xor_sync(FULL_MASK, facc.ax, o);
@@ -1009,7 +1015,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), PL_MIN_BLOCKS(LOOP, CW)) k_pipe
         atomicMin(&A.f_minngb[ti], facc.min_ngb);
       }
     }
-    if (tvalid && s4 == 0 && nh) atomicAdd(&A.count[ti], nh);
+    if (LOOP != LOOP_LIMITER && tvalid && s4 == 0 && nh) atomicAdd(&A.count[ti], nh);
     nhit_all += nhit;
   }
   int tot = nhit_all, tt = ntests;

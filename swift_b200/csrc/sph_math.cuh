@@ -25,7 +25,7 @@
 namespace swiftgpu {
 
 enum { SCH_MINIMAL = 0, SCH_GADGET2 = 1, SCH_SPHENIX = 2 };
-enum { LOOP_DENSITY = 0, LOOP_GRADIENT = 1, LOOP_FORCE = 2 };
+enum { LOOP_DENSITY = 0, LOOP_GRADIENT = 1, LOOP_FORCE = 2, LOOP_LIMITER = 3 };
 
 /* kernel_hydro.h:41-55,205-237 (cubic spline, 3D); values pinned against the
  * reference build in tests/golden/reference_constants.json. */

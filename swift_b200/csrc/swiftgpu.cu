@@ -105,6 +105,7 @@ struct swiftgpu_handle {
   bool gradient_own = false; /* L_gradient was rebuilt after the ghost (else the density list is used) */
   char *d_aos = nullptr;
   char *d_xaos = nullptr; /* device copy of the caller's struct xpart[] (drift) */
+  int32_t *d_wakeup = nullptr; /* limiter loop: limiter_data.wakeup per particle, device order */
   swiftgpu_xpart_layout xlayout = {0, 0, 0, 0, -1};
   int64_t n_x = 0;
   size_t aos_bytes = 0;
@@ -299,6 +300,8 @@ extern "C" int swiftgpu_init(swiftgpu_t **out, const swiftgpu_config *cfg) {
 }
 
 static void free_parts(H *h) {
+  cudaFree(h->d_wakeup);
+  h->d_wakeup = nullptr;
   cudaFree(h->d_xaos);
   h->d_xaos = nullptr;
   h->n_x = 0;
@@ -1036,6 +1039,7 @@ static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
   A.dA = h->dA; A.dB = h->dB; A.g_vsig = h->g_vsig; A.g_lap = h->g_lap; A.g_amax = h->g_amax;
   A.fo1 = h->fo1; A.f_hdt = h->f_hdt; A.f_vsig = h->f_vsig; A.f_minngb = h->f_minngb;
   A.count = count;
+  A.wakeup = h->d_wakeup;
   A.total = h->d_counters + counter;
   A.tests = h->d_counters + 8 + counter;
   for (int k = 0; k < 3; k++) A.dim[k] = h->cfg.dim[k];
@@ -1241,6 +1245,9 @@ static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
  * re-runs, few active particles) is served by fewer warps per task and more tasks in flight */
 template <int LOOP, bool SUBSET, int SCHEME>
 static cudaError_t launch_pipe(H *h, const LoopArgs &A, bool small = false) {
+  if (LOOP == LOOP_LIMITER)
+    return small ? launch_pipe_ns<LOOP_LIMITER, 0, PL_NS_SPARSE, 64, PL_SPARSE_CW>(h, A)
+                 : launch_pipe_ns<LOOP_LIMITER, 0, PL_NS_DENSITY, 64>(h, A);
   if (small) {
     if (LOOP == LOOP_FORCE) return launch_pipe_ns<LOOP_FORCE, SCHEME, PL_NS_SPARSE_FORCE, 64, PL_SPARSE_CW>(h, A);
     if (LOOP == LOOP_GRADIENT) return launch_pipe_ns<LOOP_GRADIENT, 0, PL_NS_SPARSE, 64, PL_SPARSE_CW>(h, A);
@@ -1883,6 +1890,59 @@ extern "C" int swiftgpu_run_kick(swiftgpu_t *h, int which, float minimal_interna
   /* kick1 leaves struct part untouched except a zeroed rate at the energy floor; the results of the
    * last step are already in the AoS copy, which is now the current state */
   h->phases_done = 0;
+  return 0;
+}
+
+/* ---- the time-step limiter loop (runner_doiact_limiter.h) ---- */
+__global__ void k_limiter_io(char *aos, int part_size, int off, const int32_t *d2h, int64_t n, int64_t n_host,
+                             int32_t *wakeup, int store) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int64_t row = d2h[p];
+  if (row >= n_host) {
+    if (!store) wakeup[p] = -56; /* time_bin_not_awake, timeline.h:48 */
+    return;
+  }
+  char *b = aos + (size_t)part_size * (size_t)row;
+  if (store)
+    *(int8_t *)(b + off) = (int8_t)wakeup[p];
+  else
+    wakeup[p] = *(const int8_t *)(b + off);
+}
+
+/* runner_dosub_{self,pair}1_limiter (runner_main.c:233,292 -> runner_doiact_functions_limiter.h): the
+ * density decomposition (cell.h:951,992 on the h_max_active the ghost left), targets = the particles
+ * starting their step, r2 < h_i^2 gamma^2, and runner_iact_nonsym_limiter: a neighbour more than
+ * time_bin_neighbour_max_delta_bin bins above the target gets limiter_data.wakeup =
+ * max(wakeup, -time_bin_i) - a scatter, done with atomicMax. wakeup_offset =
+ * offsetof(struct part, limiter_data.wakeup); the time bins are those of the last upload. */
+extern "C" int swiftgpu_run_limiter(swiftgpu_t *h, int32_t wakeup_offset) {
+  if (!h) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (wakeup_offset < 0 || wakeup_offset >= h->cfg.layout.size) return h->fail("run_limiter: bad wakeup offset");
+  if (h->cfg.nranks > 1) return h->fail("run_limiter: single rank only (woken-up proxies are not sent back)");
+  if (loop_kind() != 3) return h->fail("run_limiter needs the frame pipeline");
+  if (!(h->phases_done & SWIFTGPU_PHASE_GHOST)) return h->fail("run_limiter before run_ghost");
+  if (phase_begin(h)) return 1;
+  if (revalidate_list(h, LISTS_GRADIENT)) return 1; /* the loop-1 predicates on the post-ghost h_max_active */
+  DevList &L = h->gradient_own ? h->L_gradient : h->L_density;
+  if (build_targets(h, L)) return 1;
+  const int64_t n = h->n, nh = h->n_host > 0 ? h->n_host : h->n;
+  if (!h->d_wakeup) CK(cudaMalloc((void **)&h->d_wakeup, sizeof(int32_t) * (size_t)n));
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  k_limiter_io<<<grid, 256, 0, h->stream>>>(h->d_aos, h->cfg.layout.size, wakeup_offset, h->d_d2h, n, nh,
+                                          h->d_wakeup, 0);
+  h->stats.n_launches++;
+  CK(cudaMemsetAsync(h->d_counters + 11, 0, sizeof(unsigned long long), h->stream));
+  if (L.ntasks > 0) {
+    /* counter slot 3: the loop credits no interaction (total untouched), its distance tests go to slot 11 */
+    if (run_pipe_loop<LOOP_LIMITER, false, 0>(h, L, nullptr, 3, h->d_counters + 12, 0, main_split(), h->d_counters + 13))
+      return 1;
+  }
+  k_limiter_io<<<grid, 256, 0, h->stream>>>(h->d_aos, h->cfg.layout.size, wakeup_offset, h->d_d2h, n, nh,
+                                          h->d_wakeup, 1);
+  h->stats.n_launches++;
+  CK(cudaGetLastError());
   return 0;
 }
 

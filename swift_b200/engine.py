@@ -155,6 +155,10 @@ class SwiftGPU:
         """runner_do_kick1 (which=1) / runner_do_kick2 (which=2, + hydro_reset_predicted_values) on the device."""
         self._ck(self.lib.swiftgpu_run_kick(self.h, int(which), float(minimal_internal_energy)), "run_kick")
 
+    def run_limiter(self, wakeup_offset):
+        """runner_dosub_{self,pair}1_limiter: wake-up flags (limiter_data.wakeup at `wakeup_offset` of struct part)."""
+        self._ck(self.lib.swiftgpu_run_limiter(self.h, int(wakeup_offset)), "run_limiter")
+
     def download_counts(self):
         nd = np.zeros(self.nparts, np.int32)
         ng = np.zeros_like(nd)

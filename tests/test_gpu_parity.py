@@ -540,6 +540,51 @@ def test_kick_and_resident_leapfrog_match_reference(scheme):
     o.close()
 
 
+@pytest.mark.parametrize("scheme", ("gadget2", "sphenix"))
+def test_limiter_loop_matches_reference(scheme):
+    """SURVEY 8f row 4 (the loop half): the time-step limiter loop runner_dosub_{self,pair}1_limiter
+    (src/runner_doiact_functions_limiter.h) with runner_iact_nonsym_limiter
+    (src/timestep_limiter_iact.h:106-117) after a multi-time-step step: every particle inside the
+    kernel of a starting particle whose time bin lies more than 2 above it gets
+    limiter_data.wakeup = max(wakeup, -time_bin of the starter). Integer output: must be identical
+    to the reference's own loop for every particle (woken or not), through the C ABI with the
+    offsetof() of the member."""
+    from oracle import ref
+    if not ref.available(scheme):
+        pytest.skip("needs oracle/_ref (the reference's limiter loop)")
+    ic = host.jittered_box(16, abi.SCHEMES[scheme], jitter=0.2, h_scatter=0.05, seed=51, active_fraction=0.3)
+    rng = np.random.default_rng(8)
+    inactive_ic = ic["time_bin"] > 1
+    ic["time_bin"] = np.where(inactive_ic, rng.choice(np.array([3, 4, 6], dtype=np.int8), size=inactive_ic.size), 1).astype(np.int8)
+    c = util.make_case(scheme, ic, (3, 3, 3), max_active_bin=1)
+    c_all = util.make_case(scheme, dict(ic, time_bin=np.ones_like(ic["time_bin"])), (3, 3, 3))
+    o_all, _ = util.run_oracle(c_all)
+    c.parts = o_all.parts()
+    o_all.close()
+    n, size = c.n, c.layout.size
+    tb = host.field(c.parts, c.layout, "time_bin")
+    tb[:] = ic["time_bin"][c.tree.perm]
+    o = ref.Reference(scheme, c.cfg, c.step, c.tree.cells, c.tree.top, c.parts)
+    off = o.wakeup_offset()
+    c.parts.reshape(n, size)[:, off] = np.uint8(256 - 56)  # time_bin_not_awake = -56 (timeline.h:48)
+    o.set_parts(c.parts)
+    o.run(threads=4)
+    o.limiter(threads=4)
+    want = o.parts().reshape(n, size)[:, off].view(np.int8)
+    g = util.run_gpu(c)
+    g.run_limiter(off)
+    got = g.download_parts().reshape(n, size)[:, off].view(np.int8)
+    woken = want != -56
+    assert woken.sum() > 50, "the reference woke nobody up: the test is vacuous"
+    assert (tb[woken] > 3).all() and (want[woken] == -1).all()
+    assert (tb == 3).any() and not woken[tb == 3].any()  # exactly 2 bins above: not woken
+    assert np.array_equal(got, want), f"{(got != want).sum()} wakeup flags differ"
+    # the rest of the step's results are untouched by the loop
+    _check(c, g)
+    g.close()
+    o.close()
+
+
 def test_full_size_properties_clustered128_sphenix():
     """BASELINE config 2 shape (clustered lognormal box, SPHENIX, wide h range,
     multi-level tree) at 2 097 152 particles: properties that do not need the
