@@ -317,8 +317,8 @@ int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args);
  * sound speed, v_sig from the full-step values). Works on the device copies of
  * struct part[] / struct xpart[] like the drift; together with it and
  * swiftgpu_run_step a fixed-time-step leapfrog runs without the particles
- * crossing the host boundary. Not covered: the time-step limiter loop, the
- * assignment of new time bins (runner_do_timestep), cosmological kick factors.
+ * crossing the host boundary. Not covered: the assignment of new time bins
+ * (runner_do_timestep), cosmological kick factors.
  */
 int swiftgpu_run_kick(swiftgpu_t *h, int which, float minimal_internal_energy);
 
