@@ -344,6 +344,31 @@ def newest_traffic(workload, kernel, loop):
     return best
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: pin the process (and with it the pages of its pinned host buffers, which are
+    placed by first touch) to the CPUs of the NUMA node the rank's GPU hangs off, so that the eight
+    ranks' host<->device copies do not all cross one socket's memory controller. Returns the node or
+    None when the topology cannot be read (nothing is changed then)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def halo_parity_check(world, rank, local_rank, nccl_id):
     """Multi-GPU correctness seen on the driver box: a 64^3 SPHENIX box split over the ranks (halo
     exchanges inside run_step, local particles only across the host boundary) against the SAME box run
@@ -416,6 +441,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libswiftgpu has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -647,7 +673,8 @@ def main():
                    "ghost_iterations": int(st.ghost_iterations)},
         "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": n_local * psize,
                 "d2h_bytes_per_step": n_local * psize, "ms_per_step": (ms_e2e / args.steps) if e2e_value else None,
-                "note": "per GPU: the rank's own particles through the C ABI (pinned host AoS in and out); proxies by NCCL"},
+                "note": "per GPU: the rank's own particles through the C ABI (pinned host AoS in and out); proxies by NCCL"
+                        + ("; rank 0 bound to NUMA node %d of its GPU" % numa if numa is not None else "")},
         "gpu_launches": int(launches),
         "interactions_per_step": useful_all, "interactions_incl_ghost_reruns": executed_all,
         "phase_ms": {k: v / args.steps for k, v in phase_ms.items()},
