@@ -413,331 +413,7 @@ static cudaError_t to_device(T **dst, const std::vector<T> &v) {
   return e;
 }
 
-/* The frame array an item reads: the source cell's particles relative to the
- * origin of the reference's leaf-level call (functions_hydro.h:1327-1338).
- * slot 0 = the cell's own frame (x - loc): sources of DOPAIR when the cell is
- * the right cell cj, DOSELF_SUBSET, and the prefilter frame of the double
- * modes; slot 1 + sid = x - (cj->loc + shift) when the cell is the left cell ci
- * of a pair of orientation sid. Frames are shared by all lists. */
-static uint32_t frame_of(H *h, const Item &it) {
-  const int slot = it.mode == MODE_PAIR_R ? 1 + it.sid : 0;
-  const swiftgpu_cell &sc = h->cells[it.scell];
-  double o[3];
-  for (int k = 0; k < 3; k++) {
-    if (slot == 0)
-      o[k] = sc.loc[k];
-    else /* the targets' cell is cj: origin cj->loc + shift, as the device derives it */
-      o[k] = h->cells[it.tcell].loc[k] + (double)it.shift[k] * h->cfg.dim[k];
-  }
-  int32_t &idx = h->frame_idx[(size_t)it.scell * 14 + slot];
-  if (idx >= 0) {
-    const H::FrameRec &F = h->frames_host[idx];
-    if (F.o[0] == o[0] && F.o[1] == o[1] && F.o[2] == o[2]) return F.off;
-    /* same (cell, orientation) with another origin (tiny periodic grids): look for it, else append */
-    for (size_t k = 0; k < h->frames_host.size(); k++) {
-      const H::FrameRec &E = h->frames_host[k];
-      if (E.first == (int32_t)sc.first_part && E.count == sc.count && E.o[0] == o[0] && E.o[1] == o[1] &&
-          E.o[2] == o[2])
-        return E.off;
-    }
-  }
-  H::FrameRec F;
-  F.first = (int32_t)sc.first_part;
-  F.count = sc.count;
-  for (int k = 0; k < 3; k++) F.o[k] = o[k];
-  F.off = (uint32_t)h->frames_total;
-  F.pad = 0;
-  h->frames_total += (uint64_t)sc.count;
-  if (idx < 0) idx = (int32_t)h->frames_host.size();
-  h->frames_host.push_back(F);
-  h->frames_valid = false;
-  return F.off;
-}
-
-static int loop_kind();
-/* targets per entry of the host task list: the frame pipeline has a variant with small tasks for
- * sparse target sets and cuts the list for it (k_task_recs of a launch with larger tasks uses its head) */
-static int task_list_chunk() { return loop_kind() == 3 ? 8 * PL_SPARSE_CW : TASK_TARGETS; }
-static int upload_list(H *h, const WorkList &W, DevList &D, bool subset) {
-  D.release();
-  D.ngroups = (int)W.groups.size();
-  D.nitems = W.items.size();
-  std::vector<int32_t> tg, tc, tfirst(std::max<size_t>(W.groups.size(), 1));
-  /* Heaviest groups first (LPT) so that the tail of the launch is short. */
-  std::vector<int32_t> order(W.groups.size());
-  for (size_t g = 0; g < order.size(); g++) order[g] = (int32_t)g;
-  std::stable_sort(order.begin(), order.end(),
-                   [&](int32_t a, int32_t b) { return W.groups[a].cost > W.groups[b].cost; });
-  int64_t tot = 0;
-  for (size_t g = 0; g < W.groups.size(); g++) {
-    const swiftgpu_cell &c = h->cells[W.groups[g].tcell];
-    /* subset lists address the redo list by the leaf's own particle range */
-    tfirst[g] = subset ? (int32_t)c.first_part : (int32_t)tot;
-    tot += c.count;
-  }
-  for (int32_t g : order) {
-    const swiftgpu_cell &c = h->cells[W.groups[g].tcell];
-    const int tt = task_list_chunk();
-    const int nch = (c.count + tt - 1) / tt;
-    for (int k = 0; k < nch; k++) {
-      tg.push_back(g);
-      tc.push_back(k);
-    }
-  }
-  D.ntasks = (int)tg.size();
-  D.tgt_total = subset ? h->n : tot;
-  std::vector<Item> items(W.items);
-  for (Item &it : items) it.sframe = frame_of(h, it);
-  if (h->frames_total > 0xfffffff0ull) return h->fail("frame arrays exceed 2^32 entries");
-  CK(to_device(&D.items, items));
-  CK(to_device(&D.groups, W.groups));
-  CK(to_device(&D.task_group, tg));
-  CK(to_device(&D.task_chunk, tc));
-  CK(to_device(&D.tgt_first, tfirst));
-  CK(cudaMalloc((void **)&D.tgt_count, std::max(D.ngroups, 1) * sizeof(int32_t)));
-  CK(cudaMemset(D.tgt_count, 0, std::max(D.ngroups, 1) * sizeof(int32_t)));
-  CK(cudaMalloc((void **)&D.tgt_list, std::max<int64_t>(D.tgt_total, 1) * sizeof(int32_t)));
-  CK(cudaMalloc((void **)&D.task_recs, std::max(D.ntasks, 1) * sizeof(TaskRec)));
-  return 0;
-}
-
-/* Which lists build_lists() (re)builds. LISTS_ALL starts from the uploaded cells
- * (the gradient loop then shares the density list); the other two rebuild one
- * list after the ghost changed a recursion predicate it depends on, with the
- * h_max / h_max_active the device holds now. */
-enum { LISTS_ALL = 0, LISTS_FORCE = 1, LISTS_GRADIENT = 2 };
-
-static int pull_cell_hmax(H *h, std::vector<float> &hm, std::vector<float> &hma) {
-  hm.resize(h->ncells);
-  hma.resize(h->ncells);
-  float *d_tmp = h->d_hmax_tmp;
-  k_get_cell_hmax<<<(h->ncells + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->ncells, d_tmp,
-                                                                  d_tmp + h->ncells);
-  h->stats.n_launches++;
-  CK(cudaMemcpyAsync(hm.data(), d_tmp, sizeof(float) * h->ncells, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(hma.data(), d_tmp + h->ncells, sizeof(float) * h->ncells, cudaMemcpyDeviceToHost,
-                     h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  h->stats.n_host_syncs++;
-  return 0;
-}
-
-/* Builds worklists, the device cell table and the sort segments. */
-static int build_lists(H *h, int which) {
-  if (!h->has_step) return h->fail("swiftgpu_set_step must be called before running a phase");
-  if (h->cells.empty()) return h->fail("no cells uploaded");
-  if (h->n <= 0) return h->fail("no particles uploaded");
-  cudaSetDevice(h->cfg.device);
-  /* after the ghost: the recursion sees the h_max / h_max_active the device holds */
-  std::vector<float> hm, hma;
-  std::vector<swiftgpu_cell> saved;
-  if (which != LISTS_ALL) {
-    if (!h->d_cells) return h->fail("list rebuild before the first build");
-    if (pull_cell_hmax(h, hm, hma)) return 1;
-    saved = h->cells;
-    for (int c = 0; c < h->ncells; c++) {
-      h->cells[c].h_max = hm[c];
-      h->cells[c].h_max_active = hma[c];
-    }
-  }
-  Flattener F(h->cells.data(), h->ncells, h->top.data(), (int)h->top.size(), h->cfg.dim,
-              h->cfg.periodic, h->cfg.rank, h->step.ti_current);
-  WorkList Wd, Ws, Wf, Wg;
-  if (which == LISTS_ALL) {
-    h->frames_host.clear();
-    h->frame_idx.assign((size_t)h->ncells * 14, -1);
-    h->frames_total = 0;
-    h->frames_valid = false;
-    F.build_loop(0, Wd);
-    std::vector<int32_t> aux;
-    F.build_subset(Ws, aux);
-    h->req_density = Wd.sort_requests;
-    h->req_subset = Ws.sort_requests;
-    h->req_gradient.clear();
-    h->loop1_bits.resize(h->ncells);
-    for (int c = 0; c < h->ncells; c++)
-      h->loop1_bits[c] = (uint8_t)((Flattener::subpair1(h->cells[c]) ? 1 : 0) |
-                                   (Flattener::subself1(h->cells[c]) ? 2 : 0));
-  }
-  if (which == LISTS_ALL || which == LISTS_FORCE) {
-    F.build_loop(2, Wf);
-    h->req_force = Wf.sort_requests;
-    h->force_bits.resize(h->ncells);
-    for (int c = 0; c < h->ncells; c++)
-      h->force_bits[c] = (uint8_t)((Flattener::subpair2(h->cells[c]) ? 1 : 0) |
-                                   (Flattener::subself2(h->cells[c]) ? 2 : 0));
-  }
-  if (which == LISTS_GRADIENT) {
-    F.build_loop(1, Wg);
-    h->req_gradient = Wg.sort_requests;
-    std::vector<uint8_t> gb(h->ncells);
-    for (int c = 0; c < h->ncells; c++)
-      gb[c] = (uint8_t)((Flattener::subpair1(h->cells[c]) ? 1 : 0) | (Flattener::subself1(h->cells[c]) ? 2 : 0));
-    CK(to_device(&h->d_grad_bits, gb));
-  }
-  /* the host copy keeps the uploaded (pre-ghost) values for the density and
-   * subset recursions of a later re-run */
-  if (which != LISTS_ALL)
-    for (int c = 0; c < h->ncells; c++) {
-      h->cells[c].h_max = saved[c].h_max;
-      h->cells[c].h_max_active = saved[c].h_max_active;
-    }
-
-  /* sort segments: union of the requests of all lists */
-  std::vector<uint64_t> req(h->req_density);
-  req.insert(req.end(), h->req_subset.begin(), h->req_subset.end());
-  req.insert(req.end(), h->req_gradient.begin(), h->req_gradient.end());
-  req.insert(req.end(), h->req_force.begin(), h->req_force.end());
-  std::sort(req.begin(), req.end());
-  req.erase(std::unique(req.begin(), req.end()), req.end());
-
-  std::vector<DevCell> dc(h->ncells);
-  for (int c = 0; c < h->ncells; c++) {
-    const swiftgpu_cell &s = h->cells[c];
-    DevCell &d = dc[c];
-    memset(&d, 0, sizeof(d));
-    for (int k = 0; k < 3; k++) d.loc[k] = s.loc[k];
-    if (s.first_part + s.count > 0x7fffffffLL) return h->fail("more than 2^31 particles per GPU");
-    d.first = (int32_t)s.first_part;
-    d.count = s.count;
-    d.h_max = s.h_max;
-    d.h_max_active = s.h_max_active;
-    d.dx_max_sort = s.dx_max_sort;
-    d.h_max_allowed = s.h_max_allowed;
-    d.h_min_allowed = s.h_min_allowed;
-    d.parent = s.parent;
-    d.sort_base = -1;
-    d.sort_mask = 0;
-    d.depth = (int8_t)s.depth;
-    d.width = (float)std::max(s.width[0], std::max(s.width[1], s.width[2]));
-    d.dx_max_part = s.dx_max_part;
-    d.flags = (uint8_t)((s.ti_end_min == h->step.ti_current ? 1 : 0) |
-                        (s.nodeID == h->cfg.rank ? 2 : 0) | (s.split ? 4 : 0));
-  }
-  std::vector<SortSeg> segs;
-  std::vector<int32_t> ext_cells;
-  segs.reserve(req.size());
-  int64_t off = 0;
-  int max_seg = 0;
-  for (uint64_t r : req) {
-    const int c = (int)(r >> 4), sid = (int)(r & 15);
-    if (dc[c].sort_base < 0) {
-      dc[c].sort_base = off;
-      dc[c].seg_base = (int32_t)segs.size();
-      ext_cells.push_back(c);
-    }
-    dc[c].sort_mask |= (uint16_t)(1u << sid);
-    SortSeg s;
-    s.cell = c;
-    s.sid = sid;
-    s.off = off;
-    segs.push_back(s);
-    off += dc[c].count;
-    max_seg = std::max(max_seg, dc[c].count);
-  }
-  /* A list rebuilt after the ghost keeps the h_max the device already holds
-   * (it is newer than the host copy). */
-  if (which != LISTS_ALL)
-    for (int c = 0; c < h->ncells; c++) {
-      dc[c].h_max = hm[c];
-      dc[c].h_max_active = hma[c];
-    }
-  if (which == LISTS_ALL) {
-    /* pristine table first (uploaded h_max), then the live one */
-    std::vector<DevCell> dc0(dc);
-    for (int c = 0; c < h->ncells; c++) {
-      dc0[c].h_max = h->cells_uploaded_hmax(c);
-      dc0[c].h_max_active = h->cells_uploaded_hmax_active(c);
-    }
-    CK(to_device(&h->d_cells_init, dc0));
-    std::vector<float> dmin(h->ncells), dxp(h->ncells), dxpo(h->ncells);
-    for (int c = 0; c < h->ncells; c++) {
-      dmin[c] = h->cells[c].dmin;
-      dxp[c] = h->cells[c].dx_max_part;
-      dxpo[c] = h->cells[c].dx_max_part_old;
-    }
-    CK(to_device(&h->d_dmin, dmin));
-    CK(to_device(&h->d_dxp, dxp));
-    CK(to_device(&h->d_dxp_old, dxpo));
-    cudaFree(h->d_hmax_tmp);
-    h->d_hmax_tmp = nullptr;
-    CK(cudaMalloc((void **)&h->d_hmax_tmp, 2 * sizeof(float) * std::max(h->ncells, 1)));
-  } else {
-    /* the pristine table must know the new segments too (run_density copies it over the live one) */
-    std::vector<DevCell> dc0(dc);
-    for (int c = 0; c < h->ncells; c++) {
-      dc0[c].h_max = h->cells_uploaded_hmax(c);
-      dc0[c].h_max_active = h->cells_uploaded_hmax_active(c);
-    }
-    CK(to_device(&h->d_cells_init, dc0));
-  }
-  CK(to_device(&h->d_cells, dc));
-  {
-    /* octet boxes of every cell (tile pipeline) */
-    std::vector<int32_t> bf(h->ncells);
-    int64_t nb = 0;
-    for (int c = 0; c < h->ncells; c++) {
-      bf[c] = (int32_t)nb;
-      nb += (dc[c].count + 7) / 8;
-    }
-    if (nb > 0x7fffffffLL) return h->fail("too many octet boxes");
-    if (which == LISTS_ALL) CK(to_device(&h->d_box_first, bf));
-    if (nb != h->nboxes || !h->boxes) {
-      cudaFree(h->boxes);
-      h->boxes = nullptr;
-      CK(cudaMalloc((void **)&h->boxes, std::max<int64_t>(nb, 1) * 2 * sizeof(float4)));
-      h->nboxes = nb;
-      h->sorted = false;
-    }
-  }
-  CK(to_device(&h->d_segs, segs));
-  h->nsegs = (int)segs.size();
-  CK(to_device(&h->d_ext_cells, ext_cells));
-  h->n_ext_cells = (int)ext_cells.size();
-  cudaFree(h->d_ext);
-  h->d_ext = nullptr;
-  CK(cudaMalloc((void **)&h->d_ext, std::max<size_t>(segs.size(), 1) * sizeof(float2)));
-  h->full_sorted = false;
-  if (off != h->sort_total || !h->sort_idx) {
-    cudaFree(h->sort_idx);
-    h->sort_idx = nullptr;
-    CK(cudaMalloc((void **)&h->sort_idx, std::max<int64_t>(off, 1) * sizeof(uint32_t)));
-    h->sort_total = off;
-    cudaFree(h->d_sort_keys);
-    h->d_sort_keys = nullptr;
-  }
-  if (max_seg > SORT_SMEM_MAX && !h->d_sort_keys)
-    CK(cudaMalloc((void **)&h->d_sort_keys, std::max<int64_t>(off, 1) * sizeof(float)));
-  h->ext_valid = false; /* the key extrema follow the segments */
-  if (which == LISTS_ALL) h->sorted = false;
-
-  if (which == LISTS_ALL) {
-    if (upload_list(h, Wd, h->L_density, false)) return 1;
-    if (upload_list(h, Ws, h->L_subset, true)) return 1;
-    h->L_gradient.release();
-    h->gradient_own = false;
-    CK(to_device(&h->d_loop1_bits, h->loop1_bits));
-  }
-  if (which == LISTS_ALL || which == LISTS_FORCE) {
-    if (upload_list(h, Wf, h->L_force, false)) return 1;
-    CK(to_device(&h->d_force_bits, h->force_bits));
-  }
-  if (which == LISTS_GRADIENT) {
-    if (upload_list(h, Wg, h->L_gradient, false)) return 1;
-    h->gradient_own = true;
-  }
-  h->lists_built = true;
-  return 0;
-}
-
-static int transpose_in(H *h);
-static int ensure_lists(H *h) {
-  /* new cells after the particles were transposed: redo the device order from
-   * the AoS copy (the step restarts from the uploaded particle state) */
-  if (h->perm_stale && h->d_aos && h->n > 0 && transpose_in(h)) return 1;
-  if (h->lists_built) return 0;
-  return build_lists(h, LISTS_ALL);
-}
+#include "lists_host.inl" /* frame_of, upload_list, pull_cell_hmax, build_lists, ensure_lists */
 
 static int alloc_parts(H *h, int64_t n) {
   if (h->n == n && h->x) return 0;
@@ -1005,347 +681,7 @@ extern "C" int swiftgpu_run_sort(swiftgpu_t *h) {
   return phase_end(h, &h->stats.ms_sort);
 }
 
-static LoopArgs loop_args(H *h, const DevList &D, int32_t *count, int counter) {
-  LoopArgs A;
-  memset(&A, 0, sizeof(A));
-  A.cells = h->d_cells;
-  A.items = D.items;
-  A.groups = D.groups;
-  A.task_group = D.task_group;
-  A.task_chunk = D.task_chunk;
-  A.ntasks = D.ntasks;
-  A.tgt_list = D.tgt_list;
-  A.tgt_first = D.tgt_first;
-  A.tgt_count = D.tgt_count;
-  A.sort_idx = h->sort_idx;
-  A.ext = h->d_ext;
-  A.x = h->x; A.mv = h->mv; A.h = h->hh; A.depth_h = h->depth_h; A.time_bin = h->time_bin;
-  A.fq1 = h->fq1; A.fq2 = h->fq2; A.fq3 = h->fq3;
-  A.xf = h->xf; A.xs0 = h->xs; A.xs1 = h->xs + (h->n + 4); A.xs2 = h->xs + 2 * (h->n + 4); A.gq = h->gq; A.boxes = h->boxes; A.cell_box_first = h->d_box_first;
-  A.keyE = tile_keyE(h);
-  A.margin = tile_margin(h);
-  A.task_counter = (unsigned int *)(h->d_counters + 14);
-  A.frames = h->d_frames;
-  A.task_recs = D.task_recs;
-  A.ntask_dev = (const unsigned int *)(h->d_counters + 15);
-  {
-    static int hold = -1;
-    if (hold < 0) {
-      const char *e = getenv("SWIFTGPU_HOLD");
-      hold = e ? atoi(e) : (loop_kind() == 3 ? 0 : 2); /* tile: stages held before a drain; pipe: debug bits */
-    }
-    A.hold = hold;
-  }
-  A.dA = h->dA; A.dB = h->dB; A.g_vsig = h->g_vsig; A.g_lap = h->g_lap; A.g_amax = h->g_amax;
-  A.fo1 = h->fo1; A.f_hdt = h->f_hdt; A.f_vsig = h->f_vsig; A.f_minngb = h->f_minngb;
-  A.count = count;
-  A.wakeup = h->d_wakeup;
-  A.total = h->d_counters + counter;
-  A.tests = h->d_counters + 8 + counter;
-  for (int k = 0; k < 3; k++) A.dim[k] = h->cfg.dim[k];
-  A.a2_Hubble = h->step.a * h->step.a * h->step.H;
-  A.max_active_bin = h->step.max_active_bin;
-  return A;
-}
-
-/* sparse_out: fewer than SWIFTGPU_SPARSE targets per non-empty task on average */
-static int sparse_threshold() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SWIFTGPU_SPARSE");
-    v = e ? atoi(e) : 28;
-  }
-  return v;
-}
-static int build_targets(H *h, DevList &D, bool *sparse_out = nullptr) {
-  if (sparse_out) *sparse_out = false;
-  if (D.ngroups == 0) return 0;
-  CK(cudaMemsetAsync(h->d_counters + 12, 0, 2 * sizeof(unsigned long long), h->stream));
-  k_build_targets<<<(D.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(
-      D.groups, D.ngroups, h->d_cells, h->time_bin, h->step.max_active_bin, D.tgt_first, D.tgt_count,
-      D.tgt_list, D.items, h->depth_h, h->d_counters + 12);
-  h->stats.n_launches++;
-  CK(cudaGetLastError());
-  if (sparse_out && loop_kind() == 2) {
-    unsigned long long t[2] = {0, 0};
-    CK(cudaMemcpyAsync(t, h->d_counters + 12, sizeof(t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->stats.n_host_syncs++;
-    *sparse_out = t[1] > 0 && t[0] < (unsigned long long)sparse_threshold() * t[1];
-  }
-  return 0;
-}
-
-/* The compacted TaskRecs of one launch of the frame pipeline, from the target lists as they are NOW
- * (no host round trip: the kernel reads the number of tasks from device memory). */
-static int build_task_recs(H *h, const DevList &D, int chunk, const unsigned long long *gate = nullptr,
-                           unsigned long long gate_lo = 0, unsigned long long gate_hi = ~0ull,
-                           const unsigned long long *gate_den = nullptr) {
-  CK(cudaMemsetAsync(h->d_counters + 15, 0, sizeof(unsigned long long), h->stream));
-  if (D.ntasks == 0) return 0;
-  const int64_t n = h->n;
-  k_task_recs<<<(unsigned)(((int64_t)D.ntasks * 32 + 127) / 128), 128, 0, h->stream>>>(
-      D.task_group, D.task_chunk, D.ntasks, D.groups, h->d_cells, D.tgt_first, D.tgt_count, D.tgt_list, h->xs,
-      h->xs + (n + 4), h->xs + 2 * (n + 4), h->hh, D.task_recs, (unsigned int *)(h->d_counters + 15), gate, gate_lo,
-      gate_hi, chunk, gate_den);
-  h->stats.n_launches++;
-  CK(cudaGetLastError());
-  return 0;
-}
-
-static int read_counter(H *h, int k, int64_t *out) {
-  unsigned long long v = 0;
-  CK(cudaMemcpyAsync(&v, h->d_counters + k, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  *out = (int64_t)v;
-  return 0;
-}
-
-/* CTA-cooperative type-1 loops (loops_cta.cuh); SWIFTGPU_WARP_LOOPS=1 selects the
- * warp-private kernels of loops.cuh instead (kept for A/B measurements). */
-/* SWIFTGPU_LOOPS=pipe (default: frame pipeline, loops_pipe.cuh) | tile (loops_tile.cuh) | cta
- * (loops_cta.cuh) | warp (loops.cuh); the older kernels are kept for A/B measurements. */
-static int loop_kind() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SWIFTGPU_LOOPS");
-    const char *w = getenv("SWIFTGPU_WARP_LOOPS");
-    v = 3;
-#ifdef SWIFTGPU_LEGACY_LOOPS
-    if (e && !strcmp(e, "tile")) v = 2;
-    if (e && !strcmp(e, "cta")) v = 1;
-    if (e && !strcmp(e, "warp")) v = 0;
-    if (w && w[0] == '1') v = 0;
-#else
-    (void)e;
-    (void)w;
-#endif
-  }
-  return v;
-}
-static bool use_cta_loops() { return loop_kind() >= 1; }
-#ifdef SWIFTGPU_LEGACY_LOOPS
-#ifndef TL_FORCE_NS
-#define TL_FORCE_NS 4 /* ring stages of the force kernel (SPHENIX: one less, 4 payload columns) */
-#endif
-template <int LOOP, int SCHEME, int CW>
-static cudaError_t launch_tile_cw(H *h, const LoopArgs &A) {
-  constexpr bool FORCE = (LOOP == LOOP_FORCE);
-  constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  /* ring stages: as many as keep 3 (type-1) / 2 (force) standard CTAs, or 5 small CTAs, on an SM */
-  constexpr int NS = CW == 8 ? (FORCE ? (SCHEME == SCH_SPHENIX ? TL_FORCE_NS - 1 : TL_FORCE_NS) : (LOOP == LOOP_GRADIENT ? 3 : TL_DENS_NS)) : (FORCE ? 2 : TL_SPARSE_NS);
-  constexpr int bytes = TileSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1), CW>::kBytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_tile<LOOP, SCHEME, NS, CW>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  /* persistent CTAs: as many as are resident at once, tasks drawn from a counter */
-  static int resident = 0;
-  if (!resident) {
-    int per_sm = 0, sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile<LOOP, SCHEME, NS, CW>,
-                                                                  32 * (CW + 1), bytes);
-    if (e != cudaSuccess) return e;
-    resident = std::max(1, per_sm) * std::max(1, sms);
-  }
-  const long long ncta = (long long)A.ntasks * (TL_CWARPS / CW);
-  const int grid = (int)std::min<long long>(ncta, resident);
-  cudaError_t e = cudaMemsetAsync(A.task_counter, 0, sizeof(unsigned int), h->stream);
-  if (e != cudaSuccess) return e;
-  k_tile<LOOP, SCHEME, NS, CW><<<grid, 32 * (CW + 1), bytes, h->stream>>>(A);
-  return cudaGetLastError();
-}
-/* sparse: few targets per group (late ghost iterations): 4-consumer-warp CTAs, 5 per SM */
-template <int LOOP, int SCHEME>
-static cudaError_t launch_tile(H *h, const LoopArgs &A, bool sparse = false) {
-  if (sparse) return launch_tile_cw<LOOP, SCHEME, 4>(h, A);
-  return launch_tile_cw<LOOP, SCHEME, 8>(h, A);
-}
-#endif /* SWIFTGPU_LEGACY_LOOPS */
-
-/* sparse target sets (late ghost iterations): one warp per target, loops_direct.cuh */
-static int launch_direct_density(H *h, const DevList &D, const LoopArgs &A, const unsigned long long *gate = nullptr,
-                                 unsigned long long gate_hi = ~0ull) {
-  if (!h->d_flat_tgt) CK(cudaMalloc((void **)&h->d_flat_tgt, sizeof(int2) * (size_t)std::max<int64_t>(h->n, 1)));
-  unsigned int *nflat = (unsigned int *)(h->d_counters + 13);
-  CK(cudaMemsetAsync(nflat, 0, sizeof(unsigned long long), h->stream));
-  if (D.ngroups == 0) return 0;
-  k_flat_targets<<<(D.ngroups * 32 + 127) / 128, 128, 0, h->stream>>>(D.groups, D.ngroups, D.tgt_first, D.tgt_count,
-                                                                     D.tgt_list, h->d_flat_tgt, nflat, gate, gate_hi);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  k_direct<LOOP_DENSITY><<<sms * 8, 256, 0, h->stream>>>(A, h->d_flat_tgt, nflat);
-  h->stats.n_launches += 2;
-  CK(cudaGetLastError());
-  return 0;
-}
-
-/* frame pipeline (loops_pipe.cuh): DS = double-column slots per stage (64: only the self item of a
- * main loop is evaluated on doubles; 256: the ghost re-runs, where every pair item is) */
-template <int LOOP, int SCHEME, int NS, int DS, int CW = 8, int SL = PL_SLOTS>
-static cudaError_t launch_pipe_ns(H *h, const LoopArgs &A) {
-  constexpr bool FORCE = (LOOP == LOOP_FORCE);
-  constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  constexpr int bytes = PipeSmem<NP, NS, (FORCE ? TL_SUBCAP2 : TL_SUBCAP1), CW, DS, SL>::kBytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_pipe<LOOP, SCHEME, NS, CW, DS, SL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  static int resident = 0;
-  if (!resident) {
-    int per_sm = 0, sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipe<LOOP, SCHEME, NS, CW, DS, SL>,
-                                                                  32 * (CW + 1), bytes);
-    if (e != cudaSuccess) return e;
-    resident = std::max(1, per_sm) * std::max(1, sms);
-    if (getenv("SWIFTGPU_VERBOSE"))
-      fprintf(stderr, "k_pipe<%d,%d,NS=%d,CW=%d,DS=%d,SL=%d>: %d B smem, %d CTAs/SM\n", LOOP, SCHEME, NS, CW, DS, SL, bytes, per_sm);
-  }
-  const int grid = (int)std::min<long long>(A.ntasks, resident);
-  if (grid <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(A.task_counter, 0, sizeof(unsigned int), h->stream);
-  if (e != cudaSuccess) return e;
-  k_pipe<LOOP, SCHEME, NS, CW, DS, SL><<<grid, 32 * (CW + 1), bytes, h->stream>>>(A);
-  return cudaGetLastError();
-}
-#ifndef PL_NS_DENSITY
-/* ring depth = what fits 2 CTAs per SM: the consumer warps of a CTA need different stages (each
- * culls against its own 8 targets), so the fastest runs ahead of the slowest by up to the ring depth;
- * a deeper ring is what removes the full-barrier waits (ncu: 17-27 % of the samples at 4 stages) */
-#define PL_NS_DENSITY 7
-#define PL_NS_SUBSET 5
-#define PL_NS_GRADIENT 5
-#define PL_NS_FORCE 4
-/* SPHENIX force: 5 float4 per source, 256-slot stages fit 3 times only. 192-slot stages x 4 were
- * measured: -7 % before the direction-balanced item order, +-0 after it (sweeps in profiles/r02_sweeps.log) */
-#define PL_NS_FORCE_SPHENIX 3
-#define PL_SLOTS_FORCE_SPHENIX 256
-#endif
-#ifndef PL_NS_SPARSE
-/* the small-task variant (PL_SPARSE_CW consumer warps): 3-4 CTAs per SM */
-#define PL_NS_SPARSE 3
-#define PL_NS_SPARSE_FORCE 2
-#endif
-/* small = the variant with tasks of 8 * PL_SPARSE_CW targets: per task every consumer warp walks all
- * stages of the group's sources whatever the number of its targets, so a sparse target set (ghost
- * re-runs, few active particles) is served by fewer warps per task and more tasks in flight */
-template <int LOOP, bool SUBSET, int SCHEME>
-static cudaError_t launch_pipe(H *h, const LoopArgs &A, bool small = false) {
-  if (LOOP == LOOP_LIMITER)
-    return small ? launch_pipe_ns<LOOP_LIMITER, 0, PL_NS_SPARSE, 64, PL_SPARSE_CW>(h, A)
-                 : launch_pipe_ns<LOOP_LIMITER, 0, PL_NS_DENSITY, 64>(h, A);
-  if (small) {
-    if (LOOP == LOOP_FORCE) return launch_pipe_ns<LOOP_FORCE, SCHEME, PL_NS_SPARSE_FORCE, 64, PL_SPARSE_CW>(h, A);
-    if (LOOP == LOOP_GRADIENT) return launch_pipe_ns<LOOP_GRADIENT, 0, PL_NS_SPARSE, 64, PL_SPARSE_CW>(h, A);
-    if (SUBSET) return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SPARSE, 256, PL_SPARSE_CW>(h, A);
-    return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SPARSE, 64, PL_SPARSE_CW>(h, A);
-  }
-  if (LOOP == LOOP_FORCE && SCHEME == SCH_SPHENIX)
-    return launch_pipe_ns<LOOP_FORCE, SCHEME, PL_NS_FORCE_SPHENIX, 64, 8, PL_SLOTS_FORCE_SPHENIX>(h, A);
-  if (LOOP == LOOP_FORCE) return launch_pipe_ns<LOOP_FORCE, SCHEME, PL_NS_FORCE, 64>(h, A);
-  if (LOOP == LOOP_GRADIENT) return launch_pipe_ns<LOOP_GRADIENT, 0, PL_NS_GRADIENT, 64>(h, A);
-  if (SUBSET) return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_SUBSET, 256>(h, A);
-  return launch_pipe_ns<LOOP_DENSITY, 0, PL_NS_DENSITY, 64>(h, A);
-}
-/* Fraction of a list's potential targets below which the small-task variant takes the launch
- * (SWIFTGPU_SPARSE_FRAC, A/B knob; 0 = never, > 1 = always). The choice is made ON THE DEVICE: both
- * variants are enqueued, k_task_recs of the one whose gate is closed emits no task. */
-static double sparse_frac() {
-  static double v = -1.;
-  if (v < 0.) {
-    const char *e = getenv("SWIFTGPU_SPARSE_FRAC");
-    v = e ? atof(e) : 0.4;
-  }
-  return v;
-}
-
-/* One neighbour loop of the frame pipeline over the targets list D holds NOW. Both task sizes are
- * enqueued; which one finds tasks is decided on the device: `gate` (targets of the list, or
- * unconverged particles) in [lo, split) -> small tasks, [split, inf) -> 64-target tasks; below lo the
- * caller's direct kernel. With `den` the bounds are per 64-target chunk (the mean fill of the tasks). */
-template <int LOOP, bool SUBSET, int SCHEME>
-static int run_pipe_loop(H *h, DevList &D, int32_t *counts, int counter_slot, const unsigned long long *gate,
-                         unsigned long long lo, unsigned long long split, const unsigned long long *den) {
-  if (ensure_frames(h)) return 1;
-  if (split != ~0ull) {
-    if (build_task_recs(h, D, PL_TARGETS, gate, std::max(lo, split), ~0ull, den)) return 1;
-    LoopArgs A = loop_args(h, D, counts, counter_slot);
-    CK((launch_pipe<LOOP, SUBSET, SCHEME>(h, A, false)));
-    h->stats.n_launches++;
-  }
-  if (split > lo) {
-    if (build_task_recs(h, D, 8 * PL_SPARSE_CW, gate, lo, split, den)) return 1;
-    LoopArgs A = loop_args(h, D, counts, counter_slot);
-    CK((launch_pipe<LOOP, SUBSET, SCHEME>(h, A, true)));
-    h->stats.n_launches++;
-  }
-  return 0;
-}
-/* main loops: split on the mean number of targets per 64-target chunk of the list (k_build_targets' totals) */
-static unsigned long long main_split() {
-  const double f = sparse_frac();
-  if (f <= 0.) return 0ull;
-  if (f > 1.) return ~0ull;
-  return (unsigned long long)(f * TASK_TARGETS + 0.5);
-}
-
-#ifdef SWIFTGPU_LEGACY_LOOPS
-template <int LOOP, bool SUBSET, int SCHEME>
-static cudaError_t launch_cta(H *h, const LoopArgs &A) {
-  constexpr bool FORCE = (LOOP == LOOP_FORCE);
-  constexpr int NP = FORCE ? (SCHEME == SCH_SPHENIX ? 4 : 3) : (LOOP == LOOP_GRADIENT ? 2 : 1);
-  constexpr int bytes = CtaSmem<NP, SUBSET, FORCE>::kBytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_cta<LOOP, SUBSET, SCHEME>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  k_cta<LOOP, SUBSET, SCHEME><<<A.ntasks, CTA_THREADS, bytes, h->stream>>>(A);
-  return cudaGetLastError();
-}
-#endif
-template <int LOOP, bool SUBSET>
-static cudaError_t launch_loop1(H *h, const LoopArgs &A, bool sparse = false) {
-  if (loop_kind() == 3) return launch_pipe<LOOP, SUBSET, 0>(h, A);
-#ifdef SWIFTGPU_LEGACY_LOOPS
-  if (loop_kind() == 2) return launch_tile<LOOP, 0>(h, A, sparse);
-  if (use_cta_loops()) return launch_cta<LOOP, SUBSET, 0>(h, A);
-  k_loop1<LOOP, SUBSET><<<A.ntasks, 32, Tile1<LOOP, SUBSET>::kBytes, h->stream>>>(A);
-  return cudaGetLastError();
-#else
-  (void)sparse;
-  return cudaErrorNotSupported;
-#endif
-}
-template <int SCHEME>
-static cudaError_t launch_loop2(H *h, const LoopArgs &A, bool sparse = false) {
-  if (loop_kind() == 3) return launch_pipe<LOOP_FORCE, false, SCHEME>(h, A);
-#ifdef SWIFTGPU_LEGACY_LOOPS
-  if (loop_kind() == 2) return launch_tile<LOOP_FORCE, SCHEME>(h, A, sparse);
-  if (use_cta_loops()) return launch_cta<LOOP_FORCE, false, SCHEME>(h, A);
-  k_loop2<SCHEME><<<A.ntasks, 32, Tile2<SCHEME>::kBytes, h->stream>>>(A);
-  return cudaGetLastError();
-#else
-  (void)sparse;
-  return cudaErrorNotSupported;
-#endif
-}
+#include "launch_host.inl" /* loop_args, build_targets, build_task_recs, launch_pipe*, run_pipe_loop, launch_loop1/2 */
 
 extern "C" int swiftgpu_run_density(swiftgpu_t *h) {
   if (!h) return 1;
@@ -1759,192 +1095,7 @@ extern "C" int swiftgpu_download_cells(swiftgpu_t *h, swiftgpu_cell *cells, int3
   return 0;
 }
 
-/* ---- drift on the device (kernels_drift.cuh) ---- */
-extern "C" int swiftgpu_upload_xparts(swiftgpu_t *h, const swiftgpu_xpart_layout *layout, const void *xparts_aos,
-                                      int64_t nparts) {
-  if (!h || !layout || !xparts_aos || nparts <= 0) return 1;
-  cudaSetDevice(h->cfg.device);
-  const int64_t nh = h->n_host > 0 ? h->n_host : h->n;
-  if (nparts != nh) return h->fail("upload_xparts: one xpart per uploaded part (upload the parts first)");
-  if (layout->size <= 0 || layout->x_diff < 0 || layout->x_diff_sort < 0 || layout->v_full < 0 ||
-      layout->x_diff + 12 > layout->size || layout->x_diff_sort + 12 > layout->size ||
-      layout->v_full + 12 > layout->size)
-    return h->fail("upload_xparts: bad struct xpart layout");
-  if (layout->u_full >= 0 && layout->u_full + 4 > layout->size) return h->fail("upload_xparts: bad u_full offset");
-  if (h->n_x != nparts || h->xlayout.size != layout->size) {
-    cudaFree(h->d_xaos);
-    h->d_xaos = nullptr;
-    CK(cudaMalloc((void **)&h->d_xaos, (size_t)layout->size * (size_t)nparts));
-    h->n_x = nparts;
-  }
-  h->xlayout = *layout;
-  CK(cudaMemcpyAsync(h->d_xaos, xparts_aos, (size_t)layout->size * (size_t)nparts, cudaMemcpyHostToDevice,
-                     h->stream));
-  return 0;
-}
-
-extern "C" int swiftgpu_download_xparts(swiftgpu_t *h, void *xparts_aos, int64_t nparts) {
-  if (!h || !xparts_aos || nparts != h->n_x || !h->d_xaos) return 1;
-  cudaSetDevice(h->cfg.device);
-  CK(cudaMemcpyAsync(xparts_aos, h->d_xaos, (size_t)h->xlayout.size * (size_t)nparts, cudaMemcpyDeviceToHost,
-                     h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  h->stats.n_host_syncs++;
-  return 0;
-}
-
-extern "C" int swiftgpu_run_drift(swiftgpu_t *h, const swiftgpu_drift_args *args) {
-  if (!h || !args) return 1;
-  cudaSetDevice(h->cfg.device);
-  if (!h->d_xaos) return h->fail("run_drift before upload_xparts");
-  if (!(args->dt_drift >= 0.)) return h->fail("run_drift: attempt to drift to the past");
-  if (ensure_lists(h)) return 1; /* the device cell table */
-  if (transpose_out(h)) return 1; /* a_hydro, h_dt, u_dt ... of the last step into the AoS copy */
-  DriftArgs A;
-  A.aos = h->d_aos;
-  A.xaos = h->d_xaos;
-  A.D.L = h->cfg.layout;
-  A.D.scheme = h->cfg.scheme;
-  A.X = h->xlayout;
-  A.cells = h->d_cells;
-  A.ncells = h->ncells;
-  A.d2h = h->d_d2h;
-  A.dt_drift = args->dt_drift;
-  A.dt_kick_hydro = args->dt_kick_hydro;
-  A.dt_therm = args->dt_therm;
-  A.min_u = args->minimal_internal_energy; /* / cosmo->a_factor_internal_energy = 1 */
-  A.h_max = h->cfg.h_max;
-  A.h_min = h->cfg.h_min;
-  A.init_particles = args->init_particles;
-  A.max_active_bin = h->step.max_active_bin;
-  A.n_host = h->n_x;
-  const int nc = h->ncells;
-  k_drift_begin<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_cells, nc);
-  const unsigned grid = (unsigned)(((int64_t)nc * 32 + 127) / 128);
-  if (h->cfg.scheme == SCH_MINIMAL) k_drift<SCH_MINIMAL><<<grid, 128, 0, h->stream>>>(A);
-  else if (h->cfg.scheme == SCH_GADGET2) k_drift<SCH_GADGET2><<<grid, 128, 0, h->stream>>>(A);
-  else k_drift<SCH_SPHENIX><<<grid, 128, 0, h->stream>>>(A);
-  float *d_tmp = nullptr;
-  CK(cudaMalloc((void **)&d_tmp, 4 * sizeof(float) * (size_t)nc));
-  k_get_cell_drift<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_cells, nc, d_tmp, h->d_dxp);
-  /* the drifted cell table is the state every following step starts from (run_density restores it) */
-  CK(cudaMemcpyAsync(h->d_cells_init, h->d_cells, sizeof(DevCell) * (size_t)nc, cudaMemcpyDeviceToDevice, h->stream));
-  /* do the worklists survive? the density / subset lists were flattened with the predicates
-   * cell.h:951,992 on h_max_active (the force list is revalidated by run_force in every step) */
-  CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int32_t), h->stream));
-  k_pred_bits<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_cells, h->d_dmin, h->d_dxp_old, h->d_loop1_bits, nc, 1,
-                                                     h->d_flag);
-  h->stats.n_launches += 4;
-  std::vector<float> v(4 * (size_t)nc);
-  int32_t flag = 0;
-  cudaError_t e = cudaMemcpyAsync(v.data(), d_tmp, sizeof(float) * v.size(), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, h->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_tmp);
-  if (e != cudaSuccess) return h->fail(cudaGetErrorString(e));
-  h->stats.n_host_syncs++;
-  /* the host mirror of the cells follows: a later list rebuild flattens the recursion with it */
-  for (int c = 0; c < nc; c++) {
-    swiftgpu_cell &C = h->cells[c];
-    if (C.nodeID != h->cfg.rank && h->cfg.nranks > 1) continue;
-    if (C.count == 0) continue;
-    C.h_max = v[c];
-    C.h_max_active = v[(size_t)nc + c];
-    C.dx_max_part = v[2 * (size_t)nc + c];
-    C.dx_max_sort = v[3 * (size_t)nc + c];
-    h->up_hmax[c] = C.h_max;
-    h->up_hmax_active[c] = C.h_max_active;
-  }
-  if (flag) h->lists_built = false;
-  /* device order, SoA columns, frames: from the drifted AoS copy */
-  return transpose_in(h);
-}
-
-extern "C" int swiftgpu_run_kick(swiftgpu_t *h, int which, float minimal_internal_energy) {
-  if (!h || (which != 1 && which != 2)) return 1;
-  cudaSetDevice(h->cfg.device);
-  if (!h->d_xaos) return h->fail("run_kick before upload_xparts");
-  if (h->xlayout.u_full < 0) return h->fail("run_kick: the xpart layout has no u_full / entropy_full offset");
-  if (!h->has_step) return h->fail("swiftgpu_set_step must be called before run_kick");
-  if (transpose_out(h)) return 1; /* a_hydro, u_dt | entropy_dt of the last step into the AoS copy */
-  KickArgs A;
-  A.aos = h->d_aos;
-  A.xaos = h->d_xaos;
-  A.D.L = h->cfg.layout;
-  A.D.scheme = h->cfg.scheme;
-  A.X = h->xlayout;
-  A.n = h->n_x;
-  A.which = which;
-  A.max_active_bin = h->step.max_active_bin;
-  A.time_base = h->step.time_base;
-  A.min_u = minimal_internal_energy;
-  const unsigned grid = (unsigned)((A.n + 255) / 256);
-  if (h->cfg.scheme == SCH_MINIMAL) k_kick<SCH_MINIMAL><<<grid, 256, 0, h->stream>>>(A);
-  else if (h->cfg.scheme == SCH_GADGET2) k_kick<SCH_GADGET2><<<grid, 256, 0, h->stream>>>(A);
-  else k_kick<SCH_SPHENIX><<<grid, 256, 0, h->stream>>>(A);
-  h->stats.n_launches++;
-  CK(cudaGetLastError());
-  /* the SoA columns follow the AoS copy: v, u and the force members changed (kick2); positions did
-   * not move, so the device order, frames and lists stay */
-  if (which == 2) return transpose_in(h);
-  /* kick1 leaves struct part untouched except a zeroed rate at the energy floor; the results of the
-   * last step are already in the AoS copy, which is now the current state */
-  h->phases_done = 0;
-  return 0;
-}
-
-/* ---- the time-step limiter loop (runner_doiact_limiter.h) ---- */
-__global__ void k_limiter_io(char *aos, int part_size, int off, const int32_t *d2h, int64_t n, int64_t n_host,
-                             int32_t *wakeup, int store) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const int64_t row = d2h[p];
-  if (row >= n_host) {
-    if (!store) wakeup[p] = -56; /* time_bin_not_awake, timeline.h:48 */
-    return;
-  }
-  char *b = aos + (size_t)part_size * (size_t)row;
-  if (store)
-    *(int8_t *)(b + off) = (int8_t)wakeup[p];
-  else
-    wakeup[p] = *(const int8_t *)(b + off);
-}
-
-/* runner_dosub_{self,pair}1_limiter (runner_main.c:233,292 -> runner_doiact_functions_limiter.h): the
- * density decomposition (cell.h:951,992 on the h_max_active the ghost left), targets = the particles
- * starting their step, r2 < h_i^2 gamma^2, and runner_iact_nonsym_limiter: a neighbour more than
- * time_bin_neighbour_max_delta_bin bins above the target gets limiter_data.wakeup =
- * max(wakeup, -time_bin_i) - a scatter, done with atomicMax. wakeup_offset =
- * offsetof(struct part, limiter_data.wakeup); the time bins are those of the last upload. */
-extern "C" int swiftgpu_run_limiter(swiftgpu_t *h, int32_t wakeup_offset) {
-  if (!h) return 1;
-  cudaSetDevice(h->cfg.device);
-  if (wakeup_offset < 0 || wakeup_offset >= h->cfg.layout.size) return h->fail("run_limiter: bad wakeup offset");
-  if (h->cfg.nranks > 1) return h->fail("run_limiter: single rank only (woken-up proxies are not sent back)");
-  if (loop_kind() != 3) return h->fail("run_limiter needs the frame pipeline");
-  if (!(h->phases_done & SWIFTGPU_PHASE_GHOST)) return h->fail("run_limiter before run_ghost");
-  if (phase_begin(h)) return 1;
-  if (revalidate_list(h, LISTS_GRADIENT)) return 1; /* the loop-1 predicates on the post-ghost h_max_active */
-  DevList &L = h->gradient_own ? h->L_gradient : h->L_density;
-  if (build_targets(h, L)) return 1;
-  const int64_t n = h->n, nh = h->n_host > 0 ? h->n_host : h->n;
-  if (!h->d_wakeup) CK(cudaMalloc((void **)&h->d_wakeup, sizeof(int32_t) * (size_t)n));
-  const unsigned grid = (unsigned)((n + 255) / 256);
-  k_limiter_io<<<grid, 256, 0, h->stream>>>(h->d_aos, h->cfg.layout.size, wakeup_offset, h->d_d2h, n, nh,
-                                          h->d_wakeup, 0);
-  h->stats.n_launches++;
-  CK(cudaMemsetAsync(h->d_counters + 11, 0, sizeof(unsigned long long), h->stream));
-  if (L.ntasks > 0) {
-    /* counter slot 3: the loop credits no interaction (total untouched), its distance tests go to slot 11 */
-    if (run_pipe_loop<LOOP_LIMITER, false, 0>(h, L, nullptr, 3, h->d_counters + 12, 0, main_split(), h->d_counters + 13))
-      return 1;
-  }
-  k_limiter_io<<<grid, 256, 0, h->stream>>>(h->d_aos, h->cfg.layout.size, wakeup_offset, h->d_d2h, n, nh,
-                                          h->d_wakeup, 1);
-  h->stats.n_launches++;
-  CK(cudaGetLastError());
-  return 0;
-}
+#include "abi_time_integration.inl" /* drift, kick, limiter loop: swiftgpu_upload_xparts ... swiftgpu_run_limiter */
 
 extern "C" int swiftgpu_download_counts(swiftgpu_t *h, int32_t *n_density, int32_t *n_gradient,
                                         int32_t *n_force, int64_t nparts) {
@@ -2043,170 +1194,4 @@ extern "C" int swiftgpu_worklist_stats(const swiftgpu_config *cfg, const swiftgp
   return 0;
 }
 
-/* ======================================================================== */
-/* Multi-GPU halo exchange                                                   */
-/* ======================================================================== */
-extern "C" int swiftgpu_halo_plan(const swiftgpu_config *cfg, const swiftgpu_cell *cells,
-                                  int32_t ncells, const int32_t *top, int32_t ntop, int32_t peer,
-                                  int32_t *send_cells, int32_t *nsend_cells, int32_t *recv_cells,
-                                  int32_t *nrecv_cells, int64_t *nsend_parts, int64_t *nrecv_parts) {
-  if (!cfg || !cells || !top || ncells <= 0 || ntop <= 0) return 1;
-  std::map<int, HaloPlan> plans;
-  build_halo_plans(cells, top, ntop, cfg->dim, cfg->periodic, cfg->rank, plans);
-  HaloPlan P;
-  if (plans.count(peer)) P = plans[peer];
-  if (nsend_cells) *nsend_cells = (int32_t)P.send_cells.size();
-  if (nrecv_cells) *nrecv_cells = (int32_t)P.recv_cells.size();
-  if (nsend_parts) *nsend_parts = P.nsend;
-  if (nrecv_parts) *nrecv_parts = P.nrecv;
-  if (send_cells) std::copy(P.send_cells.begin(), P.send_cells.end(), send_cells);
-  if (recv_cells) std::copy(P.recv_cells.begin(), P.recv_cells.end(), recv_cells);
-  return 0;
-}
-
-extern "C" int swiftgpu_nccl_unique_id(void *id128) {
-  if (!id128) return 1;
-  NcclApi *N = nccl_api(g_err);
-  if (!N) return 2;
-  sg_ncclUniqueId id;
-  const int rc = N->GetUniqueId(&id);
-  if (rc != 0) {
-    g_err = std::string("ncclGetUniqueId: ") + N->GetErrorString(rc);
-    return 2;
-  }
-  memcpy(id128, &id, sizeof(id));
-  return 0;
-}
-
-/* The SoA columns each phase moves (see include/swiftgpu.h). */
-static HaloFields halo_fields(H *h, int phase) {
-  HaloFields F;
-  memset(&F, 0, sizeof(F));
-  auto add = [&](void *p, int esz) {
-    F.ptr[F.n] = p;
-    F.esz[F.n] = esz;
-    F.n++;
-  };
-  const bool sph = h->cfg.scheme == SCH_SPHENIX;
-  if (phase == 0) {
-    add(h->x, 24); add(h->mv, 16); add(h->hh, 4); add(h->u, 4); add(h->rho, 4);
-    add(h->time_bin, 1); add(h->depth_h, 1); add(h->fq1, 16); add(h->fq2, 16);
-    if (sph) { add(h->fq3, 16); add(h->alpha, 4); add(h->alpha_diff, 4); }
-  } else if (phase == 1) {
-    add(h->hh, 4); add(h->rho, 4); add(h->depth_h, 1); add(h->fq1, 16); add(h->fq2, 16);
-    if (sph) add(h->fq3, 16);
-  } else {
-    add(h->fq3, 16); add(h->alpha, 4); add(h->alpha_diff, 4);
-  }
-  return F;
-}
-
-extern "C" int swiftgpu_halo_setup(swiftgpu_t *h, const void *id128) {
-  if (!h || !id128) return 1;
-  if (h->cfg.nranks <= 1) return h->fail("halo_setup: nranks is 1");
-  if (h->cells.empty()) return h->fail("halo_setup: upload the cells first");
-  cudaSetDevice(h->cfg.device);
-  std::string e;
-  NcclApi *N = nccl_api(e);
-  if (!N) return h->fail("%s", e.c_str());
-  /* new cells: new send / receive lists; the communicator (one per handle, an NCCL id can be used
-   * once) is kept */
-  halo_release(h, /*keep_comm=*/true);
-  if (!h->comm) {
-    sg_ncclUniqueId id;
-    memcpy(&id, id128, sizeof(id));
-    int rc = N->CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank);
-    if (rc != 0) return h->fail("ncclCommInitRank: %s", N->GetErrorString(rc));
-  }
-
-  std::map<int, HaloPlan> plans;
-  build_halo_plans(h->cells.data(), h->top.data(), (int)h->top.size(), h->cfg.dim, h->cfg.periodic,
-                   h->cfg.rank, plans);
-  /* widest phase decides the slab size */
-  size_t per_part = 0;
-  for (int ph = 0; ph < 3; ph++) {
-    HaloFields F = halo_fields(h, ph);
-    size_t b = 0;
-    for (int f = 0; f < F.n; f++) b += F.esz[f];
-    per_part = std::max(per_part, b);
-  }
-  for (auto &kv : plans) {
-    HaloPeer P;
-    P.peer = kv.first;
-    P.nsend = kv.second.nsend;
-    P.nrecv = kv.second.nrecv;
-    std::vector<int32_t> si, ri;
-    si.reserve(P.nsend);
-    ri.reserve(P.nrecv);
-    /* DEVICE indices: a cell is the same contiguous range on the host and on the device, and its
-     * particles travel in the sender's device order (Morton order inside its leaves), which the
-     * receiver adopts for its proxy of the cell */
-    for (int32_t c : kv.second.send_cells)
-      for (int k = 0; k < h->cells[c].count; k++) si.push_back((int32_t)h->cells[c].first_part + k);
-    for (int32_t c : kv.second.recv_cells)
-      for (int k = 0; k < h->cells[c].count; k++) ri.push_back((int32_t)h->cells[c].first_part + k);
-    CK(to_device(&P.d_send_idx, si));
-    CK(to_device(&P.d_recv_idx, ri));
-    CK(cudaMalloc((void **)&P.d_sendbuf, per_part * std::max<int64_t>(P.nsend, 1) + 32 * HALO_MAX_FIELDS));
-    CK(cudaMalloc((void **)&P.d_recvbuf, per_part * std::max<int64_t>(P.nrecv, 1) + 32 * HALO_MAX_FIELDS));
-    h->halo.push_back(P);
-  }
-  h->halo_ready = true;
-  return 0;
-}
-
-extern "C" int swiftgpu_halo_exchange(swiftgpu_t *h, int phase) {
-  if (!h) return 1;
-  if (h->cfg.nranks <= 1) return 0;
-  if (!h->halo_ready) return h->fail("halo_exchange before halo_setup");
-  if (phase < 0 || phase > 2) return h->fail("halo_exchange: bad phase");
-  if (phase == 2 && h->cfg.scheme != SCH_SPHENIX) return 0;
-  if (!h->x) return h->fail("halo_exchange: no particles uploaded");
-  cudaSetDevice(h->cfg.device);
-  std::string e;
-  NcclApi *N = nccl_api(e);
-  if (!N) return h->fail("%s", e.c_str());
-  HaloFields F = halo_fields(h, phase);
-  int64_t bytes = 0;
-  for (HaloPeer &P : h->halo) {
-    if (P.nsend > 0) {
-      k_halo_pack<<<(unsigned)((P.nsend + 255) / 256), 256, 0, h->stream>>>(F, P.d_send_idx, nullptr, P.nsend,
-                                                                          P.d_sendbuf);
-      h->stats.n_launches++;
-    }
-  }
-  CK(cudaGetLastError());
-  int rc = N->GroupStart();
-  if (rc != 0) return h->fail("ncclGroupStart: %s", N->GetErrorString(rc));
-  for (HaloPeer &P : h->halo) {
-    const size_t sb = halo_field_offset(F, F.n, P.nsend), rb = halo_field_offset(F, F.n, P.nrecv);
-    if (P.nsend > 0) {
-      rc = N->Send(P.d_sendbuf, sb, /*ncclChar*/ 0, P.peer, h->comm, h->stream);
-      if (rc != 0) return h->fail("ncclSend: %s", N->GetErrorString(rc));
-      bytes += (int64_t)sb;
-    }
-    if (P.nrecv > 0) {
-      rc = N->Recv(P.d_recvbuf, rb, 0, P.peer, h->comm, h->stream);
-      if (rc != 0) return h->fail("ncclRecv: %s", N->GetErrorString(rc));
-    }
-  }
-  rc = N->GroupEnd();
-  if (rc != 0) return h->fail("ncclGroupEnd: %s", N->GetErrorString(rc));
-  for (HaloPeer &P : h->halo) {
-    if (P.nrecv > 0) {
-      k_halo_unpack<<<(unsigned)((P.nrecv + 255) / 256), 256, 0, h->stream>>>(F, P.d_recv_idx, nullptr, P.nrecv,
-                                                                            P.d_recvbuf);
-      h->stats.n_launches++;
-    }
-  }
-  if (phase == 1 && h->d_cells) {
-    /* foreign h changed: refresh the foreign cells' h_max like runner_do_recv_part */
-    k_foreign_hmax<<<(h->ncells * 32 + 127) / 128, 128, 0, h->stream>>>(
-        h->d_cells, h->ncells, h->hh, h->time_bin, h->step.max_active_bin);
-    h->stats.n_launches++;
-  }
-  CK(cudaGetLastError());
-  if (phase == 0) h->sorted = false; /* foreign x / h moved: tile records, octet boxes and key extrema are stale */
-  h->halo_bytes[phase] = bytes;
-  return 0;
-}
+#include "abi_halo.inl" /* swiftgpu_halo_plan, swiftgpu_nccl_unique_id, swiftgpu_halo_setup, swiftgpu_halo_exchange */
