@@ -365,6 +365,13 @@ int swiftgpu_worklist_stats(const swiftgpu_config *cfg, const swiftgpu_step *ste
                             const int32_t *top, int32_t ntop, int loop,
                             int64_t out[6]);
 
+/* Host-only: order-sensitive 64-bit digest of the flattened list of `loop`
+ * (every item and group in list order). */
+int swiftgpu_worklist_digest(const swiftgpu_config *cfg, const swiftgpu_step *step,
+                             const swiftgpu_cell *cells, int32_t ncells,
+                             const int32_t *top, int32_t ntop, int loop,
+                             uint64_t *digest);
+
 /*
  * Multi-GPU: one rank (process) per GPU, top-level cells assigned to ranks by
  * the reference's partition (cell.nodeID, src/partition.c:104-121). A rank

@@ -157,6 +157,7 @@ EXPORTS = [
     ("swiftgpu_get_stats", C.c_int, [VP, C.POINTER(Stats)]),
     ("swiftgpu_download_sort", C.c_int, [VP, I32, I32, VP, VP, VP]),
     ("swiftgpu_worklist_stats", C.c_int, [C.POINTER(Config), C.POINTER(Step), VP, I32, VP, I32, C.c_int, VP]),
+    ("swiftgpu_worklist_digest", C.c_int, [C.POINTER(Config), C.POINTER(Step), VP, I32, VP, I32, C.c_int, VP]),
     ("swiftgpu_nccl_unique_id", C.c_int, [VP]),
     ("swiftgpu_halo_setup", C.c_int, [VP, VP]),
     ("swiftgpu_halo_exchange", C.c_int, [VP, C.c_int]),

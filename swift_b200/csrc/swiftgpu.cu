@@ -1194,4 +1194,38 @@ extern "C" int swiftgpu_worklist_stats(const swiftgpu_config *cfg, const swiftgp
   return 0;
 }
 
+/* Host-only: an order-sensitive 64-bit digest (FNV-1a) of the flattened list of `loop` - every item
+ * and group in list order. The flattening runs on host threads; the digest is how the tests check
+ * that the list does not depend on their number. */
+extern "C" int swiftgpu_worklist_digest(const swiftgpu_config *cfg, const swiftgpu_step *step,
+                                        const swiftgpu_cell *cells, int32_t ncells, const int32_t *top,
+                                        int32_t ntop, int loop, uint64_t *digest) {
+  if (!cfg || !step || !cells || !top || !digest || ncells <= 0 || ntop <= 0) return 1;
+  Flattener F(cells, ncells, top, ntop, cfg->dim, cfg->periodic, cfg->rank, step->ti_current);
+  WorkList W;
+  if (loop == 3) {
+    std::vector<int32_t> aux;
+    F.build_subset(W, aux);
+  } else if (loop == 0 || loop == 1 || loop == 2) {
+    F.build_loop(loop, W);
+  } else {
+    return 1;
+  }
+  uint64_t hsh = 1469598103934665603ull;
+  auto mix = [&](const void *p, size_t n) {
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t k = 0; k < n; k++) {
+      hsh ^= b[k];
+      hsh *= 1099511628211ull;
+    }
+  };
+  for (const Item &it : W.items) {
+    mix(&it.tcell, 4); mix(&it.scell, 4); mix(&it.mode, 1); mix(&it.sid, 1);
+    mix(&it.min_depth, 1); mix(&it.max_depth, 1); mix(it.shift, 3); mix(&it.flags, 1);
+  }
+  for (const Group &g : W.groups) mix(&g, sizeof(g));
+  *digest = hsh;
+  return 0;
+}
+
 #include "abi_halo.inl" /* swiftgpu_halo_plan, swiftgpu_nccl_unique_id, swiftgpu_halo_setup, swiftgpu_halo_exchange */

@@ -134,3 +134,41 @@ def test_tree_invariants():
     # depth_h: h_min_allowed <= h < h_max_allowed at the assigned level (cell.h:1787)
     dh = host.field(c.parts, c.layout, "depth_h")
     assert (dh >= 0).all() and (dh <= cells["depth"].max()).all()
+
+
+_DIGEST_SCRIPT = """
+import sys, ctypes as C, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import util
+from swift_b200 import abi, host
+ic = host.clustered_box(32, abi.SCHEME_SPHENIX, seed=5, sigma=2.0)
+c = util.make_case("sphenix", ic, (4, 4, 4))
+lib = abi.load()
+cells = np.ascontiguousarray(c.tree.cells); top = np.ascontiguousarray(c.tree.top, np.int32)
+out = []
+for loop in (0, 2, 3):
+    d = C.c_uint64(0)
+    assert lib.swiftgpu_worklist_digest(C.byref(c.cfg), C.byref(c.step), cells.ctypes.data, len(cells),
+                                        top.ctypes.data, len(top), loop, C.byref(d)) == 0
+    out.append(d.value)
+print("DIGEST", *out)
+"""
+
+
+def test_worklists_do_not_depend_on_the_host_thread_count():
+    """The flattening of the reference's recursion runs on host threads over ranges of top-level
+    cells (worklist.hpp). The lists - every item and group, in order, hence also the order of the
+    device's sums - must be the same for 1, 3 and 8 threads (multi-level clustered tree, 64 top cells)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _DIGEST_SCRIPT.format(root=root, tests=os.path.join(root, "tests"))
+    seen = set()
+    for nt in ("1", "3", "8"):
+        e = dict(os.environ, SWIFTGPU_HOST_THREADS=nt)
+        r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+        seen.add(line)
+    assert len(seen) == 1, seen
