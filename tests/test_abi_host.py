@@ -172,3 +172,30 @@ def test_worklists_do_not_depend_on_the_host_thread_count():
         line = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
         seen.add(line)
     assert len(seen) == 1, seen
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): ONE JSON line
+    with the contract's keys, the reference's own CPU path timed on the host, nothing of the product."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from oracle import ref
+    if not ref.available("minimal"):
+        pytest.skip("needs oracle/_ref")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload",
+                        "uniform32", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["config"]["workload"] == "uniform32"
