@@ -760,7 +760,6 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
   G.a = h->step.a;
   int iter = 0;
   int64_t redo = 0;
-  int64_t extra_density = 0;
   const int max_iter = h->cfg.max_smoothing_iterations;
   if (D.ngroups > 0 && loop_kind() == 3) {
     /* The whole loop stays on the device: every iteration enqueues the ghost pass and BOTH re-run
@@ -853,7 +852,6 @@ extern "C" int swiftgpu_run_ghost(swiftgpu_t *h) {
   }
   h->stats.ghost_iterations = iter; /* (frame pipeline: replaced by the device's own count in sync_stats) */
   h->stats.ghost_unconverged = (int32_t)redo;
-  (void)extra_density;
   h->phases_done |= SWIFTGPU_PHASE_GHOST;
   if (phase_end(h, &h->stats.ms_ghost)) return 1;
   if (redo > 0)
