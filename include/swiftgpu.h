@@ -282,7 +282,11 @@ int swiftgpu_download_timestep(swiftgpu_t *h, float *dt_cfl, int64_t nparts);
  * forcing and particle removal at non-periodic borders are the host's). After
  * the call swiftgpu_download_parts / _xparts / _cells return the drifted state
  * and the next swiftgpu_run_step starts from it, without the particles
- * crossing the host boundary in between.
+ * crossing the host boundary in between. With several ranks only the rank's
+ * own cells are drifted (the reference drifts local cells only); the metadata
+ * of the proxy cells (h_max, dx_max_*) stays as uploaded until the caller
+ * refreshes it with swiftgpu_upload_cells, as it does after its own exchange
+ * of cell data (the parity tests of the drift are single-rank).
  */
 typedef struct swiftgpu_xpart_layout {
   int32_t size;        /* sizeof(struct xpart) */
