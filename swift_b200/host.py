@@ -6,6 +6,8 @@ for the tests and the benchmark only.
 """
 import ctypes as C
 import math
+import os
+
 import numpy as np
 
 from . import abi
@@ -252,31 +254,58 @@ def brick_box(L, scheme, grid=(1, 1, 1), rank=0, top=None, jitter=0.2, seed=42, 
             lo = r3[a] * (top // grid[a]) * per - per
             hi = (r3[a] + 1) * (top // grid[a]) * per + per
             axes.append(np.mod(np.arange(lo, hi, dtype=np.int64), L))
-    I, J, K = np.meshgrid(*axes, indexing="ij")
-    I, J, K = I.reshape(-1), J.reshape(-1), K.reshape(-1)
-    gidx = (I * L + J) * L + K
-    n = gidx.shape[0]
+    n0, n1, n2 = (len(ax) for ax in axes)
+    n = n0 * n1 * n2
     x = np.empty((n, 3), np.float64)
-    for a, ia in enumerate((I, J, K)):
-        x[:, a] = (ia + 0.5 + (2.0 * _hash_uniform(gidx, seed, a) - 1.0) * jitter) / L
-    del I, J, K
-    k = 2 * np.pi
     v = np.empty((n, 3), np.float32)
-    v[:, 0] = (np.sin(k * x[:, 1]) + 0.5 * np.cos(2 * k * x[:, 2])) * vamp
-    v[:, 1] = (np.sin(k * x[:, 2]) + 0.5 * np.cos(2 * k * x[:, 0])) * vamp
-    v[:, 2] = (np.sin(k * x[:, 0]) + 0.5 * np.cos(2 * k * x[:, 1])) * vamp
-    u = (u0 * (1.0 + 0.1 * np.sin(k * x[:, 0]) * np.cos(k * x[:, 1]))).astype(np.float32)
-    ic = {"x": x, "v": v, "mass": np.full(n, rho / L ** 3, np.float32),
-          "h": np.full(n, eta / L, np.float32), "u": u, "_rho0": rho}
+    u = np.empty(n, np.float32)
+    gidx = np.empty(n, np.int64)
     tb = None
+    thr = None
+    k = 2 * np.pi
     if active_fraction < 1.0:
         # active region clustered in space: where a smooth field exceeds the level that holds the
         # requested fraction of the volume (|sin sin sin| > t; the fraction is measured on this sample)
-        f = np.sin(k * x[:, 0]) * np.sin(k * x[:, 1]) * np.sin(k * x[:, 2])
         ref = np.sin(k * np.linspace(0, 1, 64, endpoint=False) + 0.01)
         fr = (ref[:, None, None] * ref[None, :, None] * ref[None, None, :]).reshape(-1)
         thr = np.quantile(fr, 1.0 - active_fraction)
-        tb = np.where(f >= thr, 1, 3)
+        tb = np.empty(n, np.int64)
+    JK_J = np.repeat(axes[1], n2)
+    JK_K = np.tile(axes[2], n1)
+
+    def fill(a, b):
+        # slabs [a, b) of the first axis: element-wise work only, so the chunking changes nothing
+        sl = slice(a * n1 * n2, b * n1 * n2)
+        I = np.repeat(axes[0][a:b], n1 * n2)
+        J = np.tile(JK_J, b - a)
+        K = np.tile(JK_K, b - a)
+        g = (I * L + J) * L + K
+        gidx[sl] = g
+        xs = x[sl]
+        for c, ia in enumerate((I, J, K)):
+            xs[:, c] = (ia + 0.5 + (2.0 * _hash_uniform(g, seed, c) - 1.0) * jitter) / L
+        vs = v[sl]
+        vs[:, 0] = (np.sin(k * xs[:, 1]) + 0.5 * np.cos(2 * k * xs[:, 2])) * vamp
+        vs[:, 1] = (np.sin(k * xs[:, 2]) + 0.5 * np.cos(2 * k * xs[:, 0])) * vamp
+        vs[:, 2] = (np.sin(k * xs[:, 0]) + 0.5 * np.cos(2 * k * xs[:, 1])) * vamp
+        u[sl] = (u0 * (1.0 + 0.1 * np.sin(k * xs[:, 0]) * np.cos(k * xs[:, 1]))).astype(np.float32)
+        if tb is not None:
+            f = np.sin(k * xs[:, 0]) * np.sin(k * xs[:, 1]) * np.sin(k * xs[:, 2])
+            tb[sl] = np.where(f >= thr, 1, 3)
+
+    # numpy releases the GIL inside these kernels: slabs of the first axis on a few host threads
+    nthreads = max(1, min(16, os.cpu_count() or 1, n0 // 4))
+    step = max(1, min(8, -(-n0 // nthreads)))
+    chunks = [(a, min(n0, a + step)) for a in range(0, n0, step)]
+    if nthreads == 1:
+        for a, b in chunks:
+            fill(a, b)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(nthreads) as ex:
+            list(ex.map(lambda ab: fill(*ab), chunks))
+    ic = {"x": x, "v": v, "mass": np.full(n, rho / L ** 3, np.float32),
+          "h": np.full(n, eta / L, np.float32), "u": u, "_rho0": rho}
     ic = _finish(ic, scheme, n, tb)
     ic["id"] = gidx + 1
     return ic
