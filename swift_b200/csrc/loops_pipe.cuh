@@ -1,18 +1,22 @@
 /*
  * loops_pipe.cuh - the neighbour loops (density, ghost re-runs, gradient,
- * force) as a TMA-fed producer/consumer pipeline over PRECOMPUTED FRAME FLOATS.
+ * force, time-step limiter) as a TMA-fed producer/consumer pipeline over
+ * PRECOMPUTED FRAME FLOATS.
  *
- * One persistent CTA = CW consumer warps (8 TARGET particles each: one Morton
- * octet of a leaf) + 1 producer warp; tasks (<= 8 CW targets of one target
- * cell) are drawn from a global counter and the ring of NS stages runs across
- * task boundaries. One __syncthreads() in the prologue, none after it.
+ * One persistent CTA = CW consumer warps (<= 8 TARGET particles each; a full
+ * task: one Morton octet of a leaf per warp) + 1 producer warp; tasks (<= 8 CW
+ * targets of one target cell, dealt evenly to the warps) are drawn from a
+ * global counter and the ring of NS stages runs across task boundaries. CW = 8
+ * (64-target tasks) or, for sparse target sets, 4 (32-target tasks, more CTAs
+ * per SM); which of the two finds tasks is decided on the device (k_task_recs).
+ * One __syncthreads() in the prologue, none after it.
  *
  * What the reference evaluates for a pair is decided in the float frame of the
  * leaf-level call, functions_hydro.h:1327-1347:
  *     pix = (float)(pi->x - (cj->loc + shift)),  pjx = (float)(pj->x - cj->loc),
  *     dx = pix - pjx,  r2 = dx*dx + dy*dy + dz*dz (un-fused),  r2 < hig2
  * Both frame floats depend on ONE particle and ONE (cell, origin) combination
- * only, so they are computed once per step by k_frames (swiftgpu.cu) into
+ * only, so they are computed once per step by k_frames (kernels_records.cuh) into
  * per-(cell, origin) arrays of float4 - 14 per leaf of a uniform tree: the
  * cell's own frame plus the 13 directions in which it is the left cell `ci` -
  * and the loops stage exactly the array an item needs with one bulk TMA copy.
@@ -50,7 +54,7 @@
  *
  * The sorted-axis conditions of DOPAIR1/DOPAIR2 (:1296-1332, :1420-1448,
  * :1652-1735, :1806-2238) are geometrically implied by the distance condition
- * up to the rounding of the float sort keys; exact_type1/2 (loops_tile.cuh)
+ * up to the rounding of the float sort keys; exact_type1/2 (loops_common.cuh)
  * evaluate them for hits within keyE of the cut-off only.
  */
 #ifndef SWIFTGPU_LOOPS_PIPE_CUH
