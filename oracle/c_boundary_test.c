@@ -35,6 +35,10 @@ swiftref_t *swiftref_create(const swiftgpu_config *cfg, const swiftgpu_step *ste
                             int ncells, const int *top, int ntop, const void *parts_aos, long long nparts);
 int swiftref_run(swiftref_t *s, unsigned mask, int nthreads, double *seconds);
 int swiftref_get_parts(swiftref_t *s, void *parts_aos);
+int swiftref_set_xparts(swiftref_t *s, const void *xparts_aos);
+int swiftref_get_xparts(swiftref_t *s, void *xparts_aos);
+int swiftref_run_kick(swiftref_t *s, int which, float minimal_internal_energy);
+int swiftref_run_drift(swiftref_t *s, long long ti_old, float minimal_internal_energy, int init_particles);
 void swiftref_destroy(swiftref_t *s);
 
 /* swift_b200/csrc/host_tree.cpp (libswiftgpu_host.so): stands in for space_regrid / space_split */
@@ -195,7 +199,6 @@ int main(int argc, char **argv) {
   }
   swiftref_run(R, SWIFTGPU_PHASE_ALL, 2, NULL);
   swiftref_get_parts(R, ref_parts);
-  swiftref_destroy(R);
 
   /* ---- (a) libswiftgpu through its C ABI, on the same array ---- */
   const int rc = swiftgpu_init(&g, &cfg);
@@ -210,7 +213,82 @@ int main(int argc, char **argv) {
   CHECK(swiftgpu_download_parts(g, parts, n));
   swiftgpu_stats st;
   CHECK(swiftgpu_get_stats(g, &st));
+
+  /* ---- (c) time integration through the same boundary: kick2, kick1 and the
+   * drift of the reference (runner_do_kick2/1, cell_drift_part) against swiftgpu_run_kick / _drift,
+   * both starting from the reference's post-step particles and the same struct xpart[] - laid out by
+   * offsetof() on the reference's own type. Integer-exact members are compared with memcmp. ---- */
+  struct xpart *xp = NULL, *ref_xp = NULL;
+  struct part *kd_parts = NULL, *ref_kd = NULL;
+  if (posix_memalign((void **)&xp, xpart_align, sizeof(struct xpart) * n) != 0) return 2;
+  if (posix_memalign((void **)&ref_xp, xpart_align, sizeof(struct xpart) * n) != 0) return 2;
+  if (posix_memalign((void **)&kd_parts, part_align, sizeof(struct part) * n) != 0) return 2;
+  if (posix_memalign((void **)&ref_kd, part_align, sizeof(struct part) * n) != 0) return 2;
+  memset(xp, 0, sizeof(struct xpart) * n);
+  for (long long k = 0; k < n; k++) {
+    for (int d = 0; d < 3; d++) {
+      xp[k].v_full[d] = ref_parts[k].v[d];
+      xp[k].x_diff[d] = 1e-4f * (float)(k % 7 - 3);
+      xp[k].x_diff_sort[d] = -1e-4f * (float)(k % 5 - 2);
+    }
+#if defined(GADGET2_SPH)
+    xp[k].entropy_full = ref_parts[k].entropy;
+#else
+    xp[k].u_full = ref_parts[k].u;
+#endif
+  }
+  const long long ti_span = 4; /* time bin 1: the whole step of every particle */
+  swiftgpu_step kstep = step;
+  kstep.time_base = 2.5e-4; /* dt = 1e-3 */
+  swiftref_destroy(R);
+  R = swiftref_create(&cfg, &kstep, cells, ncells, top, ntop, ref_parts, n);
+  if (!R) return 1;
+  swiftref_set_xparts(R, xp);
+  swiftref_run_kick(R, 2, 0.f);
+  swiftref_run_kick(R, 1, 0.f);
+  swiftref_run_drift(R, kstep.ti_current - ti_span, 0.f, 1);
+  swiftref_get_parts(R, ref_kd);
+  swiftref_get_xparts(R, ref_xp);
+  swiftref_destroy(R);
+
+  swiftgpu_xpart_layout X;
+  X.size = (int32_t)sizeof(struct xpart);
+  X.x_diff = (int32_t)offsetof(struct xpart, x_diff);
+  X.x_diff_sort = (int32_t)offsetof(struct xpart, x_diff_sort);
+  X.v_full = (int32_t)offsetof(struct xpart, v_full);
+#if defined(GADGET2_SPH)
+  X.u_full = (int32_t)offsetof(struct xpart, entropy_full);
+#else
+  X.u_full = (int32_t)offsetof(struct xpart, u_full);
+#endif
+  CHECK(swiftgpu_upload_parts(g, ref_parts, n));
+  CHECK(swiftgpu_set_step(g, &kstep));
+  CHECK(swiftgpu_upload_xparts(g, &X, xp, n));
+  CHECK(swiftgpu_run_kick(g, 2, 0.f));
+  CHECK(swiftgpu_run_kick(g, 1, 0.f));
+  swiftgpu_drift_args da_;
+  da_.dt_drift = da_.dt_kick_hydro = da_.dt_therm = (double)ti_span * kstep.time_base;
+  da_.minimal_internal_energy = 0.f;
+  da_.init_particles = 1;
+  CHECK(swiftgpu_run_drift(g, &da_));
+  CHECK(swiftgpu_download_parts(g, kd_parts, n));
+  CHECK(swiftgpu_download_xparts(g, xp, n));
   swiftgpu_destroy(g);
+  long long bad_x = 0, bad_v = 0, bad_xp = 0, bad_h = 0;
+  double moved = 0;
+  for (long long k = 0; k < n; k++) {
+    if (memcmp(kd_parts[k].x, ref_kd[k].x, sizeof(kd_parts[k].x)) != 0) bad_x++;
+    if (memcmp(kd_parts[k].v, ref_kd[k].v, sizeof(kd_parts[k].v)) != 0) bad_v++;
+    if (memcmp(&kd_parts[k].h, &ref_kd[k].h, sizeof(float)) != 0) bad_h++;
+    if (memcmp(xp[k].v_full, ref_xp[k].v_full, sizeof(xp[k].v_full)) != 0 ||
+        memcmp(xp[k].x_diff, ref_xp[k].x_diff, sizeof(xp[k].x_diff)) != 0 ||
+        memcmp(xp[k].x_diff_sort, ref_xp[k].x_diff_sort, sizeof(xp[k].x_diff_sort)) != 0)
+      bad_xp++;
+    moved = fmax(moved, fabs(ref_kd[k].x[0] - ref_parts[k].x[0]));
+  }
+  printf("c_boundary_test kick2 + kick1 + drift: moved %.3e, mismatching x %lld, v %lld, h %lld, xpart %lld of %lld\n",
+         moved, bad_x, bad_v, bad_h, bad_xp, n);
+  const int ok_ti = moved > 0 && bad_x == 0 && bad_v == 0 && bad_h == 0 && bad_xp == 0;
 
   /* ---- compare through the struct members ---- */
   double e_h = 0, e_rho = 0, e_a = 0, e_u = 0;
@@ -248,7 +326,7 @@ int main(int argc, char **argv) {
          e_h, e_rho, e_a, e_u, flips, bad_bin);
   /* flipped particles' neighbours see a 1e-4 different h: bars a decade above the clean-particle bar */
   const int ok = e_h < 1e-5 && e_rho < 1e-4 && e_a < 1e-3 && bad_bin == 0 && flips <= 3 + n / 2000 &&
-                 st.n_density > 0 && st.n_force > 0;
+                 st.n_density > 0 && st.n_force > 0 && ok_ti;
   printf(ok ? "C_BOUNDARY PASS\n" : "C_BOUNDARY FAIL\n");
   return ok ? 0 : 1;
 }
